@@ -1,0 +1,235 @@
+/*
+ * ovc_b200.h — C ABI of the B200-native batched Overcooked MDP step engine.
+ *
+ * The reference (HumanCompatibleAI/overcooked_ai) is pure Python and has no FFI layer; the
+ * boundary this library replaces is the Python call surface
+ *
+ *   OvercookedGridworld.get_state_transition   src/overcooked_ai_py/mdp/overcooked_mdp.py:1375-1430
+ *   OvercookedEnv.step / reset / is_done       src/overcooked_ai_py/mdp/overcooked_env.py:244-325
+ *   OvercookedGridworld.lossless_state_encoding  overcooked_mdp.py:2385-2561
+ *   OvercookedGridworld.featurize_state          overcooked_mdp.py:2579-2898
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes, allocates nothing that
+ * outlives the call and never throws.  All `state`, `actions`, output and table pointers are
+ * DEVICE pointers owned by the caller (torch owns every buffer); `stream` is a cudaStream_t
+ * passed as void*.  Return value: 0 on success, a negative OVC_E_* code otherwise, with a
+ * human-readable message available from ovc_last_error().  Launches are asynchronous: device
+ * faults surface at the caller's next synchronisation.
+ *
+ * ---------------------------------------------------------------------------------------------
+ * Packed environment record (int32 words, `state_words` S in {16, 32, 64, 128} per record,
+ * records contiguous: state[env * S + word]).
+ *
+ *   word 0        timestep                                   (OvercookedState.timestep, :814)
+ *   word 1, 2     player 0 / player 1                        (PlayerState, :696-781)
+ *                   bits 0-3  x      bits 4-7  y             (bits 0-7 = "pos byte" y<<4|x)
+ *                   bits 8-9  orientation index  0 N, 1 S, 2 E, 3 W   (actions.py:12-17)
+ *                   bits 10-31 held object, 22-bit object code (0 = empty hands)
+ *   word 3        bits 0-7   layout id (index into the layout table)
+ *                 bits 8-15  number of loose dishes on counters (derived cache, kept by every
+ *                            kernel; pack() computes it)
+ *                 bits 16-31 reserved, zero
+ *   word 4+k      object on object-capable cell k, 22-bit object code (0 = empty).
+ *                 Cells are ordered: the layout's pots (terrain row-major order, = the order of
+ *                 get_pot_locations(), :1799) first, then its counters 'X' (row-major).
+ *   remaining     zero padding up to S
+ *
+ * 22-bit object code (ObjectState :384-430, SoupState :433-693)
+ *   bits 0-2   type: 0 none, 1 onion, 2 tomato, 3 dish, 4 soup
+ *   bits 3-4   soup: number of ingredients (0..3)
+ *   bits 5-7   soup: ingredient kinds in insertion order, bit (5+i) = 1 if slot i is a tomato
+ *              (ordered, because SoupState.__eq__ :458-472 is order sensitive)
+ *   bits 8-21  soup: _cooking_tick + 1   (0 = idle, i.e. _cooking_tick == -1)
+ * ---------------------------------------------------------------------------------------------
+ */
+#ifndef OVC_B200_H
+#define OVC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OVC_ABI_VERSION 1
+
+/* ---- action indices: Action.INDEX_TO_ACTION, actions.py:47-57 ---- */
+#define OVC_A_NORTH 0
+#define OVC_A_SOUTH 1
+#define OVC_A_EAST 2
+#define OVC_A_WEST 3
+#define OVC_A_STAY 4
+#define OVC_A_INTERACT 5
+#define OVC_NUM_ACTIONS 6
+
+/* ---- terrain codes (low 3 bits of ovc_layout_t.cell[]) ---- */
+#define OVC_T_FLOOR 0   /* ' ' */
+#define OVC_T_COUNTER 1 /* 'X' */
+#define OVC_T_ONION 2   /* 'O' */
+#define OVC_T_TOMATO 3  /* 'T' */
+#define OVC_T_DISH 4    /* 'D' */
+#define OVC_T_POT 5     /* 'P' */
+#define OVC_T_SERVE 6   /* 'S' */
+#define OVC_T_OUTSIDE 7 /* not part of the grid */
+
+/* ---- object codes ---- */
+#define OVC_O_NONE 0
+#define OVC_O_ONION 1
+#define OVC_O_TOMATO 2
+#define OVC_O_DISH 3
+#define OVC_O_SOUP 4
+
+#define OVC_OBJ_BITS 22
+#define OVC_OBJ_MASK 0x3FFFFF
+#define OVC_MAX_TICK 16382 /* tick+1 must fit 14 bits */
+
+/* ---- event bits: index = position in EVENT_TYPES, overcooked_mdp.py:1027-1058 ---- */
+#define OVC_EV_TOMATO_PICKUP 0
+#define OVC_EV_USEFUL_TOMATO_PICKUP 1
+#define OVC_EV_TOMATO_DROP 2
+#define OVC_EV_USEFUL_TOMATO_DROP 3
+#define OVC_EV_POTTING_TOMATO 4
+#define OVC_EV_ONION_PICKUP 5
+#define OVC_EV_USEFUL_ONION_PICKUP 6
+#define OVC_EV_ONION_DROP 7
+#define OVC_EV_USEFUL_ONION_DROP 8
+#define OVC_EV_POTTING_ONION 9
+#define OVC_EV_DISH_PICKUP 10
+#define OVC_EV_USEFUL_DISH_PICKUP 11
+#define OVC_EV_DISH_DROP 12
+#define OVC_EV_USEFUL_DISH_DROP 13
+#define OVC_EV_SOUP_PICKUP 14
+#define OVC_EV_SOUP_DELIVERY 15
+#define OVC_EV_SOUP_DROP 16
+#define OVC_EV_OPTIMAL_ONION_POTTING 17
+#define OVC_EV_OPTIMAL_TOMATO_POTTING 18
+#define OVC_EV_VIABLE_ONION_POTTING 19
+#define OVC_EV_VIABLE_TOMATO_POTTING 20
+#define OVC_EV_CATASTROPHIC_ONION_POTTING 21
+#define OVC_EV_CATASTROPHIC_TOMATO_POTTING 22
+#define OVC_EV_USELESS_ONION_POTTING 23
+#define OVC_EV_USELESS_TOMATO_POTTING 24
+#define OVC_NUM_EVENTS 25
+/* events[env][agent] bits 25-28: recipe index (n_onion*4+n_tomato) of the soup this agent
+ * delivered in this transition (0 if none) — lets the host attribute sparse reward per agent.
+ * bit 30: OVC_EVF_STEPPED_DONE, the env was already done (timestep >= horizon) and was left
+ * untouched (the reference raises AssertionError there, overcooked_env.py:255). */
+#define OVC_EV_RECIPE_SHIFT 25
+#define OVC_EVF_STEPPED_DONE (1 << 30)
+
+/* ---- layout constant table: one record per layout, device resident, read only ---- */
+#define OVC_LAYOUT_OLD_DYNAMICS 1 /* flags bit 0, overcooked_mdp.py:1121-1127,1515-1522,1696-1701 */
+#define OVC_MAX_POTS 4
+#define OVC_MAX_SLOTS 124
+#define OVC_NO_SLOT 0xFF
+
+typedef struct ovc_layout {
+    int32_t width, height;
+    int32_t n_pots;  /* <= OVC_MAX_POTS */
+    int32_t n_slots; /* pots + counters, <= OVC_MAX_SLOTS */
+    int32_t flags;
+    int32_t rew_placement_in_pot; /* reward_shaping_params, overcooked_mdp.py:1018-1025,1136-1140 */
+    int32_t rew_dish_pickup;
+    int32_t rew_soup_pickup;
+    int32_t state_words; /* smallest supported S that holds this layout */
+    int32_t reserved[7];
+    /* recipe tables, index r = n_onion*4 + n_tomato (r == 0: empty pot) */
+    int32_t cook_time[16];     /* Recipe.time, :163-188 */
+    int32_t deliver_value[16]; /* get_recipe_value, :1581-1602 (bonus and all_orders applied) */
+    int32_t best_value[16];    /* value of get_optimal_possible_recipe, :1976-2061 */
+    /* cell[y<<4|x]: bits 0-2 terrain code, bits 8-15 object slot (OVC_NO_SLOT if none) */
+    uint16_t cell[256];
+    uint8_t slot_pos[128]; /* slot -> pos byte */
+} ovc_layout_t;
+
+/* ---- per-(layout, cell, orientation) lookup for featurize_state; see ovc_featurize ---- */
+typedef struct ovc_feat_lut_entry {
+    int8_t d_onion[2]; /* (dx,dy) to the closest onion dispenser by planner cost, (0,0) if none */
+    int8_t d_tomato[2];
+    int8_t d_dish[2];
+    int8_t d_serve[2];
+    uint8_t pot_order[OVC_MAX_POTS]; /* pot slots by increasing planner cost; 0xFF = unreachable */
+} ovc_feat_lut_entry_t;              /* 12 bytes; table is [n_layouts][256][4] */
+
+/* ---- error codes ---- */
+#define OVC_OK 0
+#define OVC_E_BADARG (-1)
+#define OVC_E_CUDA (-2)
+#define OVC_E_UNSUPPORTED (-3)
+
+/* flags for ovc_step / ovc_rollout */
+#define OVC_F_AUTO_RESET 1 /* an env whose new timestep reaches horizon is set back to its start record */
+/* bits 8-11 select the record I/O strategy of the step kernel (0 = library default):
+ *   1 = 2-D tensor-map TMA tile with hardware swizzle, 2 = 1-D bulk TMA (linear tile),
+ *   3 = direct vectorised global loads/stores (no staging).  All produce identical results. */
+#define OVC_F_IO_SHIFT 8
+#define OVC_F_IO_MASK (0xF << OVC_F_IO_SHIFT)
+
+/* element type of ovc_encode_lossless output */
+#define OVC_DT_F32 0
+#define OVC_DT_U8 1
+#define OVC_DT_I32 2
+
+int ovc_abi_version(void);
+size_t ovc_layout_table_size(void); /* sizeof(ovc_layout_t): the host packer checks it */
+size_t ovc_feat_lut_entry_size(void);
+const char *ovc_last_error(void);
+
+/*
+ * One joint transition of n_envs environments (replaces OvercookedGridworld.get_state_transition
+ * :1375-1430 + the reward/done part of OvercookedEnv.step, overcooked_env.py:244-274).
+ *   layouts        ovc_layout_t[n_layouts]
+ *   start_records  int32[n_layouts][S], the packed standard start state per layout (auto reset)
+ *   state          int32[n_envs][S], updated in place
+ *   actions        int32[n_envs][2], values 0..5
+ *   sparse         int32[n_envs]      sum over both agents of the delivery reward (env.step's r)
+ *   shaped         int32[n_envs][2]   shaped_reward_by_agent
+ *   done           int32[n_envs]      1 iff new timestep >= horizon
+ *   events         int32[n_envs][2]   event bit mask per agent (+ recipe / flag bits above)
+ */
+int ovc_step(const void *layouts, int n_layouts, const int32_t *start_records, int32_t *state,
+             const int32_t *actions, int32_t *sparse, int32_t *shaped, int32_t *done,
+             int32_t *events, int64_t n_envs, int state_words, int horizon, int flags,
+             void *stream);
+
+/*
+ * T consecutive transitions in ONE launch (the record stays on chip between transitions).
+ * actions int32[T][n_envs][2]; sparse/done int32[T][n_envs]; shaped/events int32[T][n_envs][2].
+ * Semantically identical to T calls of ovc_step with the same flags.
+ */
+int ovc_rollout(const void *layouts, int n_layouts, const int32_t *start_records, int32_t *state,
+                const int32_t *actions, int32_t *sparse, int32_t *shaped, int32_t *done,
+                int32_t *events, int64_t n_envs, int n_steps, int state_words, int horizon,
+                int flags, void *stream);
+
+/*
+ * OvercookedEnv.reset (overcooked_env.py:288-319) for the envs whose mask[i] != 0 (all if mask
+ * is NULL): state[i] = start_records[layout]; layout = env_layout[i] if env_layout != NULL, else
+ * the id already stored in the record.
+ */
+int ovc_reset(const int32_t *start_records, int n_layouts, int32_t *state,
+              const int32_t *env_layout, const int32_t *mask, int64_t n_envs, int state_words,
+              void *stream);
+
+/*
+ * lossless_state_encoding (:2385-2561) for envs [0, n_envs) that all share one layout shape:
+ * out[env][player][x][y][26] with element type `dtype` (OVC_DT_*).  `width`/`height` must equal
+ * the layouts' own (all envs in the range must have equal-shape layouts).
+ */
+int ovc_encode_lossless(const void *layouts, int n_layouts, const int32_t *state, void *out,
+                        int dtype, int64_t n_envs, int state_words, int width, int height,
+                        int horizon, void *stream);
+
+/*
+ * featurize_state (:2579-2898) with the default planner parameters (NO_COUNTERS_PARAMS,
+ * planners.py:27-34): out float32[n_envs][2][2*(28+10*num_pots)+4]... = [n_envs][2][F],
+ * F = 2*(num_pots*10+28), lut = ovc_feat_lut_entry_t[n_layouts][256][4].
+ */
+int ovc_featurize(const void *layouts, int n_layouts, const void *lut, const int32_t *state,
+                  float *out, int64_t n_envs, int state_words, int num_pots, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OVC_B200_H */

@@ -1,0 +1,112 @@
+"""ctypes binding of oracle/libovc_oracle.so — TEST INFRASTRUCTURE ONLY.
+
+Imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs;
+never by the product package.  All arrays are host numpy arrays.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libovc_oracle.so")
+    src = os.path.join(_HERE, "ovc_oracle.c")
+    hdr = os.path.join(_HERE, "..", "include", "ovc_b200.h")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(
+            ["gcc", "-O2", "-fPIC", "-pthread", "-std=c11", "-shared", "-o", so, src], cwd=_HERE
+        )
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "libovc_oracle.so")
+        if not os.path.exists(so):
+            build()
+        _LIB = ctypes.CDLL(so)
+        _LIB.ovo_layout_table_size.restype = ctypes.c_size_t
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _i32(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a
+
+
+def step(tables, starts, state, actions, horizon=400, flags=0, n_threads=1):
+    """One transition in place on ``state`` [N,S] int32.  Returns sparse[N], shaped[N,2], done[N], events[N,2]."""
+    assert state.dtype == np.int32 and state.flags.c_contiguous
+    n, S = state.shape
+    actions = _i32(actions)
+    sparse = np.zeros(n, np.int32)
+    shaped = np.zeros((n, 2), np.int32)
+    done = np.zeros(n, np.int32)
+    events = np.zeros((n, 2), np.int32)
+    tables = np.ascontiguousarray(tables)
+    starts = _i32(starts)
+    rc = lib().ovo_step(_p(tables), ctypes.c_int(len(tables)), _p(starts), _p(state), _p(actions), _p(sparse),
+                        _p(shaped), _p(done), _p(events), ctypes.c_int64(n), ctypes.c_int(S), ctypes.c_int(horizon),
+                        ctypes.c_int(flags), ctypes.c_int(n_threads))
+    assert rc == 0
+    return sparse, shaped, done, events
+
+
+def rollout(tables, starts, state, actions, horizon=400, flags=0, n_threads=0):
+    """T transitions in place; actions [T,N,2].  Returns sparse[T,N], shaped[T,N,2], done[T,N], events[T,N,2]."""
+    assert state.dtype == np.int32 and state.flags.c_contiguous
+    n, S = state.shape
+    actions = _i32(actions)
+    T = actions.shape[0]
+    assert actions.shape == (T, n, 2)
+    sparse = np.zeros((T, n), np.int32)
+    shaped = np.zeros((T, n, 2), np.int32)
+    done = np.zeros((T, n), np.int32)
+    events = np.zeros((T, n, 2), np.int32)
+    tables = np.ascontiguousarray(tables)
+    starts = _i32(starts)
+    rc = lib().ovo_rollout(_p(tables), ctypes.c_int(len(tables)), _p(starts), _p(state), _p(actions), _p(sparse),
+                           _p(shaped), _p(done), _p(events), ctypes.c_int64(n), ctypes.c_int(T), ctypes.c_int(S),
+                           ctypes.c_int(horizon), ctypes.c_int(flags), ctypes.c_int(n_threads))
+    assert rc == 0
+    return sparse, shaped, done, events
+
+
+def max_threads():
+    return int(lib().ovo_max_threads())
+
+
+def encode_lossless(tables, state, width, height, horizon=400):
+    """int32 [N,2,W,H,26]"""
+    state = _i32(state)
+    n, S = state.shape
+    out = np.zeros((n, 2, width, height, 26), np.int32)
+    tables = np.ascontiguousarray(tables)
+    rc = lib().ovo_encode_lossless(_p(tables), ctypes.c_int(len(tables)), _p(state), _p(out), ctypes.c_int64(n),
+                                   ctypes.c_int(S), ctypes.c_int(width), ctypes.c_int(height), ctypes.c_int(horizon))
+    assert rc == 0, "layout shape mismatch"
+    return out
+
+
+def featurize(tables, lut, state, num_pots=2):
+    """float64 [N,2,F], F = 2*(10*num_pots+28)"""
+    state = _i32(state)
+    n, S = state.shape
+    F = 2 * (10 * num_pots + 28)
+    out = np.zeros((n, 2, F), np.float64)
+    tables = np.ascontiguousarray(tables)
+    lut = np.ascontiguousarray(lut)
+    rc = lib().ovo_featurize(_p(tables), ctypes.c_int(len(tables)), _p(lut), _p(state), _p(out), ctypes.c_int64(n),
+                             ctypes.c_int(S), ctypes.c_int(num_pots))
+    assert rc == 0
+    return out

@@ -1,0 +1,141 @@
+"""CPU tests: the C oracle (oracle/ovc_oracle.c) against fixtures generated from the reference.
+
+These pin the oracle.  The fixtures under tests/golden/ were produced by tools/make_golden.py,
+which runs the unmodified reference (and asserts the reference's own golden vectors on the way).
+"""
+import json
+
+import numpy as np
+import pytest
+
+from helpers import EVENT_MASK, GOLD, TRACE_FILES, TRACE_IDS, Trace, lut_bytes
+from oracle import cpu
+from overcooked_ai_b200 import layout as L
+from overcooked_ai_b200.state import OvercookedState
+
+
+def _check_transitions(tr):
+    s0, a, s1, sparse, shaped, events = tr.flat()
+    st = s0.copy()
+    o_sp, o_sh, o_dn, o_ev = cpu.step(tr.tables, tr.starts, st, a, horizon=0)
+    assert np.array_equal(st, s1)
+    assert np.array_equal(o_sp, sparse)
+    assert np.array_equal(o_sh, shaped)
+    assert np.array_equal(o_ev & EVENT_MASK, events)
+    # engine extra: recipe index of a delivered soup sits in bits 25-28 and maps to the reward
+    deliv = (o_ev >> 15) & 1
+    rec = (o_ev >> L.EV_RECIPE_SHIFT) & 15
+    assert np.array_equal(rec > 0, deliv == 1)
+    per_agent = tr.layout.deliver_value[rec] * deliv
+    assert np.array_equal(per_agent.reshape(tr.sparse2.shape), tr.sparse2)
+
+
+def test_reference_golden_trajectory_mdp_test():
+    """testing/overcooked_test.py:516-525 (test_mdp_dynamics) — the reference's own 1500-step vector."""
+    tr = Trace(GOLD + "/dynamics_mdp_test.npz")
+    assert tr.T == 1500 and tr.sparse.sum() == 10
+    _check_transitions(tr)
+
+
+@pytest.mark.parametrize("path", TRACE_FILES, ids=TRACE_IDS)
+def test_transitions(path):
+    _check_transitions(Trace(path))
+
+
+def test_greedy_rollouts_cramped_room():
+    """5 seeded GreedyHumanModel games (180 sparse reward each): the soup pickup / delivery branches."""
+    tr = Trace(GOLD + "/greedy_cramped_room.npz")
+    assert tr.sparse.sum(1).tolist() == [180] * 5
+    # the fixture stores s_0..s_{T-1}; check the T-1 transitions between stored states
+    S = tr.S
+    s0 = np.ascontiguousarray(tr.states[:, :-1].reshape(-1, S)).copy()
+    a = np.ascontiguousarray(tr.actions[:, :-1].reshape(-1, 2))
+    o_sp, o_sh, o_dn, o_ev = cpu.step(tr.tables, tr.starts, s0, a, horizon=400)
+    assert np.array_equal(s0, tr.states[:, 1:].reshape(-1, S))
+    assert np.array_equal(o_sp, tr.sparse[:, :-1].reshape(-1))
+    assert np.array_equal(o_sh, tr.shaped[:, :-1].reshape(-1, 2))
+    assert np.array_equal(o_ev & EVENT_MASK, tr.events[:, :-1].reshape(-1, 2))
+    assert not o_dn.any()
+
+
+def test_rollout_equals_repeated_step_and_done():
+    tr = Trace(GOLD + "/greedy_cramped_room.npz")
+    st = np.ascontiguousarray(tr.states[:, 0]).copy()
+    acts = np.ascontiguousarray(tr.actions.transpose(1, 0, 2))  # [T,E,2]
+    sp, sh, dn, ev = cpu.rollout(tr.tables, tr.starts, st, acts, horizon=400, flags=0, n_threads=2)
+    assert np.array_equal(sp.T, tr.sparse) and np.array_equal(sh.transpose(1, 0, 2), tr.shaped)
+    assert dn[-1].all() and not dn[:-1].any() and (st[:, 0] == 400).all()
+    # stepping a finished env: untouched + flagged (the reference asserts, overcooked_env.py:255)
+    before = st.copy()
+    sp2, sh2, dn2, ev2 = cpu.step(tr.tables, tr.starts, st, acts[0], horizon=400)
+    assert np.array_equal(before, st) and dn2.all() and (ev2 == L.EVF_STEPPED_DONE).all()
+    # auto reset: the record becomes the layout's start record when the horizon is reached
+    st = np.ascontiguousarray(tr.states[:, 0]).copy()
+    sp, sh, dn, ev = cpu.rollout(tr.tables, tr.starts, st, acts, horizon=400, flags=1, n_threads=1)
+    assert dn[-1].all() and np.array_equal(st, np.repeat(tr.starts, st.shape[0], 0))
+
+
+def test_lossless_reference_golden_pickle():
+    """testing/overcooked_test.py:1050-1067: (5,400,2,5,4,26) expected.pickle, bit for bit."""
+    d = np.load(GOLD + "/greedy_cramped_room.npz")
+    cl = L.compile_layout("cramped_room")
+    tab, starts, S = L.build_tables([cl])
+    enc = cpu.encode_lossless(tab, d["states"].reshape(-1, S), 5, 4, horizon=400)
+    assert np.array_equal(enc.reshape(5, 400, 2, 5, 4, 26), d["lossless"].astype(np.int32))
+
+
+@pytest.mark.parametrize("num_pots", [0, 1, 2])
+def test_featurize_reference_golden_pickles(num_pots):
+    """testing/overcooked_test.py:1069-1093: expected_{0,1,2}.pickle."""
+    d = np.load(GOLD + "/greedy_cramped_room.npz")
+    cl = L.compile_layout("cramped_room")
+    tab, starts, S = L.build_tables([cl])
+    f = cpu.featurize(tab, lut_bytes([cl]), d["states"].reshape(-1, S), num_pots)
+    exp = d["feat_%d" % num_pots]
+    assert np.array_equal(f.reshape(exp.shape), exp.astype(np.float64))
+
+
+@pytest.mark.parametrize("path", TRACE_FILES, ids=TRACE_IDS)
+def test_observations(path):
+    tr = Trace(path)
+    d = tr.data
+    cl = tr.layout
+    enc = cpu.encode_lossless(tr.tables, d["obs_states"], cl.width, cl.height, horizon=400)
+    assert np.array_equal(enc, d["obs_lossless"].astype(np.int32))
+    lut = lut_bytes([cl])
+    for num_pots in (0, 1, 2, 3):
+        f = cpu.featurize(tr.tables, lut, d["obs_states"], num_pots)
+        assert np.array_equal(f, d["obs_feat_%d" % num_pots].astype(np.float64)), num_pots
+
+
+def test_feature_lut_matches_reference_planner():
+    """CompiledLayout.feature_lut() (own BFS) == argmins of the reference MotionPlanner
+    (planning/planners.py:391-423) on every bundled 2-player layout the fixture covers."""
+    d = np.load(GOLD + "/planner_luts.npz")
+    assert len(d.files) >= 40
+    for name in d.files:
+        cl = L.compile_layout(name)
+        mine = cl.feature_lut().view(np.uint8).reshape(-1)
+        assert np.array_equal(mine, d[name]), name
+
+
+@pytest.mark.parametrize("path", TRACE_FILES + [GOLD + "/dynamics_mdp_test.npz"])
+def test_pack_unpack_roundtrip_against_reference_dicts(path):
+    """unpack(pack(state)).to_dict() == the reference's own to_dict() output (wire format parity)."""
+    tr = Trace(path)
+    sample = json.loads(str(tr.data["to_dict_sample"]))
+    assert sample
+    for key, ref_dict in sample.items():
+        st = OvercookedState.from_dict(ref_dict)
+        rec = L.pack_state(tr.layout, st, 0, tr.S)
+        back = L.unpack_state(tr.layout, rec)
+        assert back == st
+        # the reference lists objects in dict-insertion (history) order; the record is canonical
+        got = json.loads(json.dumps(back.to_dict()))
+        got["objects"].sort(key=lambda o: o["position"])
+        ref_dict["objects"].sort(key=lambda o: o["position"])
+        assert got == ref_dict
+    # and every stored record survives unpack -> pack unchanged
+    flat = tr.states.reshape(-1, tr.S)[:: max(1, tr.states.size // tr.S // 300)]
+    for rec in flat:
+        assert np.array_equal(L.pack_state(tr.layout, L.unpack_state(tr.layout, rec), 0, tr.S), rec)
