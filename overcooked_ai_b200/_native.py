@@ -1,0 +1,63 @@
+"""ctypes binding of the C ABI in include/ovc_b200.h (csrc/libovc_b200.so).
+
+There is no CPU fallback anywhere in this package: if the CUDA library is missing or a CUDA
+device is not available, the calls below raise.  Build it with ``python -m overcooked_ai_b200.build``
+(or ``__graft_entry__.build()``).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libovc_b200.so")
+
+ABI_VERSION = 1
+F_AUTO_RESET = 1
+F_IO_SHIFT = 8
+IO_DEFAULT, IO_TMA_TENSOR, IO_TMA_BULK, IO_DIRECT = 0, 1, 2, 3
+DT_F32, DT_U8, DT_I32 = 0, 1, 2
+
+_lib = None
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the CUDA library; raises NativeLibraryError if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            "%s not found: the CUDA extension is not built (python -m overcooked_ai_b200.build). "
+            "This engine has no CPU fallback." % LIB_PATH
+        )
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+    L.ovc_abi_version.restype = i32
+    L.ovc_layout_table_size.restype = ctypes.c_size_t
+    L.ovc_feat_lut_entry_size.restype = ctypes.c_size_t
+    L.ovc_last_error.restype = ctypes.c_char_p
+    L.ovc_step.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]
+    L.ovc_rollout.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]
+    L.ovc_reset.argtypes = [vp, i32, vp, vp, vp, i64, i32, vp]
+    L.ovc_encode_lossless.argtypes = [vp, i32, vp, vp, i32, i64, i32, i32, i32, i32, vp]
+    L.ovc_featurize.argtypes = [vp, i32, vp, vp, vp, i64, i32, i32, vp]
+    for f in (L.ovc_step, L.ovc_rollout, L.ovc_reset, L.ovc_encode_lossless, L.ovc_featurize):
+        f.restype = i32
+    if L.ovc_abi_version() != ABI_VERSION:
+        raise NativeLibraryError("ABI version mismatch: library %d, binding %d" % (L.ovc_abi_version(), ABI_VERSION))
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = (
+    "ovc_abi_version", "ovc_layout_table_size", "ovc_feat_lut_entry_size", "ovc_last_error",
+    "ovc_step", "ovc_rollout", "ovc_reset", "ovc_encode_lossless", "ovc_featurize",
+)
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("ovc native call failed (%d): %s" % (rc, lib().ovc_last_error().decode()))

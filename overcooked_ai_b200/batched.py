@@ -1,0 +1,289 @@
+"""BatchedOvercookedEnv — N independent Overcooked environments advanced by one CUDA launch.
+
+The tensor-level API of the engine.  State lives in ONE int32 tensor
+``state[N, S]`` (record layout in include/ovc_b200.h); ``step`` / ``rollout`` / ``reset`` /
+``lossless_state_encoding`` / ``featurize_state`` are thin calls into the C ABI on torch's current
+CUDA stream, so they compose with CUDA graphs and user streams.  torch owns every buffer; the
+native library allocates nothing.
+
+Semantics follow the reference per environment:
+  step     OvercookedEnv.step      (src/overcooked_ai_py/mdp/overcooked_env.py:244-274) on top of
+           OvercookedGridworld.get_state_transition (overcooked_mdp.py:1375-1430)
+  reset    OvercookedEnv.reset     (overcooked_env.py:288-319), standard start state
+  done     OvercookedEnv.is_done   (overcooked_env.py:321-325): timestep >= horizon
+Stepping an environment that is already done leaves it untouched and sets EVF_STEPPED_DONE in its
+event words (the reference raises AssertionError, overcooked_env.py:255); with ``auto_reset=True``
+an environment that reaches the horizon is put back to its start state in the same launch (its
+``done`` output is still 1 for that transition), which is what rollout collection wants.
+"""
+import numpy as np
+import torch
+
+from overcooked_ai_b200 import _native
+from overcooked_ai_b200 import layout as L
+
+_TORCH_DT = {torch.float32: _native.DT_F32, torch.uint8: _native.DT_U8, torch.int32: _native.DT_I32}
+
+
+def _as_layouts(layouts, mdp_params):
+    if isinstance(layouts, (str, L.CompiledLayout)) or hasattr(layouts, "compiled"):
+        layouts = [layouts]
+    out = []
+    for l in layouts:
+        if isinstance(l, str):
+            l = L.compile_layout(l, **(mdp_params or {}))
+        elif hasattr(l, "compiled"):  # an overcooked_ai_b200.mdp.OvercookedGridworld
+            l = l.compiled
+        out.append(l)
+    return out
+
+
+class BatchedOvercookedEnv(object):
+    def __init__(self, layouts, n_envs, horizon=400, device="cuda", auto_reset=False, state_words=None,
+                 io=_native.IO_DEFAULT, env_layout=None, mdp_params=None):
+        """
+        layouts      layout name / CompiledLayout / OvercookedGridworld, or a list of them (mixed batch)
+        n_envs       number of environments on THIS device
+        horizon      episode length (OvercookedEnv's ``horizon``); <= 0 means no horizon
+        env_layout   optional int array [n_envs] of layout indices; default: contiguous, near-equal
+                     segments, one per layout (a warp then sees one layout)
+        io           record I/O strategy of the step kernel (_native.IO_*); 0 = library default
+        """
+        self._lib = _native.lib()
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedOvercookedEnv needs a CUDA device: this engine has no CPU fallback")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("device must be a CUDA device")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.layouts = _as_layouts(layouts, mdp_params)
+        self.n_layouts = len(self.layouts)
+        self.n_envs = int(n_envs)
+        self.horizon = int(horizon) if horizon < 2**31 else 0
+        self.auto_reset = bool(auto_reset)
+        self.io = int(io)
+        tab, starts, S = L.build_tables(self.layouts, state_words)
+        assert tab.shape[1] == self._lib.ovc_layout_table_size(), "layout table size mismatch with the native library"
+        self.state_words = S
+        self._tab_host, self._starts_host = tab, starts
+        with torch.cuda.device(self.device):
+            self.tables = torch.from_numpy(tab).to(self.device)
+            self.start_records = torch.from_numpy(starts).to(self.device)
+            if env_layout is None:
+                bounds = [self.n_envs * i // self.n_layouts for i in range(self.n_layouts + 1)]
+                env_layout = np.zeros(self.n_envs, np.int32)
+                for i in range(self.n_layouts):
+                    env_layout[bounds[i]:bounds[i + 1]] = i
+            env_layout = np.ascontiguousarray(env_layout, dtype=np.int32)
+            assert env_layout.shape == (self.n_envs,) and (env_layout >= 0).all() and (env_layout < self.n_layouts).all()
+            self.env_layout_host = env_layout
+            self.env_layout = torch.from_numpy(env_layout).to(self.device)
+            self.state = torch.zeros((self.n_envs, S), dtype=torch.int32, device=self.device)
+            self.sparse = torch.zeros(self.n_envs, dtype=torch.int32, device=self.device)
+            self.shaped = torch.zeros((self.n_envs, 2), dtype=torch.int32, device=self.device)
+            self.done = torch.zeros(self.n_envs, dtype=torch.int32, device=self.device)
+            self.events = torch.zeros((self.n_envs, 2), dtype=torch.int32, device=self.device)
+        self._lut = None
+        self._segments = None
+        self._p_tables, self._p_starts, self._p_state = self.tables.data_ptr(), self.start_records.data_ptr(), self.state.data_ptr()
+        self.reset()
+
+    # ---------------------------------------------------------------------------------------------
+    def _flags(self):
+        return (_native.F_AUTO_RESET if self.auto_reset else 0) | (self.io << _native.F_IO_SHIFT)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def reset(self, mask=None):
+        """Put all environments (or those with mask != 0; int32 tensor [N]) back to their layout's
+        standard start state (overcooked_mdp.py:1297-1305)."""
+        if mask is not None:
+            assert mask.dtype == torch.int32 and mask.is_cuda and mask.is_contiguous() and mask.numel() == self.n_envs
+        _native.check(self._lib.ovc_reset(
+            self.start_records.data_ptr(), self.n_layouts, self.state.data_ptr(), self.env_layout.data_ptr(),
+            0 if mask is None else mask.data_ptr(), self.n_envs, self.state_words, self._stream()))
+
+    def step(self, actions, out=None):
+        """One joint transition of every environment.
+
+        actions  int32 CUDA tensor [N, 2], action indices 0..5 (Action.INDEX_TO_ACTION order)
+        out      optional (sparse[N], shaped[N,2], done[N], events[N,2]) int32 CUDA tensors to write
+        returns  (sparse, shaped, done, events); without ``out`` these are buffers owned by the env and
+                 overwritten by the next call.  ``sparse`` is the summed delivery reward
+                 (what OvercookedEnv.step returns), ``shaped`` is shaped_reward_by_agent,
+                 ``events`` holds one bit per EVENT_TYPES entry per agent (layout.EVENT_TYPES).
+        """
+        assert actions.dtype == torch.int32 and actions.is_cuda and actions.is_contiguous()
+        assert actions.numel() == 2 * self.n_envs
+        sparse, shaped, done, events = (self.sparse, self.shaped, self.done, self.events) if out is None else out
+        _native.check(self._lib.ovc_step(
+            self._p_tables, self.n_layouts, self._p_starts, self._p_state,
+            actions.data_ptr(), sparse.data_ptr(), shaped.data_ptr(), done.data_ptr(),
+            events.data_ptr(), self.n_envs, self.state_words, self.horizon, self._flags(), self._stream()))
+        return sparse, shaped, done, events
+
+    def rollout(self, actions, out=None):
+        """T transitions in one launch (state stays on chip between them).
+
+        actions  int32 CUDA tensor [T, N, 2];  out: optional (sparse[T,N], shaped[T,N,2], done[T,N], events[T,N,2])
+        Equivalent to T calls of step() with the same actions.
+        """
+        assert actions.dtype == torch.int32 and actions.is_cuda and actions.is_contiguous() and actions.dim() == 3
+        T = actions.shape[0]
+        assert actions.shape[1] == self.n_envs and actions.shape[2] == 2
+        if out is None:
+            out = (
+                torch.empty((T, self.n_envs), dtype=torch.int32, device=self.device),
+                torch.empty((T, self.n_envs, 2), dtype=torch.int32, device=self.device),
+                torch.empty((T, self.n_envs), dtype=torch.int32, device=self.device),
+                torch.empty((T, self.n_envs, 2), dtype=torch.int32, device=self.device),
+            )
+        sparse, shaped, done, events = out
+        _native.check(self._lib.ovc_rollout(
+            self.tables.data_ptr(), self.n_layouts, self.start_records.data_ptr(), self.state.data_ptr(),
+            actions.data_ptr(), sparse.data_ptr(), shaped.data_ptr(), done.data_ptr(), events.data_ptr(),
+            self.n_envs, T, self.state_words, self.horizon, self._flags(), self._stream()))
+        return out
+
+    # ---------------------------------------------------------------------------------------------
+    def segments(self):
+        """[(begin, end, layout index)] maximal runs of equal layout in env order."""
+        if self._segments is None:
+            el = self.env_layout_host
+            cuts = [0] + (np.nonzero(np.diff(el))[0] + 1).tolist() + [self.n_envs]
+            self._segments = [(cuts[i], cuts[i + 1], int(el[cuts[i]])) for i in range(len(cuts) - 1) if cuts[i] < cuts[i + 1]]
+        return self._segments
+
+    def obs_shape(self, layout_index=0):
+        l = self.layouts[layout_index]
+        return (l.width, l.height, 26)
+
+    def lossless_state_encoding(self, out=None, dtype=torch.float32):
+        """lossless_state_encoding (overcooked_mdp.py:2385-2561) of every environment, both players:
+        tensor [N, 2, W, H, 26] (index order [x][y][channel], as the reference) when all layouts share
+        one grid shape, else a list of such tensors, one per layout segment.  dtype float32 (what the
+        reference's RLlib consumer casts to), uint8 or int32."""
+        shapes = {(l.width, l.height) for l in self.layouts}
+        if len(shapes) == 1:
+            runs = [(0, self.n_envs, 0)]
+        else:
+            runs = self.segments()
+        outs = []
+        for k, (b, e, li) in enumerate(runs):
+            W, H = self.layouts[li].width, self.layouts[li].height
+            o = out[k] if isinstance(out, (list, tuple)) else out
+            if o is None:
+                o = torch.empty((e - b, 2, W, H, 26), dtype=dtype, device=self.device)
+            assert o.is_cuda and o.is_contiguous() and o.numel() == (e - b) * 2 * W * H * 26
+            _native.check(self._lib.ovc_encode_lossless(
+                self.tables.data_ptr(), self.n_layouts, self.state.data_ptr() + 4 * self.state_words * b, o.data_ptr(),
+                _TORCH_DT[o.dtype], e - b, self.state_words, W, H, self.horizon if self.horizon > 0 else 2**31 - 1,
+                self._stream()))
+            outs.append(o)
+        return outs[0] if len(shapes) == 1 else outs
+
+    def feature_lut(self):
+        if self._lut is None:
+            lut = np.stack([l.feature_lut() for l in self.layouts]).view(np.uint8).reshape(self.n_layouts, -1)
+            assert lut.shape[1] == 1024 * self._lib.ovc_feat_lut_entry_size()
+            self._lut = torch.from_numpy(lut).to(self.device)
+        return self._lut
+
+    def featurize_state(self, num_pots=2, out=None):
+        """featurize_state (overcooked_mdp.py:2579-2898; default NO_COUNTERS_PARAMS planner):
+        float32 [N, 2, 2*(10*num_pots+28)]."""
+        F = 2 * (10 * num_pots + 28)
+        if out is None:
+            out = torch.empty((self.n_envs, 2, F), dtype=torch.float32, device=self.device)
+        assert out.dtype == torch.float32 and out.is_cuda and out.is_contiguous() and out.numel() == self.n_envs * 2 * F
+        _native.check(self._lib.ovc_featurize(
+            self.tables.data_ptr(), self.n_layouts, self.feature_lut().data_ptr(), self.state.data_ptr(),
+            out.data_ptr(), self.n_envs, self.state_words, num_pots, self._stream()))
+        return out
+
+    # ---------------------------------------------------------------------------------------------
+    def sparse_by_agent(self, sparse_unused, events):
+        """Per-agent delivery reward from the event words (bits 25-28 carry the delivered recipe)."""
+        val = torch.from_numpy(np.stack([l.deliver_value for l in self.layouts]).astype(np.int32)).to(events.device)
+        rec = (events >> L.EV_RECIPE_SHIFT) & 15
+        lid = self.env_layout.long().view(*([1] * (events.dim() - 2)), -1, 1).expand_as(rec)
+        return val[lid, rec.long()] * ((events >> 15) & 1)
+
+    def get_states(self, indices=None):
+        """Unpack records into OvercookedState objects (host; for debugging / the drop-in adapters)."""
+        recs = self.state.cpu().numpy()
+        idx = range(self.n_envs) if indices is None else indices
+        return [L.unpack_state(self.layouts[self.env_layout_host[i]], recs[i]) for i in idx]
+
+    def set_states(self, states, indices=None):
+        idx = list(range(self.n_envs)) if indices is None else list(indices)
+        recs = np.stack([
+            L.pack_state(self.layouts[self.env_layout_host[i]], s, int(self.env_layout_host[i]), self.state_words)
+            for i, s in zip(idx, states)
+        ])
+        self.state[torch.as_tensor(idx, device=self.device)] = torch.from_numpy(recs).to(self.device)
+
+
+class HostRolloutPipeline(object):
+    """Rollout collection with HOST buffers: the end-to-end path a host-side policy / learner sees.
+
+    ``run(actions_host[T,N,2])`` copies the action trace host->device in chunks of ``chunk`` steps
+    (pinned memory, copy stream), advances the environments with the fused rollout kernel (compute
+    stream) and copies sparse / shaped / done / events device->host (second copy stream), the three
+    stages overlapped across chunks with double buffering.  Returns pinned host tensors
+    (sparse[T,N], shaped[T,N,2], done[T,N], events[T,N,2]).  Per environment-step this moves 8 bytes
+    host->device and 24 bytes device->host.
+    """
+
+    def __init__(self, env, n_steps, chunk=50):
+        self.env, self.T, self.chunk = env, int(n_steps), int(chunk)
+        N, dev = env.n_envs, env.device
+        self.s_h2d, self.s_comp, self.s_d2h = (torch.cuda.Stream(dev) for _ in range(3))
+        mk = lambda *shape: torch.empty(shape, dtype=torch.int32, device=dev)
+        self.d_act = [mk(chunk, N, 2) for _ in range(2)]
+        self.d_out = [(mk(chunk, N), mk(chunk, N, 2), mk(chunk, N), mk(chunk, N, 2)) for _ in range(2)]
+        pin = lambda *shape: torch.empty(shape, dtype=torch.int32, pin_memory=True)
+        self.h_out = (pin(self.T, N), pin(self.T, N, 2), pin(self.T, N), pin(self.T, N, 2))
+        self.h2d_bytes_per_step = N * 2 * 4
+        self.d2h_bytes_per_step = N * (1 + 2 + 1 + 2) * 4
+
+    def run(self, actions_host):
+        assert actions_host.dtype == torch.int32 and actions_host.is_pinned() and tuple(actions_host.shape) == (self.T, self.env.n_envs, 2)
+        env = self.env
+        cur = torch.cuda.current_stream(env.device)
+        for s in (self.s_h2d, self.s_comp, self.s_d2h):
+            s.wait_stream(cur)
+        ev_comp_done = [None, None]  # compute finished with d_act[b] / produced d_out[b]
+        ev_d2h_done = [None, None]   # d_out[b] has been copied out
+        k = 0
+        for t0 in range(0, self.T, self.chunk):
+            tc = min(self.chunk, self.T - t0)
+            b = k & 1
+            with torch.cuda.stream(self.s_h2d):
+                if ev_comp_done[b] is not None:
+                    self.s_h2d.wait_event(ev_comp_done[b])  # the kernel two chunks ago has consumed d_act[b]
+                self.d_act[b][:tc].copy_(actions_host[t0:t0 + tc], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(self.s_h2d)
+            with torch.cuda.stream(self.s_comp):
+                self.s_comp.wait_event(ev_in)
+                if ev_d2h_done[b] is not None:
+                    self.s_comp.wait_event(ev_d2h_done[b])  # d_out[b] is free again
+                out = tuple(o[:tc] for o in self.d_out[b])
+                env.rollout(self.d_act[b][:tc], out=out)
+                ev_c = torch.cuda.Event()
+                ev_c.record(self.s_comp)
+                ev_comp_done[b] = ev_c
+            with torch.cuda.stream(self.s_d2h):
+                self.s_d2h.wait_event(ev_c)
+                for h, d in zip(self.h_out, out):
+                    h[t0:t0 + tc].copy_(d, non_blocking=True)
+                ev_o = torch.cuda.Event()
+                ev_o.record(self.s_d2h)
+                ev_d2h_done[b] = ev_o
+            k += 1
+        for s in (self.s_h2d, self.s_comp, self.s_d2h):
+            cur.wait_stream(s)
+        return self.h_out

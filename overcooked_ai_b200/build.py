@@ -1,0 +1,38 @@
+"""Build csrc/libovc_b200.so for sm_100a with nvcc (in-tree, so the .so travels to the GPU box).
+
+    python -m overcooked_ai_b200.build [--force]
+"""
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+SOURCES = ["ovc_b200.cu"]
+DEPS = ["ovc_b200.cu", "ovc_step.cuh", "ovc_obs.cuh", os.path.join("..", "..", "include", "ovc_b200.h")]
+OUT = os.path.join(CSRC, "libovc_b200.so")
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def find_nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    return "nvcc"
+
+
+def build(force=False, verbose=False):
+    newest = max(os.path.getmtime(os.path.join(CSRC, d)) for d in DEPS)
+    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= newest:
+        return OUT
+    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
+    subprocess.check_call(cmd, cwd=CSRC)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,394 @@
+// ovc_b200.cu — sm_100a kernels + C ABI (include/ovc_b200.h) of the batched Overcooked engine.
+//
+// K1  step_kernel<S, IO>     one joint transition of a tile of TILE environments per CTA.
+//     IO = 1  the tile [TILE][S] int32 is brought into shared memory by ONE 2-D tensor-map TMA load
+//             (cp.async.bulk.tensor.2d, SASS UTMALDG) with the hardware 64B/128B swizzle, so that the
+//             per-thread 16-byte record-chunk accesses (stride = one record) are bank-conflict free;
+//             threads update their record in place; one TMA tensor store (UTMASTG) writes it back.
+//     IO = 2  same, with a 1-D bulk copy (cp.async.bulk, SASS UBLKCP) and a linear tile.
+//     IO = 3  no staging: each thread reads / writes its record's chunks in global memory.
+// K5  rollout_kernel<S, IO>  T transitions with the tile resident in shared memory.
+// K4  reset_kernel           masked copy of the per-layout start record.
+// The observation kernels (K2 lossless encode, K3 featurize) live in ovc_obs.cuh.
+//
+// The path is integer, branchy and HBM-bound (no contraction anywhere): no tensor cores.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/ovc_b200.h"
+#include "ovc_step.cuh"
+
+namespace ovc {
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, const char *a = "", long long b = 0) {
+    snprintf(g_err, sizeof g_err, fmt, a, b);
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char *what) {
+    snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
+    return OVC_E_CUDA;
+}
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA (bulk async copies)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, const void *src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"((uint64_t)map),
+                 "r"(c0), "r"(c1), "r"(smem_u32(src))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"((uint64_t)src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store_1d(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"((uint64_t)dst), "r"(smem_u32(src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// record accessors
+// ------------------------------------------------------------------------------------------------
+// Shared-memory tile.  SWZ = number of 16-byte-chunk index bits the TMA swizzle XORs with address
+// bits 7.. (2: CU_TENSOR_MAP_SWIZZLE_64B for 64-byte records, 3: SWIZZLE_128B, 0: linear tile).
+template <int S, int SWZ>
+struct SmemRec {
+    char *tile;     // 1024-byte aligned tile base
+    uint32_t base;  // byte offset of this thread's record inside the tile
+    __device__ __forceinline__ uint32_t phys(uint32_t off) const {
+        if (SWZ == 0) return off;
+        return off ^ (((off >> 7) & ((1u << SWZ) - 1u)) << 4);
+    }
+    __device__ __forceinline__ int4 ld4(int c) const { return *reinterpret_cast<const int4 *>(tile + phys(base + c * 16)); }
+    __device__ __forceinline__ void st4(int c, int4 v) { *reinterpret_cast<int4 *>(tile + phys(base + c * 16)) = v; }
+    __device__ __forceinline__ int ldw(int w) const { return *reinterpret_cast<const int *>(tile + phys(base + w * 4)); }
+    __device__ __forceinline__ void stw(int w, int v) { *reinterpret_cast<int *>(tile + phys(base + w * 4)) = v; }
+};
+
+struct GlobalRec {
+    int32_t *rec;
+    __device__ __forceinline__ int4 ld4(int c) const { return *reinterpret_cast<const int4 *>(rec + c * 4); }
+    __device__ __forceinline__ void st4(int c, int4 v) { *reinterpret_cast<int4 *>(rec + c * 4) = v; }
+    __device__ __forceinline__ int ldw(int w) const { return rec[w]; }
+    __device__ __forceinline__ void stw(int w, int v) { rec[w] = v; }
+};
+
+template <int S>
+struct Cfg {
+    static constexpr int TILE = S <= 32 ? 128 : 64;         // environments (= threads) per CTA
+    static constexpr int ROW_WORDS = S == 16 ? 16 : 32;     // tensor-map row: 64 B or 128 B
+    static constexpr int ROWS_PER_ENV = S / ROW_WORDS;      // 1, 1, 2, 4
+    static constexpr int BOX_ROWS = TILE * ROWS_PER_ENV;    // <= 256
+    static constexpr int SWZ = S == 16 ? 2 : 3;
+    static constexpr int TILE_BYTES = TILE * S * 4;
+};
+
+struct StepArgs {
+    const ovc_layout_t *layouts;
+    const int32_t *start_records;
+    int32_t *state;
+    const int32_t *actions;
+    int32_t *sparse, *shaped, *done, *events;
+    long long n_envs;
+    int n_steps;  // rollout only
+    int horizon, flags;
+};
+
+__device__ __forceinline__ void write_outputs(const StepArgs &a, long long idx, const StepOut &o) {
+    a.sparse[idx] = o.sparse;
+    a.done[idx] = o.done;
+    reinterpret_cast<int2 *>(a.shaped)[idx] = make_int2(o.shaped0, o.shaped1);
+    reinterpret_cast<int2 *>(a.events)[idx] = make_int2((int)o.ev0, (int)o.ev1);
+}
+
+// One CTA = one tile of TILE records.  T == 1: the step kernel; T > 1: the fused rollout.
+template <int S, int IO>
+__global__ void __launch_bounds__(Cfg<S>::TILE)
+step_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
+    using C = Cfg<S>;
+    const long long env0 = (long long)blockIdx.x * C::TILE;
+    const long long env = env0 + threadIdx.x;
+    const bool live = env < a.n_envs;
+    const int T = a.n_steps;
+
+    if (IO == 3) {
+        if (!live) return;
+        GlobalRec r{a.state + env * S};
+        for (int t = 0; t < T; t++) {
+            const long long idx = (long long)t * a.n_envs + env;
+            const int2 act = reinterpret_cast<const int2 *>(a.actions)[idx];
+            StepOut o;
+            step_core(r, a.layouts, a.start_records, S, act.x, act.y, a.horizon, a.flags, o);
+            write_outputs(a, idx, o);
+        }
+        return;
+    }
+
+    extern __shared__ char smem_raw[];
+    __shared__ uint64_t bar;
+    char *tile = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const long long rem = a.n_envs - env0;
+    const uint32_t live_bytes = (uint32_t)((rem < C::TILE ? rem : C::TILE) * S * 4);
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        if (IO == 1) {
+            mbar_expect_tx(&bar, C::TILE_BYTES);  // out-of-range rows are zero filled and still counted
+            tma_load_2d(tile, &tmap, 0, (int)(env0 * C::ROWS_PER_ENV), &bar);
+        } else {
+            mbar_expect_tx(&bar, live_bytes);
+            bulk_load_1d(tile, a.state + env0 * S, live_bytes, &bar);
+        }
+    }
+    // the first action fetch overlaps the tile load
+    int2 act = make_int2(OVC_A_STAY, OVC_A_STAY);
+    if (live) act = reinterpret_cast<const int2 *>(a.actions)[env];
+    __syncthreads();  // barrier initialised and visible before anyone polls it
+    mbar_wait(&bar, 0);
+
+    if (live) {
+        SmemRec<S, IO == 1 ? C::SWZ : 0> r{tile, (uint32_t)threadIdx.x * S * 4};
+        for (int t = 0; t < T; t++) {
+            const long long idx = (long long)t * a.n_envs + env;
+            int2 nxt = act;
+            if (t + 1 < T) nxt = reinterpret_cast<const int2 *>(a.actions)[idx + a.n_envs];  // prefetch
+            StepOut o;
+            step_core(r, a.layouts, a.start_records, S, act.x, act.y, a.horizon, a.flags, o);
+            write_outputs(a, idx, o);
+            act = nxt;
+        }
+    }
+    fence_async_smem();  // generic-proxy writes -> visible to the async proxy (TMA store)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (IO == 1) tma_store_2d(&tmap, 0, (int)(env0 * C::ROWS_PER_ENV), tile);  // rows past the end are clipped
+        else bulk_store_1d(a.state + env0 * S, tile, live_bytes);
+        bulk_commit();
+        bulk_wait_read<0>();  // shared memory must stay alive until the TMA engine has read it
+    }
+}
+
+__global__ void reset_kernel(const int32_t *__restrict__ start_records, int n_layouts, int32_t *__restrict__ state,
+                             const int32_t *__restrict__ env_layout, const int32_t *__restrict__ mask,
+                             long long n_envs, int S) {
+    // one thread per 16-byte chunk: coalesced int4 stores
+    const int cpr = S / 4;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_envs * cpr) return;
+    const long long env = i / cpr;
+    const int c = (int)(i % cpr);
+    if (mask && mask[env] == 0) return;
+    int lid = env_layout ? env_layout[env] : (state[env * S + 3] & 0xFF);
+    if (lid < 0 || lid >= n_layouts) lid = 0;
+    reinterpret_cast<int4 *>(state)[i] = __ldg(reinterpret_cast<const int4 *>(start_records) + (long long)lid * cpr + c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static encode_tiled_fn get_encode_fn() {
+    static encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (encode_tiled_fn)p;
+    }
+    return fn;
+}
+
+template <int S>
+static int make_tmap(CUtensorMap *m, int32_t *state, long long n_envs) {
+    using C = Cfg<S>;
+    encode_tiled_fn enc = get_encode_fn();
+    if (!enc) return fail(OVC_E_CUDA, "cuTensorMapEncodeTiled entry point not available%s", "");
+    cuuint64_t dims[2] = {(cuuint64_t)C::ROW_WORDS, (cuuint64_t)(n_envs * C::ROWS_PER_ENV)};
+    cuuint64_t strides[1] = {(cuuint64_t)C::ROW_WORDS * 4};
+    cuuint32_t box[2] = {(cuuint32_t)C::ROW_WORDS, (cuuint32_t)C::BOX_ROWS};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, state, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     S == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(OVC_E_CUDA, "cuTensorMapEncodeTiled failed%s (CUresult %lld)", "", (long long)r);
+    return OVC_OK;
+}
+
+template <int S>
+static int launch_step(const StepArgs &a, int io, cudaStream_t st) {
+    using C = Cfg<S>;
+    const unsigned grid = (unsigned)((a.n_envs + C::TILE - 1) / C::TILE);
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    const size_t smem = io == 3 ? 0 : C::TILE_BYTES + 1024;
+    if (io == 1) {
+        int rc = make_tmap<S>(&tmap, a.state, a.n_envs);
+        if (rc) return rc;
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(step_kernel<S, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr = true;
+        }
+        step_kernel<S, 1><<<grid, C::TILE, smem, st>>>(tmap, a);
+    } else if (io == 2) {
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(step_kernel<S, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr = true;
+        }
+        step_kernel<S, 2><<<grid, C::TILE, smem, st>>>(tmap, a);
+    } else {
+        step_kernel<S, 3><<<grid, C::TILE, 0, st>>>(tmap, a);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "step kernel launch");
+    return OVC_OK;
+}
+
+static int check_common(const void *layouts, int n_layouts, const void *state, long long n_envs, int S) {
+    if (!layouts || !state) return fail(OVC_E_BADARG, "null pointer argument%s", "");
+    if (n_layouts <= 0 || n_layouts > 256) return fail(OVC_E_BADARG, "n_layouts must be 1..256%s (got %lld)", "", n_layouts);
+    if (n_envs < 0) return fail(OVC_E_BADARG, "negative n_envs%s", "");
+    if (S != 16 && S != 32 && S != 64 && S != 128)
+        return fail(OVC_E_BADARG, "state_words must be 16, 32, 64 or 128%s (got %lld)", "", S);
+    if (((uintptr_t)state & 15) != 0) return fail(OVC_E_BADARG, "state must be 16-byte aligned%s", "");
+    return OVC_OK;
+}
+
+static int step_impl(const void *layouts, int n_layouts, const int32_t *start_records, int32_t *state,
+                     const int32_t *actions, int32_t *sparse, int32_t *shaped, int32_t *done, int32_t *events,
+                     long long n_envs, int n_steps, int S, int horizon, int flags, void *stream) {
+    int rc = check_common(layouts, n_layouts, state, n_envs, S);
+    if (rc) return rc;
+    if (!actions || !sparse || !shaped || !done || !events || !start_records)
+        return fail(OVC_E_BADARG, "null pointer argument%s", "");
+    if ((((uintptr_t)actions | (uintptr_t)shaped | (uintptr_t)events) & 7) != 0)
+        return fail(OVC_E_BADARG, "actions / shaped / events must be 8-byte aligned%s", "");
+    if (n_steps < 1) return fail(OVC_E_BADARG, "n_steps must be >= 1%s", "");
+    if (n_envs == 0) return OVC_OK;
+    int io = (flags & OVC_F_IO_MASK) >> OVC_F_IO_SHIFT;
+    if (io == 0) io = 1;
+    if (io < 1 || io > 3) return fail(OVC_E_BADARG, "unknown record I/O strategy%s %lld", "", io);
+    if (io == 1 && (n_envs * (S / (S == 16 ? 16 : 32))) > 0x7FFFFFFFLL) io = 2;  // tensor coordinates are int32
+    StepArgs a{(const ovc_layout_t *)layouts, start_records, state, actions, sparse, shaped, done, events,
+               n_envs, n_steps, horizon, flags};
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (S) {
+    case 16: return launch_step<16>(a, io, st);
+    case 32: return launch_step<32>(a, io, st);
+    case 64: return launch_step<64>(a, io, st);
+    default: return launch_step<128>(a, io, st);
+    }
+}
+
+}  // namespace ovc
+
+#include "ovc_obs.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int ovc_abi_version(void) { return OVC_ABI_VERSION; }
+size_t ovc_layout_table_size(void) { return sizeof(ovc_layout_t); }
+size_t ovc_feat_lut_entry_size(void) { return sizeof(ovc_feat_lut_entry_t); }
+const char *ovc_last_error(void) { return ovc::g_err; }
+
+int ovc_step(const void *layouts, int n_layouts, const int32_t *start_records, int32_t *state, const int32_t *actions,
+             int32_t *sparse, int32_t *shaped, int32_t *done, int32_t *events, int64_t n_envs, int state_words,
+             int horizon, int flags, void *stream) {
+    return ovc::step_impl(layouts, n_layouts, start_records, state, actions, sparse, shaped, done, events, n_envs, 1,
+                          state_words, horizon, flags, stream);
+}
+
+int ovc_rollout(const void *layouts, int n_layouts, const int32_t *start_records, int32_t *state,
+                const int32_t *actions, int32_t *sparse, int32_t *shaped, int32_t *done, int32_t *events,
+                int64_t n_envs, int n_steps, int state_words, int horizon, int flags, void *stream) {
+    return ovc::step_impl(layouts, n_layouts, start_records, state, actions, sparse, shaped, done, events, n_envs,
+                          n_steps, state_words, horizon, flags, stream);
+}
+
+int ovc_reset(const int32_t *start_records, int n_layouts, int32_t *state, const int32_t *env_layout,
+              const int32_t *mask, int64_t n_envs, int state_words, void *stream) {
+    int rc = ovc::check_common(start_records, n_layouts, state, n_envs, state_words);
+    if (rc) return rc;
+    if (n_envs == 0) return OVC_OK;
+    const long long chunks = (long long)n_envs * (state_words / 4);
+    const int threads = 256;
+    ovc::reset_kernel<<<(unsigned)((chunks + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+        start_records, n_layouts, state, env_layout, mask, n_envs, state_words);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return ovc::cuda_fail(e, "reset kernel launch");
+    return OVC_OK;
+}
+
+int ovc_encode_lossless(const void *layouts, int n_layouts, const int32_t *state, void *out, int dtype,
+                        int64_t n_envs, int state_words, int width, int height, int horizon, void *stream) {
+    int rc = ovc::check_common(layouts, n_layouts, state, n_envs, state_words);
+    if (rc) return rc;
+    return ovc::encode_lossless_impl((const ovc_layout_t *)layouts, state, out, dtype, n_envs, state_words, width,
+                                     height, horizon, (cudaStream_t)stream);
+}
+
+int ovc_featurize(const void *layouts, int n_layouts, const void *lut, const int32_t *state, float *out,
+                  int64_t n_envs, int state_words, int num_pots, void *stream) {
+    int rc = ovc::check_common(layouts, n_layouts, state, n_envs, state_words);
+    if (rc) return rc;
+    return ovc::featurize_impl((const ovc_layout_t *)layouts, (const ovc_feat_lut_entry_t *)lut, state, out, n_envs,
+                               state_words, num_pots, (cudaStream_t)stream);
+}
+
+}  // extern "C"

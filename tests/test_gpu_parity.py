@@ -1,0 +1,276 @@
+"""GPU parity tests: the CUDA kernels, called through the C ABI (ctypes, include/ovc_b200.h), against
+the CPU oracle and the reference-generated golden fixtures.  Bit-exact everywhere (integer path;
+the float32 outputs hold small integers)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import EVENT_MASK, GOLD, TRACE_FILES, TRACE_IDS, Trace, lut_bytes
+from oracle import cpu
+from overcooked_ai_b200 import _native
+from overcooked_ai_b200 import layout as L
+from overcooked_ai_b200.batched import BatchedOvercookedEnv
+
+pytestmark = pytest.mark.gpu
+
+IOS = [_native.IO_TMA_TENSOR, _native.IO_TMA_BULK, _native.IO_DIRECT]
+IO_IDS = ["tma2d", "bulk1d", "direct"]
+CLASSIC5 = ["cramped_room", "asymmetric_advantages", "coordination_ring", "forced_coordination", "counter_circuit"]
+
+
+def _env_for_trace(tr, n, io, horizon=0, auto_reset=False):
+    return BatchedOvercookedEnv(tr.layout, n, horizon=horizon, io=io, auto_reset=auto_reset)
+
+
+def _np(t):
+    return t.cpu().numpy()
+
+
+@pytest.mark.parametrize("io", IOS, ids=IO_IDS)
+@pytest.mark.parametrize("path", TRACE_FILES + [GOLD + "/dynamics_mdp_test.npz"], ids=TRACE_IDS + ["dynamics_mdp_test"])
+def test_golden_transitions(path, io):
+    """Every reference transition in the fixture, as one batch, through each record-I/O strategy."""
+    tr = Trace(path)
+    s0, a, s1, sparse, shaped, events = tr.flat()
+    env = _env_for_trace(tr, len(s0), io)
+    env.state.copy_(torch.from_numpy(s0))
+    sp, sh, dn, ev = env.step(torch.from_numpy(a).cuda())
+    assert np.array_equal(_np(env.state), s1)
+    assert np.array_equal(_np(sp), sparse)
+    assert np.array_equal(_np(sh), shaped)
+    assert np.array_equal(_np(ev) & EVENT_MASK, events)
+    assert not _np(dn).any()
+    by_agent = _np(env.sparse_by_agent(sp, ev))
+    assert np.array_equal(by_agent.reshape(tr.sparse2.shape), tr.sparse2)
+
+
+def test_greedy_games_stepwise_and_fused():
+    """5 GreedyHumanModel games on cramped_room (9 deliveries each): per-step launches, then the same
+    games again through the fused T-step rollout kernel."""
+    tr = Trace(GOLD + "/greedy_cramped_room.npz")
+    acts = torch.from_numpy(np.ascontiguousarray(tr.actions.transpose(1, 0, 2))).cuda()  # [T,E,2]
+    for mode in ("step", "rollout"):
+        env = BatchedOvercookedEnv("cramped_room", tr.E, horizon=400)
+        assert np.array_equal(_np(env.state), tr.states[:, 0])
+        if mode == "step":
+            sps, shs, evs = [], [], []
+            for t in range(tr.T):
+                sp, sh, dn, ev = env.step(acts[t])
+                sps.append(_np(sp)), shs.append(_np(sh)), evs.append(_np(ev))
+                if t + 1 < tr.T:
+                    assert np.array_equal(_np(env.state), tr.states[:, t + 1])
+            sp, sh, ev = np.stack(sps), np.stack(shs), np.stack(evs)
+        else:
+            sp, sh, dn, ev = [_np(x) for x in env.rollout(acts)]
+            assert dn[-1].all() and not dn[:-1].any()
+        assert np.array_equal(sp.T, tr.sparse) and sp.sum(0).tolist() == [180] * 5
+        assert np.array_equal(sh.transpose(1, 0, 2), tr.shaped)
+        assert np.array_equal(ev.transpose(1, 0, 2) & EVENT_MASK, tr.events)
+
+
+def test_lossless_reference_golden_pickle():
+    d = np.load(GOLD + "/greedy_cramped_room.npz")
+    states = d["states"].reshape(-1, 16)
+    env = BatchedOvercookedEnv("cramped_room", len(states), horizon=400)
+    env.state.copy_(torch.from_numpy(states))
+    want = d["lossless"].reshape(-1, 2, 5, 4, 26)
+    for dt in (torch.float32, torch.uint8, torch.int32):
+        enc = env.lossless_state_encoding(dtype=dt)
+        assert enc.dtype == dt and tuple(enc.shape) == (len(states), 2, 5, 4, 26)
+        assert np.array_equal(_np(enc).astype(np.int32), want.astype(np.int32))
+
+
+@pytest.mark.parametrize("num_pots", [0, 1, 2])
+def test_featurize_reference_golden_pickles(num_pots):
+    d = np.load(GOLD + "/greedy_cramped_room.npz")
+    states = d["states"].reshape(-1, 16)
+    env = BatchedOvercookedEnv("cramped_room", len(states), horizon=400)
+    env.state.copy_(torch.from_numpy(states))
+    f = _np(env.featurize_state(num_pots=num_pots))
+    exp = d["feat_%d" % num_pots].reshape(len(states), 2, -1)
+    assert f.dtype == np.float32 and np.array_equal(f, exp.astype(np.float32))
+
+
+@pytest.mark.parametrize("path", TRACE_FILES, ids=TRACE_IDS)
+def test_golden_observations(path):
+    tr = Trace(path)
+    d = tr.data
+    st = d["obs_states"]
+    env = _env_for_trace(tr, len(st), 0, horizon=400)
+    env.state.copy_(torch.from_numpy(st))
+    enc = env.lossless_state_encoding(dtype=torch.float32)
+    assert np.array_equal(_np(enc), d["obs_lossless"].astype(np.float32))
+    enc8 = env.lossless_state_encoding(dtype=torch.uint8)
+    assert np.array_equal(_np(enc8).astype(np.int16), d["obs_lossless"])
+    for num_pots in (0, 1, 2, 3):
+        f = _np(env.featurize_state(num_pots=num_pots))
+        assert np.array_equal(f, d["obs_feat_%d" % num_pots].astype(np.float32)), num_pots
+
+
+def _random_actions(rng, T, n, p_interact=0.3):
+    a = rng.randint(0, 6, size=(T, n, 2)).astype(np.int32)
+    a[rng.rand(T, n, 2) < p_interact] = 5
+    return a
+
+
+@pytest.mark.parametrize("io", IOS, ids=IO_IDS)
+@pytest.mark.parametrize("auto_reset", [False, True], ids=["noreset", "autoreset"])
+def test_mixed_layout_rollout_vs_oracle(io, auto_reset):
+    """5 classic layouts in one batch (BASELINE config 3 shape, small), ragged env count so the last
+    tile is partial, horizon crossed: per-step kernel for the first part, fused rollout for the rest."""
+    n, T, horizon = 5 * 811 + 3, 90, 60
+    env = BatchedOvercookedEnv(CLASSIC5, n, horizon=horizon, io=io, auto_reset=auto_reset)
+    assert env.state_words == 32
+    rng = np.random.RandomState(7)
+    acts = _random_actions(rng, T, n)
+    ref_state = _np(env.state).copy()
+    ref = cpu.rollout(env._tab_host, env._starts_host, ref_state, acts, horizon=horizon, flags=int(auto_reset), n_threads=4)
+    d_acts = torch.from_numpy(acts).cuda()
+    split = 40
+    for t in range(split):
+        out = env.step(d_acts[t])
+        for got, want in zip(out, ref):
+            assert np.array_equal(_np(got), want[t]), t
+    out = env.rollout(d_acts[split:].contiguous())
+    for got, want in zip(out, ref):
+        assert np.array_equal(_np(got), want[split:])
+    assert np.array_equal(_np(env.state), ref_state)
+    if not auto_reset:  # finished envs are frozen and flagged
+        assert (ref[3][-1] == L.EVF_STEPPED_DONE).all() and (ref_state[:, 0] == horizon).all()
+
+
+@pytest.mark.parametrize("name,S", [("marshmallow_experiment", 64), ("corridor", 128), ("mdp_test", 16)])
+def test_wide_records_vs_oracle(name, S):
+    n, T = 700, 120
+    env = BatchedOvercookedEnv(name, n, horizon=100, auto_reset=True)
+    assert env.state_words == S
+    rng = np.random.RandomState(S)
+    acts = _random_actions(rng, T, n, 0.35)
+    ref_state = _np(env.state).copy()
+    ref = cpu.rollout(env._tab_host, env._starts_host, ref_state, acts, horizon=100, flags=1, n_threads=4)
+    out = env.rollout(torch.from_numpy(acts).cuda())
+    for got, want in zip(out, ref):
+        assert np.array_equal(_np(got), want)
+    assert np.array_equal(_np(env.state), ref_state)
+    l = env.layouts[0]
+    enc = env.lossless_state_encoding(dtype=torch.float32)
+    assert np.array_equal(_np(enc), cpu.encode_lossless(env._tab_host, ref_state, l.width, l.height, 100).astype(np.float32))
+    f = _np(env.featurize_state(num_pots=2))
+    assert np.array_equal(f.astype(np.float64), cpu.featurize(env._tab_host, lut_bytes([l]), ref_state, 2))
+
+
+def test_mixed_layout_observations_vs_oracle():
+    n = 5 * 600 + 1
+    env = BatchedOvercookedEnv(CLASSIC5, n, horizon=400, auto_reset=True)
+    rng = np.random.RandomState(3)
+    env.rollout(torch.from_numpy(_random_actions(rng, 380, n, 0.4)).cuda())
+    st = _np(env.state)
+    encs = env.lossless_state_encoding(dtype=torch.uint8)
+    assert len(encs) == 5
+    for (b, e, li), enc in zip(env.segments(), encs):
+        l = env.layouts[li]
+        want = cpu.encode_lossless(env._tab_host, st[b:e], l.width, l.height, 400)
+        assert np.array_equal(_np(enc).astype(np.int32), want)
+    f = _np(env.featurize_state(num_pots=2))
+    assert np.array_equal(f.astype(np.float64), cpu.featurize(env._tab_host, lut_bytes(env.layouts), st, 2))
+
+
+def _full_size_check(layouts, n, T, horizon, chunk, seed):
+    """BASELINE-size run, compared in full with the (multi-threaded) oracle, chunk by chunk."""
+    env = BatchedOvercookedEnv(layouts, n, horizon=horizon, auto_reset=True)
+    rng = np.random.RandomState(seed)
+    ref_state = _np(env.state).copy()
+    tot_sparse = 0
+    for c0 in range(0, T, chunk):
+        tc = min(chunk, T - c0)
+        acts = _random_actions(rng, tc, n, 0.25)
+        ref = cpu.rollout(env._tab_host, env._starts_host, ref_state, acts, horizon=horizon, flags=1, n_threads=0)
+        out = env.rollout(torch.from_numpy(acts).cuda())
+        for got, want in zip(out, ref):
+            assert np.array_equal(_np(got), want)
+        tot_sparse += int(ref[0].sum())
+    assert np.array_equal(_np(env.state), ref_state)
+    # size-independent properties: every env has run the same number of transitions; the horizon
+    # was crossed exactly floor(T / horizon) times
+    assert (ref_state[:, 0] == T % horizon).all()
+    return env, ref_state, tot_sparse
+
+
+def test_config2_cramped_room_65536_envs_400_steps():
+    env, st, _ = _full_size_check("cramped_room", 65536, 400, 400, 50, seed=11)
+    assert np.array_equal(st, np.repeat(env._starts_host, 65536, 0))  # all auto-reset to the start record
+
+
+def test_config3_mixed_5_layouts_262144_envs():
+    _full_size_check(CLASSIC5, 262144, 120, 400, 24, seed=12)
+
+
+def test_config4_asymmetric_advantages_one_shard_of_8():
+    _full_size_check("asymmetric_advantages", 1048576 // 8, 200, 400, 40, seed=13)
+
+
+def test_reset_mask_and_noop_properties():
+    n = 3000
+    env = BatchedOvercookedEnv(CLASSIC5, n, horizon=400)
+    rng = np.random.RandomState(5)
+    env.rollout(torch.from_numpy(_random_actions(rng, 50, n)).cuda())
+    before = _np(env.state).copy()
+    # STAY/STAY only advances the clock and the pots
+    stay = torch.full((n, 2), 4, dtype=torch.int32, device="cuda")
+    sp, sh, dn, ev = env.step(stay)
+    after = _np(env.state)
+    assert (after[:, 0] == before[:, 0] + 1).all() and np.array_equal(after[:, 1:4], before[:, 1:4])
+    assert not _np(sp).any() and not _np(sh).any() and not _np(ev).any()
+    # masked reset touches exactly the masked envs, and is idempotent
+    mask = torch.from_numpy((rng.rand(n) < 0.5).astype(np.int32)).cuda()
+    env.reset(mask)
+    once = _np(env.state).copy()
+    env.reset(mask)
+    assert np.array_equal(_np(env.state), once)
+    m = _np(mask).astype(bool)
+    assert np.array_equal(once[~m], after[~m])
+    assert np.array_equal(once[m], env._starts_host[env.env_layout_host[m]])
+    # determinism: same state + same actions -> same everything
+    a = torch.from_numpy(_random_actions(rng, 1, n)[0]).cuda()
+    s0 = env.state.clone()
+    o1 = [x.clone() for x in env.step(a)]
+    s1 = env.state.clone()
+    env.state.copy_(s0)
+    o2 = env.step(a)
+    assert torch.equal(env.state, s1) and all(torch.equal(x, y) for x, y in zip(o1, o2))
+
+
+def test_cuda_graph_capture_of_step():
+    """The C ABI launches on torch's current stream, so a step can be captured in a CUDA graph."""
+    n = 4096
+    env = BatchedOvercookedEnv("cramped_room", n, horizon=400, auto_reset=True)
+    ref_env = BatchedOvercookedEnv("cramped_room", n, horizon=400, auto_reset=True)
+    rng = np.random.RandomState(9)
+    acts = torch.from_numpy(_random_actions(rng, 20, n)).cuda()
+    static_a = acts[0].clone()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        env.step(static_a)  # warm up outside capture
+    torch.cuda.current_stream().wait_stream(s)
+    env.reset()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        env.step(static_a)
+    env.reset()
+    for t in range(20):
+        static_a.copy_(acts[t])
+        g.replay()
+        ref_env.step(acts[t])
+        assert torch.equal(env.state, ref_env.state) and torch.equal(env.sparse, ref_env.sparse)
+        assert torch.equal(env.shaped, ref_env.shaped) and torch.equal(env.events, ref_env.events)
+
+
+def test_bad_arguments_are_reported():
+    lib = _native.lib()
+    env = BatchedOvercookedEnv("cramped_room", 8)
+    rc = lib.ovc_step(env.tables.data_ptr(), 1, env.start_records.data_ptr(), env.state.data_ptr(), 0, 0, 0, 0, 0, 8, 16, 400, 0, 0)
+    assert rc == -1 and b"null" in lib.ovc_last_error()
+    rc = lib.ovc_step(env.tables.data_ptr(), 1, env.start_records.data_ptr(), env.state.data_ptr(), env.state.data_ptr(),
+                      env.sparse.data_ptr(), env.shaped.data_ptr(), env.done.data_ptr(), env.events.data_ptr(), 8, 24, 400, 0, 0)
+    assert rc == -1 and b"state_words" in lib.ovc_last_error()

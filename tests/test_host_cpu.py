@@ -1,0 +1,160 @@
+"""CPU tests of the host logic: layout compiler, value types, the C-ABI library's exports,
+and the multi-process sharding helpers (gloo, world_size 2)."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from overcooked_ai_b200 import _native
+from overcooked_ai_b200 import layout as L
+from overcooked_ai_b200.actions import Action, Direction
+from overcooked_ai_b200.state import ObjectState, OvercookedState, PlayerState, Recipe, SoupState
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_native_library_loads_and_exports_every_declared_symbol():
+    """Every function include/ovc_b200.h declares is exported by the built library (no compute calls)."""
+    import re
+
+    hdr = open(os.path.join(ROOT, "include", "ovc_b200.h")).read()
+    declared = set(re.findall(r"\b(ovc_[a-z_0-9]+)\s*\(", hdr)) - {"ovc_layout", "ovc_feat_lut_entry"}
+    assert declared == set(_native.EXPORTED_SYMBOLS)
+    lib = _native.lib()
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert lib.ovc_abi_version() == 1
+    assert lib.ovc_layout_table_size() == L.LAYOUT_DTYPE.itemsize == 896
+    assert lib.ovc_feat_lut_entry_size() == L.FEAT_LUT_DTYPE.itemsize == 12
+
+
+def test_product_package_never_touches_the_oracle():
+    """The product path must not import / link / execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "overcooked_ai_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("# no oracle", ""), f
+
+
+def test_missing_cuda_device_fails_loudly():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from overcooked_ai_b200.batched import BatchedOvercookedEnv
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        BatchedOvercookedEnv("cramped_room", 4)
+
+
+def test_recipe_tables_of_the_five_classic_layouts():
+    """SURVEY.md §8a table (probed from the reference)."""
+    for name in ("cramped_room", "asymmetric_advantages", "coordination_ring", "forced_coordination"):
+        l = L.compile_layout(name)
+        assert set(l.cook_time[[4, 1, 8, 5, 2, 12, 9, 6, 3]]) == {20}
+        assert l.deliver_value[12] == 20 and l.deliver_value.sum() == 20
+        assert l.best_value[[0, 4, 8, 12]].tolist() == [20] * 4 and l.best_value[[1, 5, 2, 9, 6, 3]].sum() == 0
+    cc = L.compile_layout("counter_circuit")
+    assert cc.cook_time[12] == 45 and cc.base_value[12] == 63
+    assert (cc.deliver_value[5], cc.deliver_value[9], cc.deliver_value[6]) == (68, 55, 47)
+    assert cc.best_value[[0, 4, 1, 8, 5, 2, 12, 9, 6, 3]].tolist() == [68, 68, 68, 55, 68, 47, 0, 55, 47, 0]
+    t = L.compile_layout("mdp_test")
+    assert (t.deliver_value[4], t.deliver_value[12], t.deliver_value[9]) == (10, 30, 50)
+    assert t.cook_time[9] == 6
+
+
+def test_layouts_are_independent_no_global_recipe_state():
+    """Quirk Q1 does not exist here: compiling counter_circuit does not change cramped_room."""
+    a = L.compile_layout("cramped_room")
+    L.compile_layout("counter_circuit")
+    b = L.compile_layout("cramped_room")
+    assert np.array_equal(a.cook_time, b.cook_time) and np.array_equal(a.deliver_value, b.deliver_value)
+
+
+def test_state_words_and_slots():
+    exp = {"cramped_room": (16, 10, 1), "asymmetric_advantages": (32, 25, 2), "coordination_ring": (32, 13, 2),
+           "forced_coordination": (32, 15, 2), "counter_circuit": (32, 25, 2), "corridor": (128, 63, 2)}
+    for name, (S, slots, pots) in exp.items():
+        l = L.compile_layout(name)
+        assert (l.state_words, l.n_slots, l.n_pots) == (S, slots, pots)
+        assert l.slot_positions[:pots] == l.pot_locations
+    with pytest.raises(ValueError):
+        L.compile_layout("cramped_room_single")  # 1 player
+    with pytest.raises(ValueError):
+        L.compile_layout("tutorial_3")  # order_bonus = inf: rewards are not integers
+
+
+def test_start_records():
+    tab, starts, S = L.build_tables([L.compile_layout(n) for n in ("cramped_room", "counter_circuit")])
+    assert S == 32 and tab.shape == (2, 896) and starts.shape == (2, 32)
+    # cramped_room: P0 (1,2) P1 (3,1) facing north, nothing held, t = 0
+    assert starts[0, :4].tolist() == [0, (2 << 4) | 1, (1 << 4) | 3, 0] and not starts[0, 4:].any()
+    assert starts[1, 3] == 1
+
+
+def test_pack_unpack_objects_and_soups():
+    l = L.compile_layout("mdp_test")
+    soup = SoupState((2, 0), [ObjectState("onion", (2, 0)), ObjectState("tomato", (2, 0))], cooking_tick=3)
+    held = SoupState.get_soup((1, 1), 2, 1, cooking_tick=6, cook_time=6)
+    st = OvercookedState(
+        [PlayerState((1, 1), Direction.EAST, held), PlayerState((3, 1), Direction.WEST, ObjectState("dish", (3, 1)))],
+        {(2, 0): soup, (0, 0): ObjectState("dish", (0, 0)), (4, 0): ObjectState("tomato", (4, 0))},
+        bonus_orders=l.start_bonus_orders, all_orders=l.start_all_orders, timestep=17)
+    rec = L.pack_state(l, st)
+    assert rec[0] == 17 and (rec[3] >> 8) & 0xFF == 1  # one loose dish
+    back = L.unpack_state(l, rec)
+    assert back == st and back.get_object((2, 0)).ingredients == ["onion", "tomato"]
+    assert back.get_object((2, 0)).cook_time == 4 and back.players[0].held_object.is_ready
+    # ordered ingredients survive (quirk Q6)
+    soup2 = SoupState((2, 0), [ObjectState("tomato", (2, 0)), ObjectState("onion", (2, 0))], cooking_tick=3)
+    assert L.pack_object(soup) != L.pack_object(soup2)
+    # a tick with bit 13 set lands in the sign bit of the player word and still round-trips
+    big = SoupState.get_soup((1, 1), 3, 0, cooking_tick=9000, cook_time=6)
+    st2 = OvercookedState([PlayerState((1, 1), Direction.EAST, big), PlayerState((3, 1), Direction.WEST)], {},
+                          bonus_orders=l.start_bonus_orders, all_orders=l.start_all_orders)
+    rec2 = L.pack_state(l, st2)
+    assert rec2[1] < 0 and L.unpack_state(l, rec2).players[0].held_object._cooking_tick == 9000
+
+
+def test_value_types_wire_format():
+    d = {"players": [{"position": [1, 2], "orientation": [0, -1], "held_object": {"name": "onion", "position": [1, 2]}},
+                     {"position": [3, 1], "orientation": [1, 0], "held_object": None}],
+         "objects": [{"name": "soup", "position": [2, 0], "_ingredients": [{"name": "onion", "position": [2, 0]}],
+                      "cooking_tick": -1, "is_cooking": False, "is_ready": False, "is_idle": True, "cook_time": -1,
+                      "_cooking_tick": -1}],
+         "bonus_orders": [], "all_orders": [{"ingredients": ["onion", "onion", "onion"]}], "timestep": 3}
+    st = OvercookedState.from_dict(d)
+    assert st.players[0].held_object == ObjectState("onion", (1, 2)) and st.timestep == 3
+    out = st.to_dict()
+    assert out["objects"][0]["cook_time"] == -1 and out["objects"][0]["is_idle"] is True
+    assert OvercookedState.from_dict(out) == st and st.deepcopy() == st
+    assert Recipe(["onion", "tomato"]) == Recipe(["tomato", "onion"]) and len(Recipe.all_recipes()) == 9
+    assert Action.to_index("interact") == 5 and Action.to_index((0, 0)) == 4 and Action.to_index([0, -1]) == 0
+    with pytest.raises(ValueError):
+        Action.to_index((1, 1))
+
+
+def test_layout_file_in_reference_format(tmp_path):
+    p = tmp_path / "tiny.layout"
+    p.write_text('{"grid": """XPDX\n             O12S\n             XXXX""", "start_all_orders": [{"ingredients": ["onion"]}], "cook_time": 5, "delivery_reward": 7}')
+    l = L.compile_layout(str(p))
+    assert (l.width, l.height, l.n_pots) == (4, 3, 1) and l.cook_time[4] == 5 and l.deliver_value[4] == 7
+    assert l.deliver_value[8] == 0 and l.best_value[0] == 7
+
+
+def test_sharding_world_size_2_gloo():
+    """Env-index sharding + seed broadcast + throughput all-reduce over gloo, 2 processes (the N>1 path
+    of bench.py without a GPU)."""
+    script = os.path.join(ROOT, "tests", "_dist_worker.py")
+    port = 29500 + os.getpid() % 2000
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), script]
+    env = dict(os.environ, PYTHONPATH=ROOT, OMP_NUM_THREADS="1")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "DIST_OK" in out.stdout
