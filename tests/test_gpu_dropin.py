@@ -118,7 +118,7 @@ def test_scripted_soup_cycle_cramped_room():
     res = p0(interact)
     assert res[-1][3]["shaped_r_by_agent"] == [5, 0] and env.state.players[0].held_object.name == "soup"
     assert not env.state.has_object((2, 0))
-    res = p0(e, s, s, interact)        # to (3,1) -> (3,2), face the serving cell (3,3), deliver
+    res = p0(s, e, s, interact)        # (2,1) -> (2,2) -> (3,2), face the serving cell (3,3), deliver (P1 sits at (3,1))
     st, r, done, info = res[-1]
     assert r == 20 and info["sparse_r_by_agent"] == [20, 0] and st.players[0].held_object is None
     assert env.game_stats["soup_delivery"][0] == [st.timestep - 1]
