@@ -160,6 +160,10 @@ typedef struct ovc_feat_lut_entry {
 
 /* flags for ovc_step / ovc_rollout */
 #define OVC_F_AUTO_RESET 1 /* an env whose new timestep reaches horizon is set back to its start record */
+/* launch the step kernel with programmatic dependent launch (stream serialization attribute): its
+ * prologue (barrier init, layout-table fetch) overlaps the tail of the previous kernel in the stream;
+ * every read of state / actions happens after griddepcontrol.wait, so results are unchanged. */
+#define OVC_F_PDL 2
 /* bits 8-11 select the record I/O strategy of the step kernel (0 = library default):
  *   1 = 2-D tensor-map TMA tile with hardware swizzle, 2 = 1-D bulk TMA (linear tile),
  *   3 = direct vectorised global loads/stores (no staging).  All produce identical results. */

@@ -40,7 +40,7 @@ def _as_layouts(layouts, mdp_params):
 
 class BatchedOvercookedEnv(object):
     def __init__(self, layouts, n_envs, horizon=400, device="cuda", auto_reset=False, state_words=None,
-                 io=_native.IO_DEFAULT, env_layout=None, mdp_params=None):
+                 io=_native.IO_DEFAULT, env_layout=None, mdp_params=None, pdl=False):
         """
         layouts      layout name / CompiledLayout / OvercookedGridworld, or a list of them (mixed batch)
         n_envs       number of environments on THIS device
@@ -63,6 +63,7 @@ class BatchedOvercookedEnv(object):
         self.horizon = int(horizon) if horizon < 2**31 else 0
         self.auto_reset = bool(auto_reset)
         self.io = int(io)
+        self.pdl = bool(pdl)  # programmatic dependent launch for back-to-back step() calls / graphs
         tab, starts, S = L.build_tables(self.layouts, state_words)
         assert tab.shape[1] == self._lib.ovc_layout_table_size(), "layout table size mismatch with the native library"
         self.state_words = S
@@ -91,7 +92,8 @@ class BatchedOvercookedEnv(object):
 
     # ---------------------------------------------------------------------------------------------
     def _flags(self):
-        return (_native.F_AUTO_RESET if self.auto_reset else 0) | (self.io << _native.F_IO_SHIFT)
+        return ((_native.F_AUTO_RESET if self.auto_reset else 0) | (_native.F_PDL if self.pdl else 0)
+                | (self.io << _native.F_IO_SHIFT))
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream

@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/ovc_b200.h"
@@ -74,6 +75,9 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"((uint64_t)map),
                  "r"(c0), "r"(c1), "r"(smem_u32(src))
                  : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
 __device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -136,6 +140,7 @@ struct StepArgs {
     const int32_t *actions;
     int32_t *sparse, *shaped, *done, *events;
     long long n_envs;
+    int n_layouts;
     int n_steps;  // rollout only
     int horizon, flags;
 };
@@ -147,7 +152,11 @@ __device__ __forceinline__ void write_outputs(const StepArgs &a, long long idx, 
     reinterpret_cast<int2 *>(a.events)[idx] = make_int2((int)o.ev0, (int)o.ev1);
 }
 
-// One CTA = one tile of TILE records.  T == 1: the step kernel; T > 1: the fused rollout.
+// Shared-memory plan of one CTA (dynamic, 1024-byte aligned so the TMA swizzle pattern lines up with
+// the tile offsets): [ tile: TILE*S*4 bytes ][ layout tables: n_tbl*896 bytes ][ mbarrier: 8 bytes ].
+constexpr int MAX_SMEM_LAYOUTS = 8;
+
+// One CTA = one tile of TILE records.  n_steps == 1: the step kernel K1; n_steps > 1: the fused rollout K5.
 template <int S, int IO>
 __global__ void __launch_bounds__(Cfg<S>::TILE)
 step_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
@@ -158,51 +167,66 @@ step_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
     const int T = a.n_steps;
 
     if (IO == 3) {
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         if (!live) return;
         GlobalRec r{a.state + env * S};
+        const TblG tb{reinterpret_cast<const char *>(a.layouts)};
         for (int t = 0; t < T; t++) {
             const long long idx = (long long)t * a.n_envs + env;
             const int2 act = reinterpret_cast<const int2 *>(a.actions)[idx];
             StepOut o;
-            step_core(r, a.layouts, a.start_records, S, act.x, act.y, a.horizon, a.flags, o);
+            step_core(r, tb, a.start_records, S, act.x, act.y, a.horizon, a.flags, o);
             write_outputs(a, idx, o);
         }
         return;
     }
 
-    extern __shared__ char smem_raw[];
-    __shared__ uint64_t bar;
-    char *tile = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) char smem[];
+    char *tile = smem;
+    const int n_tbl = a.n_layouts <= MAX_SMEM_LAYOUTS ? a.n_layouts : 0;  // 0: tables stay in global memory
+    const uint32_t tbl_bytes = (uint32_t)n_tbl * (uint32_t)sizeof(ovc_layout_t);
+    char *tbl = smem + C::TILE_BYTES;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + C::TILE_BYTES + MAX_SMEM_LAYOUTS * sizeof(ovc_layout_t));
     const long long rem = a.n_envs - env0;
     const uint32_t live_bytes = (uint32_t)((rem < C::TILE ? rem : C::TILE) * S * 4);
 
     if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        if (IO == 1) {
-            mbar_expect_tx(&bar, C::TILE_BYTES);  // out-of-range rows are zero filled and still counted
-            tma_load_2d(tile, &tmap, 0, (int)(env0 * C::ROWS_PER_ENV), &bar);
-        } else {
-            mbar_expect_tx(&bar, live_bytes);
-            bulk_load_1d(tile, a.state + env0 * S, live_bytes, &bar);
-        }
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, (IO == 1 ? (uint32_t)C::TILE_BYTES : live_bytes) + tbl_bytes);
+        if (IO == 1) prefetch_tmap(&tmap);
+        if (n_tbl) bulk_load_1d(tbl, a.layouts, tbl_bytes, bar);  // the constant table rides on the same barrier
+    }
+    // Programmatic dependent launch: everything above touches only constants, so it may overlap the
+    // previous kernel of the stream; state and actions are read after the dependency resolves.
+    // (Both instructions are no-ops when the kernel was launched without the PDL attribute.)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x == 0) {
+        if (IO == 1) tma_load_2d(tile, &tmap, 0, (int)(env0 * C::ROWS_PER_ENV), bar);  // out-of-range rows: zero fill, still counted
+        else bulk_load_1d(tile, a.state + env0 * S, live_bytes, bar);
     }
     // the first action fetch overlaps the tile load
     int2 act = make_int2(OVC_A_STAY, OVC_A_STAY);
     if (live) act = reinterpret_cast<const int2 *>(a.actions)[env];
     __syncthreads();  // barrier initialised and visible before anyone polls it
-    mbar_wait(&bar, 0);
+    mbar_wait(bar, 0);
 
     if (live) {
         SmemRec<S, IO == 1 ? C::SWZ : 0> r{tile, (uint32_t)threadIdx.x * S * 4};
-        for (int t = 0; t < T; t++) {
-            const long long idx = (long long)t * a.n_envs + env;
-            int2 nxt = act;
-            if (t + 1 < T) nxt = reinterpret_cast<const int2 *>(a.actions)[idx + a.n_envs];  // prefetch
-            StepOut o;
-            step_core(r, a.layouts, a.start_records, S, act.x, act.y, a.horizon, a.flags, o);
-            write_outputs(a, idx, o);
-            act = nxt;
-        }
+        auto run = [&](auto tb) {
+            for (int t = 0; t < T; t++) {
+                const long long idx = (long long)t * a.n_envs + env;
+                int2 nxt = act;
+                if (t + 1 < T) nxt = reinterpret_cast<const int2 *>(a.actions)[idx + a.n_envs];  // prefetch
+                StepOut o;
+                step_core(r, tb, a.start_records, S, act.x, act.y, a.horizon, a.flags, o);
+                write_outputs(a, idx, o);
+                act = nxt;
+            }
+        };
+        if (n_tbl) run(TblS{tbl});
+        else run(TblG{reinterpret_cast<const char *>(a.layouts)});
     }
     fence_async_smem();  // generic-proxy writes -> visible to the async proxy (TMA store)
     __syncthreads();
@@ -266,33 +290,37 @@ static int make_tmap(CUtensorMap *m, int32_t *state, long long n_envs) {
     return OVC_OK;
 }
 
+template <int S, int IO>
+static cudaError_t launch_one(const CUtensorMap &tmap, const StepArgs &a, unsigned grid, size_t smem, cudaStream_t st) {
+    using C = Cfg<S>;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(C::TILE), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (a.flags & OVC_F_PDL) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, step_kernel<S, IO>, tmap, a);
+}
+
 template <int S>
 static int launch_step(const StepArgs &a, int io, cudaStream_t st) {
     using C = Cfg<S>;
     const unsigned grid = (unsigned)((a.n_envs + C::TILE - 1) / C::TILE);
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
-    const size_t smem = io == 3 ? 0 : C::TILE_BYTES + 1024;
+    const size_t smem = io == 3 ? 0 : C::TILE_BYTES + MAX_SMEM_LAYOUTS * sizeof(ovc_layout_t) + 16;
+    cudaError_t e;
     if (io == 1) {
         int rc = make_tmap<S>(&tmap, a.state, a.n_envs);
         if (rc) return rc;
-        static bool attr = false;
-        if (!attr) {
-            cudaFuncSetAttribute(step_kernel<S, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr = true;
-        }
-        step_kernel<S, 1><<<grid, C::TILE, smem, st>>>(tmap, a);
+        e = launch_one<S, 1>(tmap, a, grid, smem, st);
     } else if (io == 2) {
-        static bool attr = false;
-        if (!attr) {
-            cudaFuncSetAttribute(step_kernel<S, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr = true;
-        }
-        step_kernel<S, 2><<<grid, C::TILE, smem, st>>>(tmap, a);
+        e = launch_one<S, 2>(tmap, a, grid, smem, st);
     } else {
-        step_kernel<S, 3><<<grid, C::TILE, 0, st>>>(tmap, a);
+        e = launch_one<S, 3>(tmap, a, grid, smem, st);
     }
-    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "step kernel launch");
     return OVC_OK;
 }
@@ -323,7 +351,7 @@ static int step_impl(const void *layouts, int n_layouts, const int32_t *start_re
     if (io < 1 || io > 3) return fail(OVC_E_BADARG, "unknown record I/O strategy%s %lld", "", io);
     if (io == 1 && (n_envs * (S / (S == 16 ? 16 : 32))) > 0x7FFFFFFFLL) io = 2;  // tensor coordinates are int32
     StepArgs a{(const ovc_layout_t *)layouts, start_records, state, actions, sparse, shaped, done, events,
-               n_envs, n_steps, horizon, flags};
+               n_envs, n_layouts, n_steps, horizon, flags};
     cudaStream_t st = (cudaStream_t)stream;
     switch (S) {
     case 16: return launch_step<16>(a, io, st);

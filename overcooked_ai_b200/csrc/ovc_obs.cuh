@@ -7,8 +7,9 @@
 //     async store (cp.async.bulk.global.shared::cta, SASS UBLKCP), so every HBM write is a full,
 //     coalesced line no matter how scattered the non-zeros are.  Write-bound: 2*W*H*26*sizeof(T)
 //     bytes per environment (4160 B fp32 on cramped_room) against 64-128 B read.
-// K3  featurize_kernel   featurize_state (:2579-2898) for the default planner parameters; same
-//     shared-memory-build + bulk-store structure, [env][player][F] float32.
+// K3  featurize_kernel   featurize_state (:2579-2898) for the default planner parameters,
+//     [env][player][F] float32: per-player feature blocks staged feature-major in shared memory
+//     (conflict free), then assembled and written as coalesced float4 rows.
 #pragma once
 
 namespace ovc {
@@ -157,7 +158,13 @@ static int encode_lossless_impl(const ovc_layout_t *layouts, const int32_t *stat
     a.S = S, a.W = W, a.H = H, a.horizon = horizon;
     a.obs_elems = 2 * W * H * N_PLANES;
     const int obs_bytes = a.obs_elems * esize;
-    const int BUF = 48 * 1024;                       // 4 CTAs per SM keep loads, fills and stores overlapped
+    static int buf_kb = 0;  // tile buffer size: 48 KB = 4 CTAs per SM keep loads, fills and stores overlapped
+    if (buf_kb == 0) {
+        const char *env = getenv("OVC_ENC_BUF_KB");  // tuning knob for experiments
+        buf_kb = env ? atoi(env) : 48;
+        if (buf_kb < 4 || buf_kb > 200) buf_kb = 48;
+    }
+    const int BUF = buf_kb * 1024;
     const int mult = 16 / gcd_int(16, obs_bytes);    // tiles must start 16-byte aligned in the output
     int E = BUF / obs_bytes;
     E -= E % mult;
@@ -184,6 +191,14 @@ static int encode_lossless_impl(const ovc_layout_t *layouts, const int32_t *stat
 // ------------------------------------------------------------------------------------------------
 // K3 featurize_state
 // ------------------------------------------------------------------------------------------------
+// Two phases per CTA (tile of E environments = 2E player views):
+//   1. one thread per (environment, player) computes that player's feature block (26 + 10*num_pots
+//      small integers) into shared memory in FEATURE-MAJOR order blk[feature][view] — consecutive
+//      lanes hit consecutive words, so the writes are bank-conflict free (a view-major tile would
+//      put every lane on the same bank: the view stride F is a multiple of 32 words);
+//   2. all threads assemble the output rows [own block, other block, other-self offset, self position]
+//      (:2877-2896) as float4 and write them straight to global memory, consecutive threads ->
+//      consecutive 16-byte pieces of the contiguous output tile (fully coalesced, full lines).
 struct FeatArgs {
     const ovc_layout_t *layouts;
     const ovc_feat_lut_entry_t *lut;
@@ -193,14 +208,16 @@ struct FeatArgs {
     int S, num_pots, B, F, E;
 };
 
-// Block of player j (:2748-2840) -> own[0..B) (view j) and other[0..B) (view 1-j, offset B).
+constexpr int FEAT_E = 64;              // environments per tile
+constexpr int FEAT_LD = 2 * FEAT_E + 1;  // odd leading dimension: phase-2 reads (stride LD) stay conflict free
+
+// Block of player `me` (:2748-2840), written as int16 blk[n * FEAT_LD + view].
 __device__ __forceinline__ void feat_block(const FeatArgs &a, const ovc_layout_t *__restrict__ L,
                                            const ovc_feat_lut_entry_t *__restrict__ le, const int32_t *__restrict__ rec,
-                                           unsigned me, float *own, float *other) {
+                                           unsigned me, short *blk) {
     int n = 0;
     auto put = [&](int v) {
-        own[n] = (float)v;
-        other[n] = (float)v;
+        blk[n * FEAT_LD] = (short)v;
         n++;
     };
     const int x = me & 15, y = (me >> 4) & 15, ori = (me >> 8) & 3;
@@ -250,37 +267,48 @@ __device__ __forceinline__ void feat_block(const FeatArgs &a, const ovc_layout_t
         put((__ldg(&L->cell[(((y << 4) | x) + dir_delta(d)) & 0xFF]) & 7) != OVC_T_FLOOR);
 }
 
-__global__ void __launch_bounds__(128) featurize_kernel(const FeatArgs a) {
-    extern __shared__ char smem_raw[];
-    float *buf = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-    const long long env0 = (long long)blockIdx.x * a.E;
+__global__ void __launch_bounds__(256) featurize_kernel(const FeatArgs a) {
+    extern __shared__ __align__(16) char fsm[];
+    short *blk = reinterpret_cast<short *>(fsm);      // [B][FEAT_LD] int16 (cook times go up to 16382)
+    short *posx = blk + (size_t)a.B * FEAT_LD;        // [2E] player x
+    short *posy = posx + 2 * FEAT_E;                  // [2E] player y
+    const long long env0 = (long long)blockIdx.x * FEAT_E;
     const long long rem = a.n_envs - env0;
-    const int ne = (int)(rem < a.E ? rem : a.E);
-    // one thread per (environment, player)
-    for (int it = threadIdx.x; it < ne * 2; it += blockDim.x) {
-        const int el = it >> 1, j = it & 1;
+    const int ne = (int)(rem < FEAT_E ? rem : FEAT_E);
+    const int nv = ne * 2;
+    // ---- phase 1: one thread per view ----
+    if ((int)threadIdx.x < nv) {
+        const int v = threadIdx.x, el = v >> 1, j = v & 1;
         const int32_t *__restrict__ rec = a.state + (env0 + el) * a.S;
         const int lid = __ldg(rec + 3) & 0xFF;
         const ovc_layout_t *__restrict__ L = a.layouts + lid;
-        const unsigned me = (unsigned)__ldg(rec + 1 + j), ot = (unsigned)__ldg(rec + 2 - j);
+        const unsigned me = (unsigned)__ldg(rec + 1 + j);
         const ovc_feat_lut_entry_t *le = a.lut + (size_t)lid * 1024 + ((me & 0xFF) << 2 | ((me >> 8) & 3));
-        float *view_me = buf + ((size_t)el * 2 + j) * a.F;
-        float *view_ot = buf + ((size_t)el * 2 + (1 - j)) * a.F;
-        feat_block(a, L, le, rec, me, view_me, view_ot + a.B);
-        // :2877-2896: [own block, other block, other - self, self position]
-        view_me[2 * a.B + 0] = (float)((int)(ot & 15) - (int)(me & 15));
-        view_me[2 * a.B + 1] = (float)((int)((ot >> 4) & 15) - (int)((me >> 4) & 15));
-        view_me[2 * a.B + 2] = (float)(me & 15);
-        view_me[2 * a.B + 3] = (float)((me >> 4) & 15);
+        feat_block(a, L, le, rec, me, blk + v);
+        posx[v] = (short)(me & 15);
+        posy[v] = (short)((me >> 4) & 15);
     }
-    const size_t tile_bytes = (size_t)ne * 2 * a.F * sizeof(float);
-    char *dst = reinterpret_cast<char *>(a.out) + (size_t)env0 * 2 * a.F * sizeof(float);
-    fence_async_smem();
     __syncthreads();
-    if (threadIdx.x == 0) {  // 2*F*4 bytes per env is a multiple of 16 for every num_pots (F = 20*np + 56)
-        bulk_store_1d(dst, buf, (uint32_t)tile_bytes);
-        bulk_commit();
-        bulk_wait_read<0>();
+    // ---- phase 2: assemble rows, float4 per thread, coalesced ----
+    const int G = a.F / 4;  // F = 20*num_pots + 56 is a multiple of 4
+    float4 *dst = reinterpret_cast<float4 *>(a.out + (size_t)env0 * 2 * a.F);
+    for (int idx = threadIdx.x; idx < nv * G; idx += blockDim.x) {
+        const int v = idx / G, g = idx - v * G;
+        float r[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int f = g * 4 + q;
+            int val;
+            if (f < a.B) val = blk[f * FEAT_LD + v];
+            else if (f < 2 * a.B) val = blk[(f - a.B) * FEAT_LD + (v ^ 1)];
+            else {
+                const int z = f - 2 * a.B;  // 0,1: other - self; 2,3: self position
+                const int sx = posx[v], sy = posy[v];
+                val = z == 0 ? posx[v ^ 1] - sx : z == 1 ? posy[v ^ 1] - sy : z == 2 ? sx : sy;
+            }
+            r[q] = (float)val;
+        }
+        dst[idx] = make_float4(r[0], r[1], r[2], r[3]);
     }
 }
 
@@ -293,11 +321,14 @@ static int featurize_impl(const ovc_layout_t *layouts, const ovc_feat_lut_entry_
     FeatArgs a;
     a.layouts = layouts, a.lut = lut, a.state = state, a.out = out, a.n_envs = n_envs, a.S = S;
     a.num_pots = num_pots, a.B = 10 * num_pots + 26, a.F = 2 * a.B + 4;
-    a.E = 64;  // 64 envs x 2 views x F floats: 48 KB at num_pots = 2
-    const size_t smem = (size_t)a.E * 2 * a.F * sizeof(float) + 128;
-    cudaError_t e = cudaFuncSetAttribute(featurize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e, "featurize kernel attribute");
-    featurize_kernel<<<(unsigned)((n_envs + a.E - 1) / a.E), 128, smem, st>>>(a);
+    a.E = FEAT_E;
+    const size_t smem = 2 * ((size_t)a.B * FEAT_LD + 4 * FEAT_E) + 16;
+    cudaError_t e;
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(featurize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "featurize kernel attribute");
+    }
+    featurize_kernel<<<(unsigned)((n_envs + FEAT_E - 1) / FEAT_E), 256, smem, st>>>(a);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "featurize kernel launch");
     return OVC_OK;

@@ -14,7 +14,28 @@
 
 #include "../../include/ovc_b200.h"
 
+#include <stddef.h>
+
 namespace ovc {
+
+// Layout-table accessors.  TblG reads the ovc_layout_t records from global memory through the
+// read-only path; TblS reads a copy staged in shared memory (the step kernel bulk-copies the table next
+// to the record tile, so a launch — which always starts with a cold L1 — pays no serial L2 round trips).
+struct TblG {
+    const char *base;
+    __device__ __forceinline__ TblG at(unsigned id) const { return TblG{base + (size_t)id * sizeof(ovc_layout_t)}; }
+    __device__ __forceinline__ int i32(int off) const { return __ldg(reinterpret_cast<const int *>(base + off)); }
+    __device__ __forceinline__ unsigned u16(int off) const { return __ldg(reinterpret_cast<const unsigned short *>(base + off)); }
+    __device__ __forceinline__ unsigned u8(int off) const { return __ldg(reinterpret_cast<const unsigned char *>(base + off)); }
+};
+struct TblS {
+    const char *base;  // derived from the __shared__ array, so these compile to LDS
+    __device__ __forceinline__ TblS at(unsigned id) const { return TblS{base + id * (uint32_t)sizeof(ovc_layout_t)}; }
+    __device__ __forceinline__ int i32(int off) const { return *reinterpret_cast<const int *>(base + off); }
+    __device__ __forceinline__ unsigned u16(int off) const { return *reinterpret_cast<const unsigned short *>(base + off); }
+    __device__ __forceinline__ unsigned u8(int off) const { return *reinterpret_cast<const unsigned char *>(base + off); }
+};
+#define OVC_OFF(field) ((int)offsetof(ovc_layout_t, field))
 
 struct StepOut {
     int sparse;
@@ -41,14 +62,15 @@ __device__ __forceinline__ int recipe_row(unsigned code) {
     return ((n - nt) << 2) | nt;
 }
 
-__device__ __forceinline__ bool soup_ready(const ovc_layout_t *__restrict__ L, unsigned code) {
+template <class TB>
+__device__ __forceinline__ bool soup_ready(const TB &L, unsigned code) {
     unsigned tp1 = (code >> 8) & 0x3FFF;  // _cooking_tick + 1, 0 = idle
-    return (code & 7) == OVC_O_SOUP && tp1 != 0 && (int)(tp1 - 1) >= __ldg(&L->cook_time[recipe_row(code)]);  // :537-540
+    return (code & 7) == OVC_O_SOUP && tp1 != 0 && (int)(tp1 - 1) >= L.i32(OVC_OFF(cook_time) + 4 * recipe_row(code));  // :537-540
 }
 
 // One player's INTERACT (the body of the loop at :1446-1577) on the live record.
-template <class R>
-__device__ __forceinline__ void interact_one(R &r, const ovc_layout_t *__restrict__ L, unsigned &p_me,
+template <class R, class TB>
+__device__ __forceinline__ void interact_one(R &r, const TB &L, unsigned &p_me,
                                              const unsigned p_other, unsigned &misc, const int n_full,
                                              const int n_dishable, const bool all_full, int &sparse, int &shaped_me,
                                              unsigned &ev_me) {
@@ -57,7 +79,7 @@ __device__ __forceinline__ void interact_one(R &r, const ovc_layout_t *__restric
     const int held_t = held & 7;
     const int other_t = (p_other >> 10) & 7;
     const int fpos = ((int)(me & 0xFF) + dir_delta((me >> 8) & 3)) & 0xFF;
-    const unsigned cell = __ldg(&L->cell[fpos]);
+    const unsigned cell = L.u16(OVC_OFF(cell) + 2 * fpos);
     const int terr = cell & 7;
     const int w_idx = 4 + (int)(cell >> 8);
     unsigned cw = 0;
@@ -91,7 +113,7 @@ __device__ __forceinline__ void interact_one(R &r, const ovc_layout_t *__restric
         }
     } else if (terr == OVC_T_POT) {
         if (held_t == 0) {  // :1515-1522 start cooking an idle, non-empty soup (new dynamics only)
-            if (!(__ldg(&L->flags) & OVC_LAYOUT_OLD_DYNAMICS) && (cw & 7) == OVC_O_SOUP &&
+            if (!(L.i32(OVC_OFF(flags)) & OVC_LAYOUT_OLD_DYNAMICS) && (cw & 7) == OVC_O_SOUP &&
                 ((cw >> 8) & 0x3FFF) == 0 && ((cw >> 3) & 3) != 0)
                 new_cw = cw | (1u << 8);  // begin_cooking: tick := 0
         } else if (held_t == OVC_O_DISH) {
@@ -99,16 +121,16 @@ __device__ __forceinline__ void interact_one(R &r, const ovc_layout_t *__restric
                 e = 1u << OVC_EV_SOUP_PICKUP;
                 held = cw;
                 new_cw = 0;
-                shaped_me += __ldg(&L->rew_soup_pickup);
+                shaped_me += L.i32(OVC_OFF(rew_soup_pickup));
             }
         } else if (held_t <= OVC_O_TOMATO) {  // :1541-1568 add an ingredient
             unsigned soup = cw ? cw : (unsigned)OVC_O_SOUP;  // empty pot: a fresh soup first (:1544-1546)
             const int n = (soup >> 3) & 3;
             if (((soup >> 8) & 0x3FFF) == 0 && n < 3) {  // not is_full :547-551
                 const bool tom = held_t == OVC_O_TOMATO;
-                const int old_val = __ldg(&L->best_value[n ? recipe_row(soup) : 0]);
+                const int old_val = L.i32(OVC_OFF(best_value) + 4 * (n ? recipe_row(soup) : 0));
                 soup = (soup & ~(3u << 3)) | ((unsigned)(n + 1) << 3) | ((unsigned)tom << (5 + n));
-                const int new_val = __ldg(&L->best_value[recipe_row(soup)]);
+                const int new_val = L.i32(OVC_OFF(best_value) + 4 * recipe_row(soup));
                 // log_object_potting :2121-2140 + is_potting_* :2256-2308 (+ potting_onion again at :1567)
                 e = 1u << (tom ? OVC_EV_POTTING_TOMATO : OVC_EV_POTTING_ONION);
                 const int sh = tom ? 1 : 0;  // <kind>_tomato_potting = <kind>_onion_potting + 1
@@ -116,7 +138,7 @@ __device__ __forceinline__ void interact_one(R &r, const ovc_layout_t *__restric
                 if (new_val > 0) e |= 1u << (OVC_EV_VIABLE_ONION_POTTING + sh);
                 if (old_val > 0 && new_val == 0) e |= 1u << (OVC_EV_CATASTROPHIC_ONION_POTTING + sh);
                 if (old_val == 0) e |= 1u << (OVC_EV_USELESS_ONION_POTTING + sh);
-                shaped_me += __ldg(&L->rew_placement_in_pot);
+                shaped_me += L.i32(OVC_OFF(rew_placement_in_pot));
                 new_cw = soup;
                 held = 0;
             }
@@ -132,13 +154,13 @@ __device__ __forceinline__ void interact_one(R &r, const ovc_layout_t *__restric
             e = 1u << OVC_EV_DISH_PICKUP;
             if (((misc >> 8) & 0xFF) == 0 && (other_t == OVC_O_DISH) < n_dishable) {
                 e |= 1u << OVC_EV_USEFUL_DISH_PICKUP;
-                shaped_me += __ldg(&L->rew_dish_pickup);
+                shaped_me += L.i32(OVC_OFF(rew_dish_pickup));
             }
             held = OVC_O_DISH;
         }
     } else if (terr == OVC_T_SERVE && held_t == OVC_O_SOUP) {  // :1570-1577, deliver_soup :1631-1642
         const int row = recipe_row(held);
-        sparse += __ldg(&L->deliver_value[row]);
+        sparse += L.i32(OVC_OFF(deliver_value) + 4 * row);
         e = (1u << OVC_EV_SOUP_DELIVERY) | ((unsigned)row << OVC_EV_RECIPE_SHIFT);
         held = 0;
     }
@@ -147,8 +169,8 @@ __device__ __forceinline__ void interact_one(R &r, const ovc_layout_t *__restric
     ev_me = e;
 }
 
-template <class R>
-__device__ __forceinline__ void step_core(R &r, const ovc_layout_t *__restrict__ layouts,
+template <class R, class TB>
+__device__ __forceinline__ void step_core(R &r, const TB &layouts,
                                           const int32_t *__restrict__ start_records, int S, int a0, int a1,
                                           int horizon, int flags, StepOut &o) {
     int4 h = r.ld4(0);
@@ -160,9 +182,9 @@ __device__ __forceinline__ void step_core(R &r, const ovc_layout_t *__restrict__
     }
     unsigned p[2] = {(unsigned)h.y, (unsigned)h.z};
     unsigned misc = (unsigned)h.w;
-    const ovc_layout_t *__restrict__ L = layouts + (misc & 0xFF);
-    const int n_pots = __ldg(&L->n_pots);
-    const int act[2] = {a0, a1};
+    const TB L = layouts.at(misc & 0xFF);
+    const int n_pots = L.i32(OVC_OFF(n_pots));
+    const int lflags = L.i32(OVC_OFF(flags));
 
     // ---- pot snapshot, taken once before either player acts (get_pot_states :1809-1838 at :1439,
     //      quirk Q3).  Only two aggregates are ever consumed:
@@ -187,9 +209,24 @@ __device__ __forceinline__ void step_core(R &r, const ovc_layout_t *__restrict__
     int shaped[2] = {0, 0};
     unsigned ev[2] = {0u, 0u};
 
-    // ---- resolve_interacts :1446-1577: player 0 then player 1 on the same live record ----
-    if (a0 == OVC_A_INTERACT) interact_one(r, L, p[0], p[1], misc, n_full, n_dishable, all_full, sparse, shaped[0], ev[0]);
-    if (a1 == OVC_A_INTERACT) interact_one(r, L, p[1], p[0], misc, n_full, n_dishable, all_full, sparse, shaped[1], ev[1]);
+    // ---- resolve_interacts :1446-1577: player 0 then player 1 on the same live record.  The body
+    //      is emitted once: the second trip runs it with the players' roles swapped (two swaps put
+    //      everything back), which halves the code the instruction cache has to hold. ----
+    {
+        unsigned pa = p[0], pb = p[1], ea = 0u, eb = 0u;
+        int sa = 0, sb = 0, aa = a0, ab = a1;
+#pragma unroll 1
+        for (int trip = 0; trip < 2; trip++) {
+            if (aa == OVC_A_INTERACT) interact_one(r, L, pa, pb, misc, n_full, n_dishable, all_full, sparse, sa, ea);
+            unsigned tu;
+            int ti;
+            tu = pa, pa = pb, pb = tu;
+            tu = ea, ea = eb, eb = tu;
+            ti = sa, sa = sb, sb = ti;
+            ti = aa, aa = ab, ab = ti;
+        }
+        p[0] = pa, p[1] = pb, ev[0] = ea, ev[1] = eb, shaped[0] = sa, shaped[1] = sb;
+    }
 
     // ---- resolve_movement :1644-1727 from the pre-step positions; a blocked or collided player
     //      still turns (quirk Q8) ----
@@ -198,10 +235,11 @@ __device__ __forceinline__ void step_core(R &r, const ovc_layout_t *__restrict__
     for (int i = 0; i < 2; i++) {
         const int pos = p[i] & 0xFF;
         npos[i] = pos;
-        if (act[i] < 4) {
-            const int tpos = (pos + dir_delta(act[i])) & 0xFF;
-            if ((__ldg(&L->cell[tpos]) & 7) == OVC_T_FLOOR) npos[i] = tpos;
-            p[i] = (p[i] & ~0x300u) | ((unsigned)act[i] << 8);
+        const int a = i == 0 ? a0 : a1;
+        if (a < 4) {
+            const int tpos = (pos + dir_delta(a)) & 0xFF;
+            if ((L.u16(OVC_OFF(cell) + 2 * tpos) & 7) == OVC_T_FLOOR) npos[i] = tpos;
+            p[i] = (p[i] & ~0x300u) | ((unsigned)a << 8);
         }
     }
     {
@@ -218,14 +256,14 @@ __device__ __forceinline__ void step_core(R &r, const ovc_layout_t *__restrict__
     {
         int4 pw = r.ld4(1);
         bool changed = false;
-        const bool old_dyn = __ldg(&L->flags) & OVC_LAYOUT_OLD_DYNAMICS;
+        const bool old_dyn = lflags & OVC_LAYOUT_OLD_DYNAMICS;
 #pragma unroll
         for (int k = 0; k < OVC_MAX_POTS; k++) {
             unsigned w = (unsigned)comp(pw, k);
             if (k < n_pots && (w & 7) == OVC_O_SOUP) {
                 unsigned tp1 = (w >> 8) & 0x3FFF;
                 if (old_dyn && tp1 == 0 && ((w >> 3) & 3) == 3) tp1 = 1;  // auto start :1696-1701
-                if (tp1 != 0 && (int)(tp1 - 1) < __ldg(&L->cook_time[recipe_row(w)])) tp1 += 1;  // cook :601-606
+                if (tp1 != 0 && (int)(tp1 - 1) < L.i32(OVC_OFF(cook_time) + 4 * recipe_row(w))) tp1 += 1;  // cook :601-606
                 unsigned nw = (w & 0xFFu) | (tp1 << 8);
                 changed |= nw != w;
                 set_comp(pw, k, (int)nw);
@@ -240,6 +278,7 @@ __device__ __forceinline__ void step_core(R &r, const ovc_layout_t *__restrict__
     o.done = horizon > 0 && tn >= horizon;  // is_done overcooked_env.py:321-325
     if (o.done && (flags & OVC_F_AUTO_RESET)) {
         const int4 *__restrict__ src = reinterpret_cast<const int4 *>(start_records + (size_t)(misc & 0xFF) * S);
+#pragma unroll 4
         for (int c = 0; c < S / 4; c++) r.st4(c, __ldg(src + c));
     } else {
         r.st4(0, make_int4(tn, (int)p[0], (int)p[1], (int)misc));

@@ -240,10 +240,12 @@ def test_reset_mask_and_noop_properties():
     assert torch.equal(env.state, s1) and all(torch.equal(x, y) for x, y in zip(o1, o2))
 
 
-def test_cuda_graph_capture_of_step():
-    """The C ABI launches on torch's current stream, so a step can be captured in a CUDA graph."""
+@pytest.mark.parametrize("pdl", [False, True], ids=["plain", "pdl"])
+def test_cuda_graph_capture_of_step(pdl):
+    """The C ABI launches on torch's current stream, so a step can be captured in a CUDA graph
+    (also with programmatic dependent launch between consecutive transitions)."""
     n = 4096
-    env = BatchedOvercookedEnv("cramped_room", n, horizon=400, auto_reset=True)
+    env = BatchedOvercookedEnv("cramped_room", n, horizon=400, auto_reset=True, pdl=pdl)
     ref_env = BatchedOvercookedEnv("cramped_room", n, horizon=400, auto_reset=True)
     rng = np.random.RandomState(9)
     acts = torch.from_numpy(_random_actions(rng, 20, n)).cuda()
@@ -264,6 +266,23 @@ def test_cuda_graph_capture_of_step():
         ref_env.step(acts[t])
         assert torch.equal(env.state, ref_env.state) and torch.equal(env.sparse, ref_env.sparse)
         assert torch.equal(env.shaped, ref_env.shaped) and torch.equal(env.events, ref_env.events)
+    # a whole episode of back-to-back transitions in ONE graph (the bench's "graph" mode)
+    T = 60
+    seq = torch.from_numpy(_random_actions(rng, T, n)).cuda()
+    outs = [tuple(torch.empty_like(x) for x in (env.sparse, env.shaped, env.done, env.events)) for _ in range(T)]
+    env.reset(), ref_env.reset()
+    torch.cuda.synchronize()
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g2):
+        for t in range(T):
+            env.step(seq[t], out=outs[t])
+    env.reset()
+    g2.replay()
+    want = ref_env.rollout(seq)
+    for t in range(T):
+        for got, w in zip(outs[t], want):
+            assert torch.equal(got, w[t])
+    assert torch.equal(env.state, ref_env.state)
 
 
 def test_bad_arguments_are_reported():
