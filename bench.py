@@ -186,12 +186,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
-    ap.add_argument("--mode", default="graph", choices=["step", "graph", "rollout"])
+    ap.add_argument("--mode", default="rollout", choices=["step", "graph", "rollout"])
     ap.add_argument("--io", type=int, default=0, help="record I/O strategy of K1 (0 default, 1 TMA tensor, 2 TMA bulk, 3 direct)")
     ap.add_argument("--envs", type=int, default=0, help="override environments per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--extra", action="store_true", help="also time the other modes and a cold-HBM large batch")
+    ap.add_argument("--extra", action="store_true", help="also time the remaining modes")
+    ap.add_argument("--pdl", action="store_true", help="programmatic dependent launch between K1 launches (step / graph modes)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -217,7 +218,7 @@ def main():
     if args.envs:
         n_envs = args.envs
     T = horizon
-    env = BatchedOvercookedEnv(layouts, n_envs, horizon=horizon, device=dev, auto_reset=True, io=args.io)
+    env = BatchedOvercookedEnv(layouts, n_envs, horizon=horizon, device=dev, auto_reset=True, io=args.io, pdl=args.pdl)
     S = env.state_words
     gen = torch.Generator(device=dev)
     gen.manual_seed(seed + rank)
@@ -252,8 +253,7 @@ def main():
             pass_step()
         return g
 
-    if args.mode == "graph" or args.extra:
-        graph = make_graph()
+    graph = make_graph()  # always: the per-transition kernel K1 is reported next to the headline mode
     passes = {"step": pass_step, "graph": pass_graph, "rollout": pass_rollout}
 
     def timed(fn, k, w):
@@ -308,30 +308,48 @@ def main():
                "api": "overcooked_ai_b200.batched.HostRolloutPipeline.run (pinned host actions in, pinned host rewards/done/events out, 50-transition chunks)",
                "checksum_sparse": int(h_out[0].sum().item())}
 
+    # ---- the per-transition kernel K1 (400 launches from one CUDA graph), measured in the same run ----
+    k1_steps = max(2, min(args.steps, 5))
+    if args.mode == "graph":
+        k1_ms, k1_launches = ms, launches
+        k1_steps = args.steps
+    else:
+        k1_ms, k1_launches = timed(pass_graph, k1_steps, 3)
     extra = {}
-    if args.extra and rank == 0:
-        for m in ("step", "graph", "rollout"):
+    if args.extra:
+        for m in ("step", "rollout"):
             if m == args.mode:
                 continue
             ms_m, l_m = timed(passes[m], max(3, args.steps // 2), 3)
-            extra[m] = {"env_steps_per_s": float(n_envs) * T * max(3, args.steps // 2) / (ms_m * 1e-3), "launches": l_m}
+            extra[m] = {"env_steps_per_s_per_gpu": float(n_envs) * T * max(3, args.steps // 2) / (ms_m * 1e-3), "launches": l_m}
 
     if rank != 0:
         return
 
     peak, peak_src = load_peaks()
     bytes_per = algorithmic_bytes_per_env_step(S)
-    # dominant kernel: K1 (one launch = n_envs env-steps) in step/graph mode, K5 (one launch = T*n_envs) in rollout mode
-    per_launch_env_steps = n_envs * (T if args.mode == "rollout" else 1)
-    avg_launch_s = ms * 1e-3 / launches
-    achieved = per_launch_env_steps * bytes_per / avg_launch_s / 1e9
-    roofline = {
-        "bound": "hbm", "kernel": "step_kernel<S=%d> (%s)" % (S, "fused T-step launch" if args.mode == "rollout" else "one transition per launch"),
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-        "algorithmic_bytes_per_env_step": bytes_per, "env_steps_per_launch": per_launch_env_steps,
-        "avg_launch_us": avg_launch_s * 1e6, "traffic": None,
-        "note": "avg launch duration = CUDA-event time of the timed region / launches (includes launch gaps)",
-    }
+
+    def roofline_of(mode, ms_, launches_):
+        fused = mode == "rollout"
+        per_launch_env_steps = n_envs * (T if fused else 1)
+        avg_launch_s = ms_ * 1e-3 / launches_
+        achieved = per_launch_env_steps * bytes_per / avg_launch_s / 1e9
+        r = {
+            "bound": "hbm",
+            "kernel": "ovc::step_kernel<S=%d> %s" % (S, "K5: T=%d transitions fused in one launch, record tile resident in shared memory" % T if fused else "K1: one transition per launch"),
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+            "algorithmic_bytes_per_env_step": bytes_per, "env_steps_per_launch": per_launch_env_steps,
+            "avg_launch_us": avg_launch_s * 1e6, "traffic": None,
+            "note": "achieved = env_steps_per_launch x %d B (SURVEY 8d) / avg launch duration; avg launch duration = CUDA-event time of the timed region / launches (includes launch gaps)" % bytes_per,
+        }
+        if fused:
+            r["streamed_GBps"] = per_launch_env_steps * 32 / avg_launch_s / 1e9
+            r["note"] += "; the fused kernel keeps the record on chip between transitions, so only actions + outputs (32 B per env-step, streamed_GBps) cross HBM: a frac near or above 1 is traffic avoided by fusion, not bandwidth"
+        return r
+
+    roofline = roofline_of(args.mode, ms, launches)
+    roofline_k1 = roofline_of("graph", k1_ms, k1_launches)
+    roofline_k1["env_steps_per_s_per_gpu"] = float(n_envs) * T * k1_steps / (k1_ms * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -342,7 +360,7 @@ def main():
             "l2": "per bench step the action trace + outputs (%.0f MB) stream through HBM and exceed the 126 MB L2; the %.1f MB state tensor is the carried value and stays L2 resident"
                   % (n_envs * T * 32 / 1e6, n_envs * S * 4 / 1e6),
         },
-        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_k1": roofline_k1,
         "episode_sparse_reward_sum": tot_reward,
     }
     if extra:

@@ -158,11 +158,14 @@ static int encode_lossless_impl(const ovc_layout_t *layouts, const int32_t *stat
     a.S = S, a.W = W, a.H = H, a.horizon = horizon;
     a.obs_elems = 2 * W * H * N_PLANES;
     const int obs_bytes = a.obs_elems * esize;
-    static int buf_kb = 0;  // tile buffer size: 48 KB = 4 CTAs per SM keep loads, fills and stores overlapped
+    // Tile buffer size.  Measured on B200 (tools/kbench.py, 262 144 envs, fp32): 16 KB 85 %, 24 KB 105 %,
+    // 32 KB 104 %, 48 KB 82 %, 64 KB 79 %, 96 KB 61 % of the measured HBM copy peak — small tiles keep
+    // ~8 CTAs per SM in flight so fill, scatter and bulk store of different tiles overlap.
+    static int buf_kb = 0;
     if (buf_kb == 0) {
         const char *env = getenv("OVC_ENC_BUF_KB");  // tuning knob for experiments
-        buf_kb = env ? atoi(env) : 48;
-        if (buf_kb < 4 || buf_kb > 200) buf_kb = 48;
+        buf_kb = env ? atoi(env) : 24;
+        if (buf_kb < 4 || buf_kb > 200) buf_kb = 24;
     }
     const int BUF = buf_kb * 1024;
     const int mult = 16 / gcd_int(16, obs_bytes);    // tiles must start 16-byte aligned in the output
@@ -211,25 +214,32 @@ struct FeatArgs {
 constexpr int FEAT_E = 64;              // environments per tile
 constexpr int FEAT_LD = 2 * FEAT_E + 1;  // odd leading dimension: phase-2 reads (stride LD) stay conflict free
 
-// Block of player `me` (:2748-2840), written as int16 blk[n * FEAT_LD + view].
+// Block of player `me` (:2748-2840).  `own` points at column `view` of the feature-major tile
+// asm_[F][FEAT_LD]; the same values are the "other player" block of the partner view (`oth` = rows B.. of
+// column view^1), so phase 2 is a pure transpose.
 __device__ __forceinline__ void feat_block(const FeatArgs &a, const ovc_layout_t *__restrict__ L,
                                            const ovc_feat_lut_entry_t *__restrict__ le, const int32_t *__restrict__ rec,
-                                           unsigned me, short *blk) {
+                                           unsigned me, short *own, short *oth) {
     int n = 0;
     auto put = [&](int v) {
-        blk[n * FEAT_LD] = (short)v;
+        own[n * FEAT_LD] = (short)v;
+        oth[n * FEAT_LD] = (short)v;
         n++;
     };
     const int x = me & 15, y = (me >> 4) & 15, ori = (me >> 8) & 3;
     const unsigned held = me >> 10;
     const int ht = held & 7;
+    // the 12-byte LUT entry as three words: {d_onion, d_tomato}, {d_dish, d_serve}, pot_order
+    const unsigned lw0 = __ldg(reinterpret_cast<const unsigned *>(le)), lw1 = __ldg(reinterpret_cast<const unsigned *>(le) + 1),
+                   lw2 = __ldg(reinterpret_cast<const unsigned *>(le) + 2);
+    auto sb = [](unsigned w, int k) { return (int)(signed char)((w >> (8 * k)) & 0xFF); };
     for (int k = 0; k < 4; k++) put(ori == k);  // pi_orientation :2750-2753
     // pi_objs one-hot over IDX_TO_OBJ = [onion, soup, dish, tomato] :2742-2764
     put(ht == OVC_O_ONION), put(ht == OVC_O_SOUP), put(ht == OVC_O_DISH), put(ht == OVC_O_TOMATO);
     // closest onion / tomato / dish source: (0,0) when that object is held :2632-2641
-    put(ht == OVC_O_ONION ? 0 : le->d_onion[0]), put(ht == OVC_O_ONION ? 0 : le->d_onion[1]);
-    put(ht == OVC_O_TOMATO ? 0 : le->d_tomato[0]), put(ht == OVC_O_TOMATO ? 0 : le->d_tomato[1]);
-    put(ht == OVC_O_DISH ? 0 : le->d_dish[0]), put(ht == OVC_O_DISH ? 0 : le->d_dish[1]);
+    put(ht == OVC_O_ONION ? 0 : sb(lw0, 0)), put(ht == OVC_O_ONION ? 0 : sb(lw0, 1));
+    put(ht == OVC_O_TOMATO ? 0 : sb(lw0, 2)), put(ht == OVC_O_TOMATO ? 0 : sb(lw0, 3));
+    put(ht == OVC_O_DISH ? 0 : sb(lw1, 0)), put(ht == OVC_O_DISH ? 0 : sb(lw1, 1));
     // closest soup: counters are never motion goals (NO_COUNTERS_PARAMS) -> (0,0); counts from a held soup
     put(0), put(0);
     int son = 0, sto = 0;
@@ -239,10 +249,10 @@ __device__ __forceinline__ void feat_block(const FeatArgs &a, const ovc_layout_t
         son = ns - sto;
     }
     put(son), put(sto);
-    put(le->d_serve[0]), put(le->d_serve[1]);
+    put(sb(lw1, 2)), put(sb(lw1, 3));
     put(0), put(0);  // closest empty counter: unreachable goal -> (0,0)
     for (int k = 0; k < a.num_pots; k++) {  // make_pot_feature :2658-2740, pots by planner cost :2820-2831
-        const int slot = k < OVC_MAX_POTS ? le->pot_order[k] : OVC_NO_SLOT;
+        const int slot = k < OVC_MAX_POTS ? (int)((lw2 >> (8 * k)) & 0xFF) : OVC_NO_SLOT;
         if (slot == OVC_NO_SLOT) {
             for (int z = 0; z < 10; z++) put(0);
             continue;
@@ -269,46 +279,35 @@ __device__ __forceinline__ void feat_block(const FeatArgs &a, const ovc_layout_t
 
 __global__ void __launch_bounds__(256) featurize_kernel(const FeatArgs a) {
     extern __shared__ __align__(16) char fsm[];
-    short *blk = reinterpret_cast<short *>(fsm);      // [B][FEAT_LD] int16 (cook times go up to 16382)
-    short *posx = blk + (size_t)a.B * FEAT_LD;        // [2E] player x
-    short *posy = posx + 2 * FEAT_E;                  // [2E] player y
+    short *asm_ = reinterpret_cast<short *>(fsm);  // [F][FEAT_LD] int16 (cook times go up to 16382), feature-major
     const long long env0 = (long long)blockIdx.x * FEAT_E;
     const long long rem = a.n_envs - env0;
     const int ne = (int)(rem < FEAT_E ? rem : FEAT_E);
     const int nv = ne * 2;
-    // ---- phase 1: one thread per view ----
+    // ---- phase 1: one thread per view builds its row pieces ----
     if ((int)threadIdx.x < nv) {
         const int v = threadIdx.x, el = v >> 1, j = v & 1;
         const int32_t *__restrict__ rec = a.state + (env0 + el) * a.S;
         const int lid = __ldg(rec + 3) & 0xFF;
         const ovc_layout_t *__restrict__ L = a.layouts + lid;
-        const unsigned me = (unsigned)__ldg(rec + 1 + j);
+        const unsigned me = (unsigned)__ldg(rec + 1 + j), ot = (unsigned)__ldg(rec + 2 - j);
         const ovc_feat_lut_entry_t *le = a.lut + (size_t)lid * 1024 + ((me & 0xFF) << 2 | ((me >> 8) & 3));
-        feat_block(a, L, le, rec, me, blk + v);
-        posx[v] = (short)(me & 15);
-        posy[v] = (short)((me >> 4) & 15);
+        feat_block(a, L, le, rec, me, asm_ + v, asm_ + (size_t)a.B * FEAT_LD + (v ^ 1));
+        // :2877-2896 tail of the row: other - self, then self position
+        short *tail = asm_ + (size_t)2 * a.B * FEAT_LD + v;
+        tail[0 * FEAT_LD] = (short)((int)(ot & 15) - (int)(me & 15));
+        tail[1 * FEAT_LD] = (short)((int)((ot >> 4) & 15) - (int)((me >> 4) & 15));
+        tail[2 * FEAT_LD] = (short)(me & 15);
+        tail[3 * FEAT_LD] = (short)((me >> 4) & 15);
     }
     __syncthreads();
-    // ---- phase 2: assemble rows, float4 per thread, coalesced ----
+    // ---- phase 2: transpose to rows, float4 per thread, coalesced ----
     const int G = a.F / 4;  // F = 20*num_pots + 56 is a multiple of 4
     float4 *dst = reinterpret_cast<float4 *>(a.out + (size_t)env0 * 2 * a.F);
     for (int idx = threadIdx.x; idx < nv * G; idx += blockDim.x) {
         const int v = idx / G, g = idx - v * G;
-        float r[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int f = g * 4 + q;
-            int val;
-            if (f < a.B) val = blk[f * FEAT_LD + v];
-            else if (f < 2 * a.B) val = blk[(f - a.B) * FEAT_LD + (v ^ 1)];
-            else {
-                const int z = f - 2 * a.B;  // 0,1: other - self; 2,3: self position
-                const int sx = posx[v], sy = posy[v];
-                val = z == 0 ? posx[v ^ 1] - sx : z == 1 ? posy[v ^ 1] - sy : z == 2 ? sx : sy;
-            }
-            r[q] = (float)val;
-        }
-        dst[idx] = make_float4(r[0], r[1], r[2], r[3]);
+        const short *src = asm_ + (size_t)(4 * g) * FEAT_LD + v;
+        dst[idx] = make_float4((float)src[0], (float)src[FEAT_LD], (float)src[2 * FEAT_LD], (float)src[3 * FEAT_LD]);
     }
 }
 
@@ -322,7 +321,7 @@ static int featurize_impl(const ovc_layout_t *layouts, const ovc_feat_lut_entry_
     a.layouts = layouts, a.lut = lut, a.state = state, a.out = out, a.n_envs = n_envs, a.S = S;
     a.num_pots = num_pots, a.B = 10 * num_pots + 26, a.F = 2 * a.B + 4;
     a.E = FEAT_E;
-    const size_t smem = 2 * ((size_t)a.B * FEAT_LD + 4 * FEAT_E) + 16;
+    const size_t smem = 2 * (size_t)a.F * FEAT_LD + 16;
     cudaError_t e;
     if (smem > 48 * 1024) {
         e = cudaFuncSetAttribute(featurize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
