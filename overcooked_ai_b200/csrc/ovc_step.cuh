@@ -191,17 +191,15 @@ __device__ __forceinline__ void step_core(R &r, const TB &layouts,
     //      n_full     = cooking + ready + idle-with-3      (get_full_pots :1875-1880)
     //      n_dishable = ready + cooking + idle-with-1-or-2 (is_dish_pickup_useful :2199-2203)
     int n_full = 0, n_dishable = 0;
-    {
-        const int4 pw = r.ld4(1);
-#pragma unroll
-        for (int k = 0; k < OVC_MAX_POTS; k++) {
-            unsigned w = (unsigned)comp(pw, k);
-            bool is_pot_soup = k < n_pots && (w & 7) == OVC_O_SOUP;
-            int n = (w >> 3) & 3;
-            bool idle = ((w >> 8) & 0x3FFF) == 0;
-            n_full += is_pot_soup && (!idle || n == 3);
-            n_dishable += is_pot_soup && (!idle || n == 1 || n == 2);
-        }
+    int4 pw = r.ld4(1);
+#pragma unroll 1
+    for (int k = 0; k < n_pots; k++) {  // n_pots is uniform across a layout segment: 1 or 2 trips, not 4
+        const unsigned w = (unsigned)comp(pw, k);
+        const bool soup = (w & 7) == OVC_O_SOUP;
+        const int n = (w >> 3) & 3;
+        const bool idle = (w & (0x3FFFu << 8)) == 0;
+        n_full += soup && (!idle || n == 3);
+        n_dishable += soup && (!idle || n == 1 || n == 2);
     }
     const bool all_full = n_full == n_pots;
 
@@ -209,23 +207,26 @@ __device__ __forceinline__ void step_core(R &r, const TB &layouts,
     int shaped[2] = {0, 0};
     unsigned ev[2] = {0u, 0u};
 
-    // ---- resolve_interacts :1446-1577: player 0 then player 1 on the same live record.  The body
-    //      is emitted once: the second trip runs it with the players' roles swapped (two swaps put
-    //      everything back), which halves the code the instruction cache has to hold. ----
+    // ---- resolve_interacts :1446-1577: player 0 then player 1 on the same live record.  The body is
+    //      emitted once and run as a loop of up to two trips: trip 0 handles, per environment, the first
+    //      interacting player (player 0 if it interacts, else player 1); trip 1 handles player 1 where
+    //      BOTH interact (1 environment in 36 under a uniform policy), so most warps skip it. ----
     {
-        unsigned pa = p[0], pb = p[1], ea = 0u, eb = 0u;
-        int sa = 0, sb = 0, aa = a0, ab = a1;
+        const bool i0 = a0 == OVC_A_INTERACT, i1 = a1 == OVC_A_INTERACT;
 #pragma unroll 1
         for (int trip = 0; trip < 2; trip++) {
-            if (aa == OVC_A_INTERACT) interact_one(r, L, pa, pb, misc, n_full, n_dishable, all_full, sparse, sa, ea);
-            unsigned tu;
-            int ti;
-            tu = pa, pa = pb, pb = tu;
-            tu = ea, ea = eb, eb = tu;
-            ti = sa, sa = sb, sb = ti;
-            ti = aa, aa = ab, ab = ti;
+            const bool now = trip == 0 ? (i0 || i1) : (i0 && i1);
+            if (now) {
+                const bool second = trip == 1 || !i0;  // the acting player is player 1
+                unsigned pa = second ? p[1] : p[0];
+                const unsigned pb = second ? p[0] : p[1];
+                int sa = 0;
+                unsigned ea = 0u;
+                interact_one(r, L, pa, pb, misc, n_full, n_dishable, all_full, sparse, sa, ea);
+                if (second) p[1] = pa, shaped[1] = sa, ev[1] = ea;
+                else p[0] = pa, shaped[0] = sa, ev[0] = ea;
+            }
         }
-        p[0] = pa, p[1] = pb, ev[0] = ea, ev[1] = eb, shaped[0] = sa, shaped[1] = sb;
     }
 
     // ---- resolve_movement :1644-1727 from the pre-step positions; a blocked or collided player
@@ -254,17 +255,17 @@ __device__ __forceinline__ void step_core(R &r, const TB &layouts,
     // ---- step_environment_effects :1691-1703 (soups outside pots are always finished: no tick) ----
     const int tn = t + 1;
     {
-        int4 pw = r.ld4(1);
+        pw = r.ld4(1);
         bool changed = false;
         const bool old_dyn = lflags & OVC_LAYOUT_OLD_DYNAMICS;
-#pragma unroll
-        for (int k = 0; k < OVC_MAX_POTS; k++) {
-            unsigned w = (unsigned)comp(pw, k);
-            if (k < n_pots && (w & 7) == OVC_O_SOUP) {
+#pragma unroll 1
+        for (int k = 0; k < n_pots; k++) {
+            const unsigned w = (unsigned)comp(pw, k);
+            if ((w & 7) == OVC_O_SOUP) {
                 unsigned tp1 = (w >> 8) & 0x3FFF;
                 if (old_dyn && tp1 == 0 && ((w >> 3) & 3) == 3) tp1 = 1;  // auto start :1696-1701
                 if (tp1 != 0 && (int)(tp1 - 1) < L.i32(OVC_OFF(cook_time) + 4 * recipe_row(w))) tp1 += 1;  // cook :601-606
-                unsigned nw = (w & 0xFFu) | (tp1 << 8);
+                const unsigned nw = (w & 0xFFu) | (tp1 << 8);
                 changed |= nw != w;
                 set_comp(pw, k, (int)nw);
             }
