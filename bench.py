@@ -40,6 +40,8 @@ WORKLOADS = {
     "config2": (["cramped_room"], 65536, 400),
     "config3": (["cramped_room", "asymmetric_advantages", "coordination_ring", "forced_coordination", "counter_circuit"], 262144, 400),
     "config4": (["asymmetric_advantages"], 131072, 400),
+    # config 5: PPO-style self-play rollout (K2 encode -> torch CNN -> multinomial -> K1 step), 262 144 envs on 8 GPUs
+    "config5": (["cramped_room"], 32768, 400),
 }
 METRIC = "env-steps/sec (joint transitions)"
 
@@ -155,7 +157,7 @@ def run_reference(args, rank, world):
 
     layouts, n_envs, horizon = WORKLOADS[args.workload]
     threads = oracle_cpu.max_threads()
-    sample_envs = min(n_envs, 16384)
+    sample_envs = min(n_envs, 65536 if threads >= 32 else 16384)
     T = horizon
     for _ in range(args.warmup):
         cpu_run(layouts, min(sample_envs, 2048), 50, horizon, threads)
@@ -175,6 +177,69 @@ def run_reference(args, rank, world):
                          "sample": "%d steps x %d envs x %d transitions, oracle/ovc_oracle.c, %d threads" % (args.steps, sample_envs, T, threads)},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_policy_pipeline(args, rank, world, local):
+    """BASELINE config 5: step + lossless_state_encoding feeding a random-init torch CNN policy."""
+    import torch
+
+    from overcooked_ai_b200 import dist as D
+    from overcooked_ai_b200.batched import BatchedOvercookedEnv
+    from overcooked_ai_b200.selfplay import SelfPlayRollout
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    D.init("nccl")
+    seed = D.broadcast_seed(20260922, device=dev)
+    torch.manual_seed(seed + rank)
+    layouts, n_envs, horizon = WORKLOADS[args.workload]
+    if args.envs:
+        n_envs = args.envs
+    T = horizon
+    env = BatchedOvercookedEnv(layouts, n_envs, horizon=horizon, device=dev, auto_reset=True)
+    sp = SelfPlayRollout(env, use_graph=True)
+
+    def timed(fn, k, w):
+        for _ in range(w):
+            fn(T // 4)
+        D.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn(T)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        D.barrier()
+        return e0.elapsed_time(e1)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(sp.run, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_env = timed(sp.env_only, max(2, args.steps // 2), 1)
+    steps_local = float(n_envs) * T * args.steps
+    tot_steps, max_ms, tot_reward = D.reduce_counters(steps_local, ms, float(sp.ret_sparse.sum().item()), device=dev)
+    _, max_ms_env, _ = D.reduce_counters(0, ms_env / max(2, args.steps // 2), 0, device=dev)
+    if rank != 0:
+        return
+    S = env.state_words
+    l = env.layouts[0]
+    enc_bytes = 4 * S + 2 * l.width * l.height * 26 * 4
+    line = {
+        "metric": METRIC, "value": tot_steps / (max_ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32 env / fp32 observations / bf16-autocast policy", "data": "synthetic",
+        "config": {"workload": "config5: %s, %d envs/GPU, self-play: K2 lossless encode fp32 -> torch CNN (RllibPPOModel-shaped, random init, shared) -> multinomial -> K1 step, whole transition in one CUDA graph"
+                               % ("+".join(layouts), n_envs), "state_words": S, "parallelism": "env-index sharding x%d" % world},
+        "clocks": clocks, "gpu_launches": 2 * T * args.steps,
+        "env_only": {"ms_per_400_transitions": max_ms_env, "env_steps_per_s_per_gpu": n_envs * T / (max_ms_env * 1e-3),
+                     "share_of_pipeline_time": max_ms_env / (max_ms / args.steps),
+                     "algorithmic_bytes_per_env_step": algorithmic_bytes_per_env_step(S) + enc_bytes},
+        "sparse_reward_sum": tot_reward,
     }
     print(json.dumps(line), flush=True)
 
@@ -201,6 +266,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "config5":
+        run_policy_pipeline(args, rank, world, local)
         return
 
     import torch

@@ -220,18 +220,22 @@ int ovc_reset(const int32_t *start_records, int n_layouts, int32_t *state,
  * lossless_state_encoding (:2385-2561) for envs [0, n_envs) that all share one layout shape:
  * out[env][player][x][y][26] with element type `dtype` (OVC_DT_*).  `width`/`height` must equal
  * the layouts' own (all envs in the range must have equal-shape layouts).
+ * view_swap (nullable, int32[n_envs]): where non-zero the two player views are written in swapped
+ * order, out[env][0] = player 1's view — the "primary agent first" order of the gym wrapper
+ * (overcooked_env.py:850-866) without a second pass over the observations.
  */
-int ovc_encode_lossless(const void *layouts, int n_layouts, const int32_t *state, void *out,
-                        int dtype, int64_t n_envs, int state_words, int width, int height,
+int ovc_encode_lossless(const void *layouts, int n_layouts, const int32_t *state, const int32_t *view_swap,
+                        void *out, int dtype, int64_t n_envs, int state_words, int width, int height,
                         int horizon, void *stream);
 
 /*
  * featurize_state (:2579-2898) with the default planner parameters (NO_COUNTERS_PARAMS,
- * planners.py:27-34): out float32[n_envs][2][2*(28+10*num_pots)+4]... = [n_envs][2][F],
- * F = 2*(num_pots*10+28), lut = ovc_feat_lut_entry_t[n_layouts][256][4].
+ * planners.py:27-34): out float32[n_envs][2][F],
+ * F = 2*(num_pots*10+28), lut = ovc_feat_lut_entry_t[n_layouts][256][4].  view_swap as above.
  */
 int ovc_featurize(const void *layouts, int n_layouts, const void *lut, const int32_t *state,
-                  float *out, int64_t n_envs, int state_words, int num_pots, void *stream);
+                  const int32_t *view_swap, float *out, int64_t n_envs, int state_words, int num_pots,
+                  void *stream);
 
 #ifdef __cplusplus
 }

@@ -43,8 +43,8 @@ def lib():
     L.ovc_step.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]
     L.ovc_rollout.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]
     L.ovc_reset.argtypes = [vp, i32, vp, vp, vp, i64, i32, vp]
-    L.ovc_encode_lossless.argtypes = [vp, i32, vp, vp, i32, i64, i32, i32, i32, i32, vp]
-    L.ovc_featurize.argtypes = [vp, i32, vp, vp, vp, i64, i32, i32, vp]
+    L.ovc_encode_lossless.argtypes = [vp, i32, vp, vp, vp, i32, i64, i32, i32, i32, i32, vp]
+    L.ovc_featurize.argtypes = [vp, i32, vp, vp, vp, vp, i64, i32, i32, vp]
     for f in (L.ovc_step, L.ovc_rollout, L.ovc_reset, L.ovc_encode_lossless, L.ovc_featurize):
         f.restype = i32
     if L.ovc_abi_version() != ABI_VERSION:

@@ -162,11 +162,14 @@ class BatchedOvercookedEnv(object):
         l = self.layouts[layout_index]
         return (l.width, l.height, 26)
 
-    def lossless_state_encoding(self, out=None, dtype=torch.float32):
+    def lossless_state_encoding(self, out=None, dtype=torch.float32, view_swap=None):
         """lossless_state_encoding (overcooked_mdp.py:2385-2561) of every environment, both players:
         tensor [N, 2, W, H, 26] (index order [x][y][channel], as the reference) when all layouts share
         one grid shape, else a list of such tensors, one per layout segment.  dtype float32 (what the
-        reference's RLlib consumer casts to), uint8 or int32."""
+        reference's RLlib consumer casts to), uint8 or int32.  ``view_swap`` (int32 CUDA tensor [N]):
+        where non-zero, ``out[env, 0]`` is player 1's view (primary-agent-first order of the gym wrapper)."""
+        if view_swap is not None:
+            assert view_swap.dtype == torch.int32 and view_swap.is_cuda and view_swap.is_contiguous() and view_swap.numel() == self.n_envs
         shapes = {(l.width, l.height) for l in self.layouts}
         if len(shapes) == 1:
             runs = [(0, self.n_envs, 0)]
@@ -180,7 +183,8 @@ class BatchedOvercookedEnv(object):
                 o = torch.empty((e - b, 2, W, H, 26), dtype=dtype, device=self.device)
             assert o.is_cuda and o.is_contiguous() and o.numel() == (e - b) * 2 * W * H * 26
             _native.check(self._lib.ovc_encode_lossless(
-                self.tables.data_ptr(), self.n_layouts, self.state.data_ptr() + 4 * self.state_words * b, o.data_ptr(),
+                self.tables.data_ptr(), self.n_layouts, self.state.data_ptr() + 4 * self.state_words * b,
+                0 if view_swap is None else view_swap.data_ptr() + 4 * b, o.data_ptr(),
                 _TORCH_DT[o.dtype], e - b, self.state_words, W, H, self.horizon if self.horizon > 0 else 2**31 - 1,
                 self._stream()))
             outs.append(o)
@@ -193,7 +197,7 @@ class BatchedOvercookedEnv(object):
             self._lut = torch.from_numpy(lut).to(self.device)
         return self._lut
 
-    def featurize_state(self, num_pots=2, out=None):
+    def featurize_state(self, num_pots=2, out=None, view_swap=None):
         """featurize_state (overcooked_mdp.py:2579-2898; default NO_COUNTERS_PARAMS planner):
         float32 [N, 2, 2*(10*num_pots+28)]."""
         F = 2 * (10 * num_pots + 28)
@@ -202,7 +206,8 @@ class BatchedOvercookedEnv(object):
         assert out.dtype == torch.float32 and out.is_cuda and out.is_contiguous() and out.numel() == self.n_envs * 2 * F
         _native.check(self._lib.ovc_featurize(
             self.tables.data_ptr(), self.n_layouts, self.feature_lut().data_ptr(), self.state.data_ptr(),
-            out.data_ptr(), self.n_envs, self.state_words, num_pots, self._stream()))
+            0 if view_swap is None else view_swap.data_ptr(), out.data_ptr(), self.n_envs, self.state_words, num_pots,
+            self._stream()))
         return out
 
     # ---------------------------------------------------------------------------------------------

@@ -403,20 +403,21 @@ int ovc_reset(const int32_t *start_records, int n_layouts, int32_t *state, const
     return OVC_OK;
 }
 
-int ovc_encode_lossless(const void *layouts, int n_layouts, const int32_t *state, void *out, int dtype,
-                        int64_t n_envs, int state_words, int width, int height, int horizon, void *stream) {
+int ovc_encode_lossless(const void *layouts, int n_layouts, const int32_t *state, const int32_t *view_swap,
+                        void *out, int dtype, int64_t n_envs, int state_words, int width, int height, int horizon,
+                        void *stream) {
     int rc = ovc::check_common(layouts, n_layouts, state, n_envs, state_words);
     if (rc) return rc;
-    return ovc::encode_lossless_impl((const ovc_layout_t *)layouts, state, out, dtype, n_envs, state_words, width,
-                                     height, horizon, (cudaStream_t)stream);
+    return ovc::encode_lossless_impl((const ovc_layout_t *)layouts, state, view_swap, out, dtype, n_envs, state_words,
+                                     width, height, horizon, (cudaStream_t)stream);
 }
 
-int ovc_featurize(const void *layouts, int n_layouts, const void *lut, const int32_t *state, float *out,
-                  int64_t n_envs, int state_words, int num_pots, void *stream) {
+int ovc_featurize(const void *layouts, int n_layouts, const void *lut, const int32_t *state,
+                  const int32_t *view_swap, float *out, int64_t n_envs, int state_words, int num_pots, void *stream) {
     int rc = ovc::check_common(layouts, n_layouts, state, n_envs, state_words);
     if (rc) return rc;
-    return ovc::featurize_impl((const ovc_layout_t *)layouts, (const ovc_feat_lut_entry_t *)lut, state, out, n_envs,
-                               state_words, num_pots, (cudaStream_t)stream);
+    return ovc::featurize_impl((const ovc_layout_t *)layouts, (const ovc_feat_lut_entry_t *)lut, state, view_swap, out,
+                               n_envs, state_words, num_pots, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -25,6 +25,7 @@ enum {
 struct EncodeArgs {
     const ovc_layout_t *layouts;
     const int32_t *state;
+    const int32_t *view_swap;  // nullable
     void *out;
     long long n_envs;
     int S, W, H, horizon;
@@ -106,11 +107,13 @@ __global__ void __launch_bounds__(256) encode_kernel(const EncodeArgs a) {
             const unsigned w = (unsigned)__ldg(rec + 1 + j);
             const int x = w & 15, y = (w >> 4) & 15, ori = (w >> 8) & 3;
             const int base = (x * a.H + y) * N_PLANES;
-            // view p: own layers first — loc plane (j==p ? 0 : 1), orientation planes 2+4*(j!=p)+ori
-            obs[(size_t)j * WH26 + base + PL_LOC] = (T)1;
-            obs[(size_t)j * WH26 + base + PL_ORI + ori] = (T)1;
-            obs[(size_t)(1 - j) * WH26 + base + PL_LOC + 1] = (T)1;
-            obs[(size_t)(1 - j) * WH26 + base + PL_ORI + 4 + ori] = (T)1;
+            // view p: own layers first — loc plane (j==p ? 0 : 1), orientation planes 2+4*(j!=p)+ori;
+            // player j's own view lands in output slot j, or 1-j where view_swap says so
+            const int own = (a.view_swap && __ldg(a.view_swap + env0 + el)) ? 1 - j : j;
+            obs[(size_t)own * WH26 + base + PL_LOC] = (T)1;
+            obs[(size_t)own * WH26 + base + PL_ORI + ori] = (T)1;
+            obs[(size_t)(1 - own) * WH26 + base + PL_LOC + 1] = (T)1;
+            obs[(size_t)(1 - own) * WH26 + base + PL_ORI + 4 + ori] = (T)1;
             put_object(obs, WH26, a.H, L, w >> 10, x, y, false);
         } else {  // loose objects: one per object-capable cell
             const int slot = k - WH - 2;
@@ -144,8 +147,8 @@ __global__ void __launch_bounds__(256) encode_kernel(const EncodeArgs a) {
 
 static int gcd_int(int a, int b) { return b ? gcd_int(b, a % b) : a; }
 
-static int encode_lossless_impl(const ovc_layout_t *layouts, const int32_t *state, void *out, int dtype,
-                                long long n_envs, int S, int W, int H, int horizon, cudaStream_t st) {
+static int encode_lossless_impl(const ovc_layout_t *layouts, const int32_t *state, const int32_t *view_swap, void *out,
+                                int dtype, long long n_envs, int S, int W, int H, int horizon, cudaStream_t st) {
     if (!out) return fail(OVC_E_BADARG, "null output pointer%s", "");
     if (((uintptr_t)out & 15) != 0) return fail(OVC_E_BADARG, "output must be 16-byte aligned%s", "");
     if (W < 1 || W > 16 || H < 1 || H > 16) return fail(OVC_E_BADARG, "grid shape out of range%s", "");
@@ -154,7 +157,7 @@ static int encode_lossless_impl(const ovc_layout_t *layouts, const int32_t *stat
     if (dtype != OVC_DT_F32 && dtype != OVC_DT_U8 && dtype != OVC_DT_I32)
         return fail(OVC_E_BADARG, "unknown dtype%s %lld", "", dtype);
     EncodeArgs a;
-    a.layouts = layouts, a.state = state, a.out = out, a.n_envs = n_envs;
+    a.layouts = layouts, a.state = state, a.view_swap = view_swap, a.out = out, a.n_envs = n_envs;
     a.S = S, a.W = W, a.H = H, a.horizon = horizon;
     a.obs_elems = 2 * W * H * N_PLANES;
     const int obs_bytes = a.obs_elems * esize;
@@ -206,6 +209,7 @@ struct FeatArgs {
     const ovc_layout_t *layouts;
     const ovc_feat_lut_entry_t *lut;
     const int32_t *state;
+    const int32_t *view_swap;  // nullable
     float *out;
     long long n_envs;
     int S, num_pots, B, F, E;
@@ -305,20 +309,22 @@ __global__ void __launch_bounds__(256) featurize_kernel(const FeatArgs a) {
     const int G = a.F / 4;  // F = 20*num_pots + 56 is a multiple of 4
     float4 *dst = reinterpret_cast<float4 *>(a.out + (size_t)env0 * 2 * a.F);
     for (int idx = threadIdx.x; idx < nv * G; idx += blockDim.x) {
-        const int v = idx / G, g = idx - v * G;
+        const int row = idx / G, g = idx - row * G;
+        // output row `row` of the tile is player (row & 1)'s view, or the partner's where view_swap is set
+        const int v = (a.view_swap && __ldg(a.view_swap + env0 + (row >> 1))) ? row ^ 1 : row;
         const short *src = asm_ + (size_t)(4 * g) * FEAT_LD + v;
         dst[idx] = make_float4((float)src[0], (float)src[FEAT_LD], (float)src[2 * FEAT_LD], (float)src[3 * FEAT_LD]);
     }
 }
 
-static int featurize_impl(const ovc_layout_t *layouts, const ovc_feat_lut_entry_t *lut, const int32_t *state, float *out,
-                          long long n_envs, int S, int num_pots, cudaStream_t st) {
+static int featurize_impl(const ovc_layout_t *layouts, const ovc_feat_lut_entry_t *lut, const int32_t *state,
+                          const int32_t *view_swap, float *out, long long n_envs, int S, int num_pots, cudaStream_t st) {
     if (!out || !lut) return fail(OVC_E_BADARG, "null pointer argument%s", "");
     if (((uintptr_t)out & 15) != 0) return fail(OVC_E_BADARG, "output must be 16-byte aligned%s", "");
     if (num_pots < 0 || num_pots > 16) return fail(OVC_E_BADARG, "num_pots out of range%s", "");
     if (n_envs == 0) return OVC_OK;
     FeatArgs a;
-    a.layouts = layouts, a.lut = lut, a.state = state, a.out = out, a.n_envs = n_envs, a.S = S;
+    a.layouts = layouts, a.lut = lut, a.state = state, a.view_swap = view_swap, a.out = out, a.n_envs = n_envs, a.S = S;
     a.num_pots = num_pots, a.B = 10 * num_pots + 26, a.F = 2 * a.B + 4;
     a.E = FEAT_E;
     const size_t smem = 2 * (size_t)a.F * FEAT_LD + 16;

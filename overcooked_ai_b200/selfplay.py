@@ -1,0 +1,106 @@
+"""Self-play rollout collection with a torch policy on top of the batched engine (BASELINE config 5).
+
+The reference collects PPO rollouts with Ray workers that each run one Python env and a TF copy of
+the policy (human_aware_rl/rllib/rllib.py:293-342, ppo/ppo_rllib.py:7-80).  Here one process per GPU
+keeps N environments on the device and runs, per transition,
+
+    lossless_state_encoding (K2, fp32 [N,2,W,H,26])  ->  policy CNN (torch)  ->  multinomial
+    ->  ovc_step (K1)  ->  reward accumulation
+
+with no host round trip; the whole transition can be captured in one CUDA graph.  The observation
+tensor is consumed zero-copy: ``[N,2,W,H,26]`` viewed as ``(2N, 26, W, H)`` is exactly torch's
+channels-last memory format.
+
+The policy is shaped like the reference's ``RllibPPOModel`` defaults (ppo_rllib.py:43-79 with
+ppo_rllib_client.py:85-88: conv 5x5x25 'same', conv 3x3x25 'same', conv 3x3x25 'valid', 3 dense layers
+of 64, leaky ReLU, heads 6 + 1), random init, shared by both agents.  It is a CONSUMER of the hot
+path (library kernels: cuDNN / cuBLAS through torch), not part of it.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class RllibShapedCNN(nn.Module):
+    def __init__(self, width, height, in_planes=26, num_filters=25, hidden=64, num_hidden_layers=3, num_actions=6):
+        super().__init__()
+        self.conv_initial = nn.Conv2d(in_planes, num_filters, 5, padding=2)
+        self.conv_0 = nn.Conv2d(num_filters, num_filters, 3, padding=1)
+        self.conv_1 = nn.Conv2d(num_filters, num_filters, 3, padding=0)
+        flat = num_filters * (width - 2) * (height - 2)
+        dims = [flat] + [hidden] * num_hidden_layers
+        self.dense = nn.ModuleList([nn.Linear(dims[i], dims[i + 1]) for i in range(num_hidden_layers)])
+        self.logits = nn.Linear(hidden, num_actions)
+        self.value = nn.Linear(hidden, 1)
+
+    def forward(self, obs_nchw):
+        x = F.leaky_relu(self.conv_initial(obs_nchw), 0.2)
+        x = F.leaky_relu(self.conv_0(x), 0.2)
+        x = F.leaky_relu(self.conv_1(x), 0.2)
+        x = x.flatten(1)
+        for d in self.dense:
+            x = F.leaky_relu(d(x), 0.3)
+        return self.logits(x), self.value(x).squeeze(-1)
+
+
+class SelfPlayRollout(object):
+    """Policy-in-the-loop rollout: both agents of every environment act from the same network."""
+
+    def __init__(self, env, model=None, autocast_dtype=torch.bfloat16, use_graph=True, reward_shaping_factor=1.0):
+        assert len({(l.width, l.height) for l in env.layouts}) == 1, "one grid shape per rollout (group envs by layout)"
+        self.env = env
+        l = env.layouts[0]
+        self.W, self.H = l.width, l.height
+        dev = env.device
+        self.model = (model or RllibShapedCNN(self.W, self.H)).to(dev).to(memory_format=torch.channels_last).eval()
+        self.autocast_dtype = autocast_dtype
+        self.factor = float(reward_shaping_factor)
+        N = env.n_envs
+        self.obs = torch.empty((N, 2, self.W, self.H, 26), dtype=torch.float32, device=dev)
+        self.actions = torch.zeros((N, 2), dtype=torch.int32, device=dev)
+        self.ret_sparse = torch.zeros(N, dtype=torch.int64, device=dev)      # running episode return (sparse)
+        self.ret_mixed = torch.zeros(N, dtype=torch.float32, device=dev)    # sparse + factor * shaped (rllib.py:328-329)
+        self.values = torch.zeros((N, 2), dtype=torch.float32, device=dev)
+        self.graph = None
+        self.use_graph = use_graph
+
+    def _transition(self):
+        env = self.env
+        env.lossless_state_encoding(out=self.obs)  # K2
+        x = self.obs.view(2 * env.n_envs, self.W, self.H, 26).permute(0, 3, 1, 2)  # (2N,26,W,H), channels-last strides
+        with torch.no_grad(), torch.autocast("cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
+            logits, value = self.model(x)
+        probs = torch.softmax(logits.float(), dim=-1)
+        a = torch.multinomial(probs, 1).view(env.n_envs, 2)
+        self.actions.copy_(a)
+        self.values.copy_(value.float().view(env.n_envs, 2))
+        sparse, shaped, done, events = env.step(self.actions)  # K1 (auto-reset inside)
+        self.ret_sparse += sparse
+        self.ret_mixed += sparse.float() + self.factor * shaped.sum(-1).float()
+
+    def run(self, n_steps):
+        """Advance every environment n_steps transitions; returns the number of env-steps done."""
+        if self.use_graph and self.graph is None:
+            s = torch.cuda.Stream(self.env.device)
+            s.wait_stream(torch.cuda.current_stream(self.env.device))
+            with torch.cuda.stream(s):
+                for _ in range(3):
+                    self._transition()
+            torch.cuda.current_stream(self.env.device).wait_stream(s)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._transition()
+        for _ in range(n_steps):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._transition()
+        return n_steps * self.env.n_envs
+
+    def env_only(self, n_steps):
+        """The same transitions without the policy: encode + step with the last sampled actions
+        (used to report the env-only share of the pipeline)."""
+        for _ in range(n_steps):
+            self.env.lossless_state_encoding(out=self.obs)
+            self.env.step(self.actions)
+        return n_steps * self.env.n_envs

@@ -293,3 +293,24 @@ def test_bad_arguments_are_reported():
     rc = lib.ovc_step(env.tables.data_ptr(), 1, env.start_records.data_ptr(), env.state.data_ptr(), env.state.data_ptr(),
                       env.sparse.data_ptr(), env.shaped.data_ptr(), env.done.data_ptr(), env.events.data_ptr(), 8, 24, 400, 0, 0)
     assert rc == -1 and b"state_words" in lib.ovc_last_error()
+
+
+def test_selfplay_policy_rollout_matches_oracle_replay():
+    """Config-5 pipeline (K2 -> torch CNN -> multinomial -> K1): whatever the policy samples, the
+    environments must follow the oracle on those very actions; graph replay == eager."""
+    from overcooked_ai_b200.selfplay import SelfPlayRollout
+
+    n, T = 512, 25
+    torch.manual_seed(0)
+    env = BatchedOvercookedEnv("cramped_room", n, horizon=20, auto_reset=True)
+    sp = SelfPlayRollout(env, use_graph=False, autocast_dtype=None)
+    ref_state = _np(env.state).copy()
+    for t in range(T):
+        sp.run(1)
+        a = _np(sp.actions)
+        assert a.min() >= 0 and a.max() <= 5
+        cpu.step(env._tab_host, env._starts_host, ref_state, a, horizon=20, flags=1)
+        assert np.array_equal(_np(env.state), ref_state), t
+    env2 = BatchedOvercookedEnv("cramped_room", n, horizon=20, auto_reset=True)
+    sp2 = SelfPlayRollout(env2, model=sp.model, use_graph=True)
+    assert sp2.run(30) == 30 * n and (_np(env2.state)[:, 0] == 30 % 20).all()
