@@ -81,6 +81,8 @@ class SelfPlayRollout(object):
     def run(self, n_steps):
         """Advance every environment n_steps transitions; returns the number of env-steps done."""
         if self.use_graph and self.graph is None:
+            # warm-up + capture must not advance the environments: snapshot, then restore
+            saved = (self.env.state.clone(), self.ret_sparse.clone(), self.ret_mixed.clone())
             s = torch.cuda.Stream(self.env.device)
             s.wait_stream(torch.cuda.current_stream(self.env.device))
             with torch.cuda.stream(s):
@@ -90,6 +92,7 @@ class SelfPlayRollout(object):
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self._transition()
+            self.env.state.copy_(saved[0]), self.ret_sparse.copy_(saved[1]), self.ret_mixed.copy_(saved[2])
         for _ in range(n_steps):
             if self.graph is not None:
                 self.graph.replay()
