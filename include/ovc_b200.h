@@ -152,6 +152,29 @@ typedef struct ovc_feat_lut_entry {
     uint8_t pot_order[OVC_MAX_POTS]; /* pot slots by increasing planner cost; 0xFF = unreachable */
 } ovc_feat_lut_entry_t;              /* 12 bytes; table is [n_layouts][256][4] */
 
+/* ---- potential_function constants (overcooked_mdp.py:2920-3250), one per layout, for ONE gamma ---- */
+typedef struct ovc_potential {
+    double steady;         /* steady-state term, :2985-2999 */
+    double disc_value[16]; /* discounted value of the best recipe reachable from recipe r (r == 0: empty), :1976-2061 */
+    int32_t opt_recipe[16]; /* that recipe's index (the DFS order of the reference decides ties) */
+    int32_t max_delivery_steps, max_pickup_steps, pot_onion_steps, pot_tomato_steps; /* POTENTIAL_CONSTANTS :1060-1073 */
+    int32_t onion_value, tomato_value;                                              /* :2975-2978 */
+    int32_t reserved[2];
+    /* iteration order of list(set().union(one_item_pots, two_item_pots)) (:1882-1890) for every assignment of
+     * pots to {not partial, 1 item, 2 items}: index = sum class_k * 3^k, entries = pot slots, 0xFF ends */
+    uint8_t partial_order[81][4];
+    uint8_t pad[4];
+} ovc_potential_t; /* 560 bytes */
+
+/* planner costs per (layout, cell, orientation): MotionPlanner.min_cost_to_feature (planners.py:391-423) to
+ * the serving cells and to each pot; 255 = unreachable.  Table is [n_layouts][256][4]. */
+typedef struct ovc_cost_lut_entry {
+    uint8_t serve;
+    uint8_t pot[OVC_MAX_POTS];
+    uint8_t pad[3];
+} ovc_cost_lut_entry_t; /* 8 bytes */
+#define OVC_COST_INF 255
+
 /* ---- error codes ---- */
 #define OVC_OK 0
 #define OVC_E_BADARG (-1)
@@ -236,6 +259,18 @@ int ovc_encode_lossless(const void *layouts, int n_layouts, const int32_t *state
 int ovc_featurize(const void *layouts, int n_layouts, const void *lut, const int32_t *state,
                   const int32_t *view_swap, float *out, int64_t n_envs, int state_words, int num_pots,
                   void *stream);
+
+/*
+ * potential_function (:2920-3250): out double[n_envs] = phi(state) for the gamma the tables were built
+ * for.  pot_tables = ovc_potential_t[n_layouts], cost_lut = ovc_cost_lut_entry_t[n_layouts][256][4],
+ * gpow = double[n_pow] with gpow[k] = gamma**k as computed by the host (the reference evaluates
+ * gamma ** integer in double precision; taking the powers from the host table and following the
+ * reference's order of operations makes the result bit-identical, not merely close).
+ */
+int ovc_potential(const void *layouts, int n_layouts, const void *pot_tables, const void *cost_lut,
+                  const double *gpow, int n_pow, const int32_t *state, double *out, int64_t n_envs,
+                  int state_words, void *stream);
+size_t ovc_potential_table_size(void);
 
 #ifdef __cplusplus
 }

@@ -110,3 +110,16 @@ def featurize(tables, lut, state, num_pots=2):
                              ctypes.c_int(S), ctypes.c_int(num_pots))
     assert rc == 0
     return out
+
+
+def potential(tables, pot_tables, cost_lut, gpow, state):
+    """float64 [N]: potential_function of every record."""
+    state = _i32(state)
+    n, S = state.shape
+    out = np.zeros(n, np.float64)
+    tables, pot_tables, cost_lut = np.ascontiguousarray(tables), np.ascontiguousarray(pot_tables), np.ascontiguousarray(cost_lut)
+    gpow = np.ascontiguousarray(gpow, dtype=np.float64)
+    rc = lib().ovo_potential(_p(tables), ctypes.c_int(len(tables)), _p(pot_tables), _p(cost_lut), _p(gpow),
+                             ctypes.c_int(len(gpow)), _p(state), _p(out), ctypes.c_int64(n), ctypes.c_int(S))
+    assert rc == 0
+    return out

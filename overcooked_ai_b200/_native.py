@@ -45,7 +45,9 @@ def lib():
     L.ovc_reset.argtypes = [vp, i32, vp, vp, vp, i64, i32, vp]
     L.ovc_encode_lossless.argtypes = [vp, i32, vp, vp, vp, i32, i64, i32, i32, i32, i32, vp]
     L.ovc_featurize.argtypes = [vp, i32, vp, vp, vp, vp, i64, i32, i32, vp]
-    for f in (L.ovc_step, L.ovc_rollout, L.ovc_reset, L.ovc_encode_lossless, L.ovc_featurize):
+    L.ovc_potential.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, i64, i32, vp]
+    L.ovc_potential_table_size.restype = ctypes.c_size_t
+    for f in (L.ovc_step, L.ovc_rollout, L.ovc_reset, L.ovc_encode_lossless, L.ovc_featurize, L.ovc_potential):
         f.restype = i32
     if L.ovc_abi_version() != ABI_VERSION:
         raise NativeLibraryError("ABI version mismatch: library %d, binding %d" % (L.ovc_abi_version(), ABI_VERSION))
@@ -55,7 +57,8 @@ def lib():
 
 EXPORTED_SYMBOLS = (
     "ovc_abi_version", "ovc_layout_table_size", "ovc_feat_lut_entry_size", "ovc_last_error",
-    "ovc_step", "ovc_rollout", "ovc_reset", "ovc_encode_lossless", "ovc_featurize",
+    "ovc_step", "ovc_rollout", "ovc_reset", "ovc_encode_lossless", "ovc_featurize", "ovc_potential",
+    "ovc_potential_table_size",
 )
 
 

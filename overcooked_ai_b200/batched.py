@@ -210,6 +210,24 @@ class BatchedOvercookedEnv(object):
             self._stream()))
         return out
 
+    def potential(self, gamma=0.99, out=None):
+        """potential_function (overcooked_mdp.py:2920-3250) of every environment: float64 [N], bit-identical
+        to the reference's Python floats (planner costs from the default NO_COUNTERS_PARAMS planner)."""
+        if getattr(self, "_pot_gamma", None) != gamma:
+            pt, cl, gpow = L.build_potential_tables(self.layouts, gamma)
+            assert pt.shape[1] == self._lib.ovc_potential_table_size()
+            self._pot = (torch.from_numpy(pt).to(self.device), torch.from_numpy(cl).to(self.device),
+                         torch.from_numpy(gpow).to(self.device))
+            self._pot_gamma = gamma
+        if out is None:
+            out = torch.empty(self.n_envs, dtype=torch.float64, device=self.device)
+        assert out.dtype == torch.float64 and out.is_cuda and out.is_contiguous() and out.numel() == self.n_envs
+        pt, cl, gpow = self._pot
+        _native.check(self._lib.ovc_potential(
+            self.tables.data_ptr(), self.n_layouts, pt.data_ptr(), cl.data_ptr(), gpow.data_ptr(), gpow.numel(),
+            self.state.data_ptr(), out.data_ptr(), self.n_envs, self.state_words, self._stream()))
+        return out
+
     # ---------------------------------------------------------------------------------------------
     def sparse_by_agent(self, sparse_unused, events):
         """Per-agent delivery reward from the event words (bits 25-28 carry the delivered recipe)."""

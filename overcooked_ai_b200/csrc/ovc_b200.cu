@@ -364,6 +364,7 @@ static int step_impl(const void *layouts, int n_layouts, const int32_t *start_re
 }  // namespace ovc
 
 #include "ovc_obs.cuh"
+#include "ovc_potential.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // C ABI
@@ -419,5 +420,15 @@ int ovc_featurize(const void *layouts, int n_layouts, const void *lut, const int
     return ovc::featurize_impl((const ovc_layout_t *)layouts, (const ovc_feat_lut_entry_t *)lut, state, view_swap, out,
                                n_envs, state_words, num_pots, (cudaStream_t)stream);
 }
+
+int ovc_potential(const void *layouts, int n_layouts, const void *pot_tables, const void *cost_lut, const double *gpow,
+                  int n_pow, const int32_t *state, double *out, int64_t n_envs, int state_words, void *stream) {
+    int rc = ovc::check_common(layouts, n_layouts, state, n_envs, state_words);
+    if (rc) return rc;
+    return ovc::potential_impl((const ovc_layout_t *)layouts, (const ovc_potential_t *)pot_tables,
+                               (const ovc_cost_lut_entry_t *)cost_lut, gpow, n_pow, state, out, n_envs, state_words,
+                               (cudaStream_t)stream);
+}
+size_t ovc_potential_table_size(void) { return sizeof(ovc_potential_t); }
 
 }  // extern "C"

@@ -63,6 +63,10 @@ class OvercookedEnv(object):
     def featurize_state_mdp(self, state, num_pots=2):
         return self.mdp.featurize_state(state, None, num_pots=num_pots)
 
+    def potential(self, mlam=None, state=None, gamma=0.99):
+        """overcooked_env.py:327-337"""
+        return self.mdp.potential_function(state if state else self.state, gamma=gamma)
+
     def reset(self, regen_mdp=True, outside_info={}):
         if regen_mdp:
             self.mdp = self.mdp_generator_fn(outside_info)

@@ -78,6 +78,25 @@ FEAT_LUT_DTYPE = np.dtype(
 )
 assert FEAT_LUT_DTYPE.itemsize == 12
 
+POTENTIAL_CONSTANTS = {  # overcooked_mdp.py:1060-1073
+    "default": {"max_delivery_steps": 10, "max_pickup_steps": 10, "pot_onion_steps": 10, "pot_tomato_steps": 10},
+    "mdp_test_tomato": {"max_delivery_steps": 4, "max_pickup_steps": 4, "pot_onion_steps": 5, "pot_tomato_steps": 6},
+}
+
+POTENTIAL_DTYPE = np.dtype(
+    [
+        ("steady", "<f8"), ("disc_value", "<f8", (16,)), ("opt_recipe", "<i4", (16,)),
+        ("max_delivery_steps", "<i4"), ("max_pickup_steps", "<i4"), ("pot_onion_steps", "<i4"), ("pot_tomato_steps", "<i4"),
+        ("onion_value", "<i4"), ("tomato_value", "<i4"), ("reserved", "<i4", (2,)),
+        ("partial_order", "u1", (81, 4)), ("pad", "u1", (4,)),
+    ]
+)
+assert POTENTIAL_DTYPE.itemsize == 560
+
+COST_LUT_DTYPE = np.dtype([("serve", "u1"), ("pot", "u1", (MAX_POTS,)), ("pad", "u1", (3,))])
+assert COST_LUT_DTYPE.itemsize == 8
+COST_INF = 255
+
 _DATA = os.path.join(os.path.dirname(__file__), "data", "layouts.json")
 _LAYOUTS = None
 
@@ -296,24 +315,19 @@ class CompiledLayout(object):
         rec["slot_pos"] = sp
         return rec
 
-    # -- featurize_state lookup ------------------------------------------------------------------
-    def feature_lut(self):
-        """Per (cell, orientation): deltas to the closest onion / tomato / dish dispenser and
-        serving cell, and the pots ordered by planner cost.
+    # -- planner distances ------------------------------------------------------------------------
+    def _bfs(self):
+        """For every (free cell, orientation) start: BFS distances over (cell, orientation) nodes.
 
-        Restates MotionPlanner.min_cost_to_feature (planning/planners.py:391-423) for the default
-        NO_COUNTERS_PARAMS (planners.py:27-34): BFS over (cell, orientation) nodes whose edges are
-        the four direction actions (move if the target is floor, else turn in place —
-        _move_if_direction, overcooked_mdp.py:1718-1727; graph at planners.py:315-358); the goals
-        of a feature cell f are (f+d, opposite(d)) for d in N,S,E,W order when f+d is floor
-        (planners.py:439-450); counters are never goals; the first minimum in (feature order,
-        d order) wins (planners.py:406-417).
+        Restates the motion-planner graph of the reference for the default NO_COUNTERS_PARAMS
+        (planning/planners.py:27-34): edges are the four direction actions (move if the target is floor,
+        else turn in place — _move_if_direction, overcooked_mdp.py:1718-1727; graph at planners.py:315-358);
+        the goals of a feature cell f are (f+d, opposite(d)) for d in N,S,E,W order when f+d is floor
+        (planners.py:439-450); counters are never goals.  Yields (start, orientation index, dist, goals_of).
         """
         free = [p for p in self.terrain_pos_dict[" "]]
         free_set = set(free)
         dirs = Direction.ALL_DIRECTIONS
-        lut = np.zeros((256, 4), FEAT_LUT_DTYPE)
-        lut["pot_order"] = NO_SLOT
 
         def goals_of(f):
             out = []
@@ -335,30 +349,127 @@ class CompiledLayout(object):
                         if nxt not in dist:
                             dist[nxt] = dist[(p, o)] + 1
                             q.append(nxt)
+                yield start, so, dist, goals_of
 
-                def closest(features, exclude=()):
-                    best, best_f = None, None
-                    for f in features:
-                        if f in exclude:
-                            continue
-                        for g in goals_of(f):
-                            if g in dist and (best is None or dist[g] < best):
-                                best, best_f = dist[g], f
-                    return best_f
+    @staticmethod
+    def _closest(dist, goals_of, features, exclude=()):
+        """MotionPlanner.min_cost_to_feature (planners.py:391-423): (cost, feature); the first minimum in
+        (feature order, direction order) wins; cost = distance + 1 for the interact; (None, None) if unreachable."""
+        best, best_f = None, None
+        for f in features:
+            if f in exclude:
+                continue
+            for g in goals_of(f):
+                if g in dist and (best is None or dist[g] < best):
+                    best, best_f = dist[g], f
+        return (None if best is None else best + 1), best_f
 
-                e = lut[pos_byte(start), so]
-                for key, terr in (("d_onion", "O"), ("d_tomato", "T"), ("d_dish", "D"), ("d_serve", "S")):
-                    f = closest(self.terrain_pos_dict[terr])
-                    if f is not None:
-                        e[key] = (f[0] - start[0], f[1] - start[1])
-                taken = []
-                for k in range(self.n_pots):
-                    f = closest(self.pot_locations, exclude=taken)
-                    if f is None:
-                        break
-                    taken.append(f)
-                    e["pot_order"][k] = self.slot_of[f]
+    def feature_lut(self):
+        """featurize_state lookup: per (cell, orientation), deltas to the closest onion / tomato / dish
+        dispenser and serving cell, and the pots ordered by planner cost."""
+        lut = np.zeros((256, 4), FEAT_LUT_DTYPE)
+        lut["pot_order"] = NO_SLOT
+        for start, so, dist, goals_of in self._bfs():
+            e = lut[pos_byte(start), so]
+            for key, terr in (("d_onion", "O"), ("d_tomato", "T"), ("d_dish", "D"), ("d_serve", "S")):
+                _, f = self._closest(dist, goals_of, self.terrain_pos_dict[terr])
+                if f is not None:
+                    e[key] = (f[0] - start[0], f[1] - start[1])
+            taken = []
+            for k in range(self.n_pots):
+                _, f = self._closest(dist, goals_of, self.pot_locations, exclude=taken)
+                if f is None:
+                    break
+                taken.append(f)
+                e["pot_order"][k] = self.slot_of[f]
         return lut
+
+    def cost_lut(self):
+        """potential_function lookup: per (cell, orientation), min_cost_to_feature to the serving cells and
+        to each pot (COST_INF = unreachable)."""
+        lut = np.zeros((256, 4), COST_LUT_DTYPE)
+        lut["serve"], lut["pot"] = COST_INF, COST_INF
+        for start, so, dist, goals_of in self._bfs():
+            e = lut[pos_byte(start), so]
+            c, _ = self._closest(dist, goals_of, self.terrain_pos_dict["S"])
+            if c is not None:
+                e["serve"] = min(c, COST_INF - 1)
+            for k, pot in enumerate(self.pot_locations):
+                c, _ = self._closest(dist, goals_of, [pot])
+                if c is not None:
+                    e["pot"][k] = min(c, COST_INF - 1)
+        return lut
+
+    # -- potential_function constants -----------------------------------------------------------
+    def potential_params(self):
+        """overcooked_mdp.py:2972-2982 (onion / tomato value default to 21 / 13 when the layout has none)."""
+        conf = self.recipe_config
+        p = dict(POTENTIAL_CONSTANTS.get(self.layout_name, POTENTIAL_CONSTANTS["default"]))
+        p["tomato_value"] = conf.get("tomato_value") if conf.get("tomato_value") else 13
+        p["onion_value"] = conf.get("onion_value") if conf.get("onion_value") else 21
+        return p
+
+    def potential_table(self, gamma=0.99):
+        """Per-layout constants of potential_function (overcooked_mdp.py:2920-3250) for a given gamma: the
+        discounted best-recipe search (DFS of :1976-2016 with the discounted value of :1603-1629, whose
+        visiting order decides ties), the steady-state term (:2985-2999) and CPython's iteration order of
+        the set built by get_partially_full_pots (:1882-1890), which fixes the order idle soups are visited."""
+        pp = self.potential_params()
+        all_recipes = {r.index: r for r in Recipe.all_recipes()}
+
+        def disc_value(idx, base_idx):
+            o, t = idx >> 2, idx & 3
+            bo, bt = (base_idx >> 2, base_idx & 3) if base_idx else (0, 0)
+            n_on, n_to = o - bo, t - bt
+            return (gamma ** int(self.cook_time[idx]) * gamma ** (pp["pot_onion_steps"] * n_on)
+                    * gamma ** (pp["pot_tomato_steps"] * n_to) * int(self.deliver_value[idx]))
+
+        def neighbors(idx):
+            o, t = idx >> 2, idx & 3
+            if o + t == MAX_NUM_INGREDIENTS:
+                return []
+            return [((o + 1) << 2) | t, (o << 2) | (t + 1)]  # ALL_INGREDIENTS order: onion, tomato (:201-204)
+
+        rec = np.zeros((), POTENTIAL_DTYPE)
+        for start in [0] + sorted(all_recipes):
+            stack = [4, 1] if start == 0 else [start]  # [onion], [tomato] pushed in that order (:1991-1992)
+            visited, best_idx, best_val = set(), start, 0
+            while stack:
+                cur = stack.pop()
+                if cur in visited:
+                    continue
+                visited.add(cur)
+                v = disc_value(cur, start)
+                if v > best_val:
+                    best_val, best_idx = v, cur
+                for nb in neighbors(cur):
+                    if nb not in visited:
+                        stack.append(nb)
+            rec["opt_recipe"][start] = best_idx
+            rec["disc_value"][start] = best_val
+        opt = int(rec["opt_recipe"][0])
+        opt_value = int(self.deliver_value[opt]) if opt else 0
+        if opt_value <= 0:
+            raise ValueError("potential_function needs a recipe with a positive value (overcooked_mdp.py:2996-2998)")
+        discount = float(rec["disc_value"][0]) / opt_value
+        rec["steady"] = (discount / (1 - discount)) * opt_value
+        for k in ("max_delivery_steps", "max_pickup_steps", "pot_onion_steps", "pot_tomato_steps", "onion_value", "tomato_value"):
+            rec[k] = _as_int(pp[k], k)
+        # order of list(set().union(one_item_pots, two_item_pots)) for every assignment of pots to classes
+        order = np.full((81, 4), NO_SLOT, np.uint8)
+        for code in range(3 ** self.n_pots):
+            cls = [(code // 3 ** k) % 3 for k in range(self.n_pots)]
+            ones = [self.pot_locations[k] for k in range(self.n_pots) if cls[k] == 1]
+            twos = [self.pot_locations[k] for k in range(self.n_pots) if cls[k] == 2]
+            for j, pos in enumerate(list(set().union(*[ones, twos]))):
+                order[code, j] = self.slot_of[pos]
+        rec["partial_order"] = order
+        return rec
+
+    def potential_pow_len(self):
+        pp = self.potential_params()
+        return int(self.cook_time.max() + pp["max_delivery_steps"] + pp["max_pickup_steps"]
+                   + 3 * max(pp["pot_onion_steps"], pp["pot_tomato_steps"]) + 8)
 
 
 def compile_layout(layout_name, **params_to_overwrite):
@@ -480,3 +591,12 @@ def build_tables(layouts, state_words=None):
     tab = np.stack([l.table() for l in layouts])
     starts = np.stack([pack_state(l, l.get_standard_start_state(), i, S) for i, l in enumerate(layouts)])
     return tab.view(np.uint8).reshape(len(layouts), -1), starts.astype(np.int32), S
+
+
+def build_potential_tables(layouts, gamma=0.99):
+    """(pot tables uint8 [n, 560], cost LUT uint8 [n, 256*4*8], gamma powers float64 [n_pow])."""
+    pt = np.stack([l.potential_table(gamma) for l in layouts]).view(np.uint8).reshape(len(layouts), -1)
+    cl = np.stack([l.cost_lut() for l in layouts]).view(np.uint8).reshape(len(layouts), -1)
+    n_pow = max(l.potential_pow_len() for l in layouts)
+    gpow = np.array([gamma ** k for k in range(n_pow)], np.float64)  # Python float pow, as the reference computes it
+    return pt, cl, gpow

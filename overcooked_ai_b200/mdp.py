@@ -114,8 +114,6 @@ class OvercookedGridworld(object):
     def get_state_transition(self, state, joint_action, display_phi=False, motion_planner=None):
         """(new_state, infos) exactly like the reference (:1375-1430); infos has ``event_infos``
         (25 event names -> [bool, bool]), ``sparse_reward_by_agent`` and ``shaped_reward_by_agent``."""
-        if display_phi:
-            raise NotImplementedError("potential_function (display_phi) is a 'next' row, SURVEY.md §8f")
         if len(joint_action) != 2:
             raise ValueError("Illegal action %s in state %s" % (joint_action, state))
         try:
@@ -123,6 +121,7 @@ class OvercookedGridworld(object):
         except ValueError:
             raise ValueError("Illegal action %s in state %s" % (joint_action, state))
         eng = self._load(state)
+        phi_s = float(eng.potential(0.99)[0].item()) if display_phi else None
         self._act.copy_(torch.tensor([idx], dtype=torch.int32))
         sparse, shaped, done, events = eng.step(self._act)
         rec = eng.state[0].cpu().numpy()
@@ -140,7 +139,15 @@ class OvercookedGridworld(object):
             "sparse_reward_by_agent": per_agent,
             "shaped_reward_by_agent": [int(shaped[0]), int(shaped[1])],
         }
+        if display_phi:  # :1422-1429
+            infos["phi_s"] = phi_s
+            infos["phi_s_prime"] = float(eng.potential(0.99)[0].item())
         return new_state, infos
+
+    def potential_function(self, state, mp=None, gamma=0.99):
+        """phi(state) (:2920-3250).  ``mp`` is accepted for signature compatibility and ignored: the planner
+        costs of the default NO_COUNTERS_PARAMS planner are baked into the layout's cost table."""
+        return float(self._load(state).potential(gamma)[0].item())
 
     def lossless_state_encoding(self, overcooked_state, horizon=400, debug=False):
         """Tuple of two (W, H, 26) int64 arrays, one per player (:2385-2561)."""

@@ -79,9 +79,16 @@ class BatchedOvercookedGym(object):
 class BatchedOvercookedMultiAgent(object):
     AGENTS = ("ppo_0", "ppo_1")
 
-    def __init__(self, env, reward_shaping_factor=0.0, reward_shaping_horizon=0, obs_dtype=torch.float32):
+    def __init__(self, env, reward_shaping_factor=0.0, reward_shaping_horizon=0, obs_dtype=torch.float32,
+                 use_phi=False, gamma=0.99):
+        """use_phi: dense reward = phi(s') - phi(s) for both agents (rllib.py:314-319) instead of the
+        per-agent shaped reward; the potential of s' is taken BEFORE a finished environment is reset,
+        so the env must be built with auto_reset=False (this wrapper resets finished envs itself)."""
         assert isinstance(env, BatchedOvercookedEnv)
+        assert not (use_phi and env.auto_reset), "use_phi needs auto_reset=False (phi(s') is evaluated on the terminal state)"
         self.env = env
+        self.use_phi, self.gamma = bool(use_phi), gamma
+        self._phi = None
         self._initial_reward_shaping_factor = reward_shaping_factor
         self.reward_shaping_factor = reward_shaping_factor
         self.reward_shaping_horizon = reward_shaping_horizon
@@ -108,6 +115,8 @@ class BatchedOvercookedMultiAgent(object):
 
     def reset(self, regen_mdp=True):
         self.env.reset()
+        if self.use_phi:
+            self._phi = self.env.potential(self.gamma)
         return self._get_obs()
 
     def step(self, action_dict):
@@ -116,7 +125,14 @@ class BatchedOvercookedMultiAgent(object):
         self._joint[:, 1].copy_(action_dict[self.AGENTS[1]])
         sparse, shaped, done, events = self.env.step(self._joint)
         sp = sparse.to(torch.float32)
-        rewards = {a: sp + self.reward_shaping_factor * shaped[:, i].to(torch.float32) for i, a in enumerate(self.AGENTS)}
+        if self.use_phi:
+            phi_next = self.env.potential(self.gamma)
+            dense = (phi_next - self._phi).to(torch.float32)
+            rewards = {a: sp + self.reward_shaping_factor * dense for a in self.AGENTS}
+            self.env.reset(done)  # finished envs start their next episode now
+            self._phi = torch.where(done != 0, self.env.potential(self.gamma), phi_next)
+        else:
+            rewards = {a: sp + self.reward_shaping_factor * shaped[:, i].to(torch.float32) for i, a in enumerate(self.AGENTS)}
         d = done != 0
         dones = {self.AGENTS[0]: d, self.AGENTS[1]: d, "__all__": d}
         info = {"sparse_r": sparse, "shaped_r_by_agent": shaped, "events": events}

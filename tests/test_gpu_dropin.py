@@ -152,3 +152,18 @@ def test_featurization_symmetry():
         f0, f1 = mdp.featurize_state(st, None)
         g0, g1 = mdp.featurize_state(sw, None)
         assert np.array_equal(f0, g1) and np.array_equal(f1, g0)
+
+
+def test_potential_function_and_display_phi():
+    """testing/overcooked_test.py:607-999 style: phi through the drop-in mdp / env, exact reference values."""
+    g = np.load(GOLD + "/potential.npz")
+    tr = Trace(GOLD + "/trace_mdp_test.npz")
+    mdp = OvercookedGridworld.from_layout_name("mdp_test")
+    for k in range(0, len(tr.data["obs_states"]), 301):
+        st = L.unpack_state(mdp.compiled, tr.data["obs_states"][k])
+        assert mdp.potential_function(st, None, gamma=0.99) == g["mdp_test__phi"][k, 0]
+        assert mdp.potential_function(st, None, gamma=0.9) == g["mdp_test__phi"][k, 1]
+    env = OvercookedEnv.from_mdp(mdp, horizon=20, info_level=0)
+    phi0 = env.potential()
+    s1, r, done, info = env.step((n, interact), display_phi=True)
+    assert info["phi_s"] == phi0 and info["phi_s_prime"] == env.potential()

@@ -314,3 +314,31 @@ def test_selfplay_policy_rollout_matches_oracle_replay():
     env2 = BatchedOvercookedEnv("cramped_room", n, horizon=20, auto_reset=True)
     sp2 = SelfPlayRollout(env2, model=sp.model, use_graph=True)
     assert sp2.run(30) == 30 * n and (_np(env2.state)[:, 0] == 30 % 20).all()
+
+
+@pytest.mark.parametrize("gamma_idx,gamma", [(0, 0.99), (1, 0.9)])
+def test_potential_kernel_bit_exact_vs_reference(gamma_idx, gamma):
+    """K6: phi(s) equals the reference's potential_function float for float (fixture from the reference)."""
+    g = np.load(GOLD + "/potential.npz")
+    for path in TRACE_FILES:
+        name = path.split("trace_")[-1][:-4]
+        if name + "__phi" not in g.files:
+            continue
+        tr = Trace(path)
+        st = tr.data["obs_states"]
+        env = _env_for_trace(tr, len(st), 0)
+        env.state.copy_(torch.from_numpy(st))
+        phi = _np(env.potential(gamma))
+        assert phi.dtype == np.float64 and np.array_equal(phi, g[name + "__phi"][:, gamma_idx]), name
+
+
+def test_potential_kernel_vs_oracle_mixed_layouts():
+    n = 5 * 4000 + 7
+    env = BatchedOvercookedEnv(CLASSIC5, n, horizon=400, auto_reset=True)
+    rng = np.random.RandomState(21)
+    env.rollout(torch.from_numpy(_random_actions(rng, 150, n, 0.45)).cuda())
+    st = _np(env.state)
+    pt, cst, gpow = L.build_potential_tables(env.layouts, 0.99)
+    want = cpu.potential(env._tab_host, pt, cst, gpow, st)
+    got = _np(env.potential(0.99))
+    assert np.array_equal(got, want) and len(np.unique(got)) > 50

@@ -85,3 +85,29 @@ def test_multi_agent_wrapper_rewards_and_annealing():
     enc = cpu.encode_lossless(env._tab_host, ref, l.width, l.height, 400).astype(np.float32)
     assert obs["ppo_0"].dtype == torch.float32
     assert np.array_equal(_np(obs["ppo_0"]), enc[:, 0]) and np.array_equal(_np(obs["ppo_1"]), enc[:, 1])
+
+
+def test_multi_agent_wrapper_use_phi_dense_reward():
+    """rllib.py:314-329 with use_phi=True: reward_i = sparse + factor * (phi(s') - phi(s)), phi(s') on the
+    terminal state of a finishing episode."""
+    from overcooked_ai_b200 import layout as L
+
+    n, horizon = 700, 12
+    env = BatchedOvercookedEnv("cramped_room", n, horizon=horizon, auto_reset=False)
+    ma = BatchedOvercookedMultiAgent(env, reward_shaping_factor=0.5, use_phi=True)
+    ma.reset()
+    pt, cst, gpow = L.build_potential_tables(env.layouts, 0.99)
+    ref = _np(env.state).copy()
+    rng = np.random.RandomState(4)
+    for t in range(30):
+        a = rng.randint(0, 6, size=(n, 2)).astype(np.int32)
+        a[rng.rand(n, 2) < 0.4] = 5
+        phi_s = cpu.potential(env._tab_host, pt, cst, gpow, ref)
+        sp, sh, dn, ev = cpu.step(env._tab_host, env._starts_host, ref, a, horizon=horizon, flags=0)
+        phi_n = cpu.potential(env._tab_host, pt, cst, gpow, ref)
+        obs, rew, dones, infos = ma.step({"ppo_0": torch.from_numpy(a[:, 0].copy()).cuda(), "ppo_1": torch.from_numpy(a[:, 1].copy()).cuda()})
+        want = (sp.astype(np.float32) + np.float32(0.5) * (phi_n - phi_s).astype(np.float32)).astype(np.float32)
+        assert np.allclose(_np(rew["ppo_0"]), want, rtol=0, atol=1e-5) and np.array_equal(_np(rew["ppo_0"]), _np(rew["ppo_1"]))
+        assert np.array_equal(_np(dones["__all__"]), dn != 0)
+        ref[dn != 0] = env._starts_host[0]
+        assert np.array_equal(_np(env.state), ref)

@@ -139,3 +139,30 @@ def test_pack_unpack_roundtrip_against_reference_dicts(path):
     flat = tr.states.reshape(-1, tr.S)[:: max(1, tr.states.size // tr.S // 300)]
     for rec in flat:
         assert np.array_equal(L.pack_state(tr.layout, L.unpack_state(tr.layout, rec), 0, tr.S), rec)
+
+
+def _potential_cases():
+    g = np.load(GOLD + "/potential.npz")
+    for path in TRACE_FILES:
+        name = path.split("trace_")[-1][:-4]
+        if name + "__phi" in g.files:
+            yield path, name, g
+
+
+@pytest.mark.parametrize("gamma_idx,gamma", [(0, 0.99), (1, 0.9)])
+def test_potential_function_bit_exact(gamma_idx, gamma):
+    """potential_function (overcooked_mdp.py:2920-3250): the C oracle reproduces the reference's Python floats
+    exactly (==, not allclose) on every fixture state; the planner costs it uses equal the reference
+    MotionPlanner's min_cost_to_feature."""
+    n_states = 0
+    for path, name, g in _potential_cases():
+        tr = Trace(path)
+        cl = tr.layout
+        cost = cl.cost_lut()
+        assert np.array_equal(cost["serve"], g[name + "__cost"][..., 0]), name
+        assert np.array_equal(cost["pot"][..., :cl.n_pots], g[name + "__cost"][..., 1:1 + cl.n_pots]), name
+        pt, cst, gpow = L.build_potential_tables([cl], gamma)
+        phi = cpu.potential(tr.tables, pt, cst, gpow, tr.data["obs_states"])
+        assert np.array_equal(phi, g[name + "__phi"][:, gamma_idx]), name
+        n_states += len(phi)
+    assert n_states > 10000

@@ -253,6 +253,39 @@ def gen_planner_luts(ns):
     print("planner_luts: %d layouts" % len(out))
 
 
+def gen_potential(ns):
+    """potential_function (overcooked_mdp.py:2920-3250, gamma 0.99 and 0.9) of the reference on the observation
+    states of every trace fixture, plus the MotionPlanner costs it consumes — pins the potential oracle/kernel."""
+    out = {}
+    for name, layout, params, eps, steps in TRACE_LAYOUTS:
+        d = np.load(os.path.join(GOLD, "trace_%s.npz" % name))
+        m = refboot.make_mdp(ns, layout, **params)
+        refboot.use_mdp(ns, m)
+        cl = L.compile_layout(layout, **params)
+        if cl.width * cl.height > 70:
+            continue  # corridor: the reference planner needs minutes
+        mp = ns.planners.MotionPlanner(m)
+        states = d["obs_states"]
+        phis = np.zeros((len(states), 2), np.float64)
+        for k, rec in enumerate(states):
+            st = L.unpack_state(cl, rec)
+            ref_st = ns.mdp.OvercookedState.from_dict(jsonable(st.to_dict()))
+            phis[k, 0] = m.potential_function(ref_st, mp, gamma=0.99)
+            phis[k, 1] = m.potential_function(ref_st, mp, gamma=0.9)
+        cost = np.full((256, 4, 5), 255, np.int32)
+        for pos in m.get_valid_player_positions():
+            for oi, o in enumerate(ns.actions.Direction.ALL_DIRECTIONS):
+                c = mp.min_cost_to_feature((pos, o), m.get_serving_locations())
+                cost[L.pos_byte(pos), oi, 0] = 255 if c == np.inf else int(c)
+                for j, pot in enumerate(m.get_pot_locations()):
+                    c = mp.min_cost_to_feature((pos, o), [pot])
+                    cost[L.pos_byte(pos), oi, 1 + j] = 255 if c == np.inf else int(c)
+        out[name + "__phi"] = phis
+        out[name + "__cost"] = cost.astype(np.uint8)
+        print("potential %s: %d states, phi range [%.3f, %.3f]" % (name, len(states), phis[:, 0].min(), phis[:, 0].max()))
+    np.savez_compressed(os.path.join(GOLD, "potential.npz"), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ns = refboot.boot()
@@ -267,6 +300,8 @@ def main():
         gen_greedy_cramped_room(ns)
     if not only or "luts" in only:
         gen_planner_luts(ns)
+    if not only or "potential" in only:
+        gen_potential(ns)
     print("done in %.1fs" % (time.time() - t0))
 
 
