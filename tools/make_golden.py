@@ -253,11 +253,63 @@ def gen_planner_luts(ns):
     print("planner_luts: %d layouts" % len(out))
 
 
+def gen_human_2020(ns):
+    """Real human-human games (src/human_aware_rl/static/human_data/dummy/dummy_2020_hh_trials.csv; the
+    reference replays such data in human_aware_rl/human/tests.py:197-211): every recorded transition is
+    pushed through the reference's get_state_transition and must land on the next recorded state and
+    reward; stored in the trace-fixture format."""
+    import pandas as pd
+
+    csv = os.path.join(refboot.REFERENCE_ROOT, "src", "human_aware_rl", "static", "human_data", "dummy", "dummy_2020_hh_trials.csv")
+    df = pd.read_csv(csv)
+    for (layout, trial), g in df.groupby(["layout_name", "trial_id"], sort=False):
+        m = refboot.make_mdp(ns, layout)
+        refboot.use_mdp(ns, m)
+        cl = L.compile_layout(layout)
+        S = cl.state_words
+        rows = list(g.sort_values("cur_gameloop").itertuples())
+        acts = []
+        for r in rows:
+            ja = [tuple(x) if isinstance(x, list) else x.lower() for x in json.loads(r.joint_action)]
+            acts.append([ns.actions.Action.ACTION_TO_INDEX[a] for a in ja])
+        acts = np.array(acts, np.int32)
+        start = ns.mdp.OvercookedState.from_dict(json.loads(rows[0].state))
+        states, sparse, shaped, events, _ = run_trace(ns, m, cl, start, acts, S)
+        for t in range(len(rows) - 1):
+            exp = ns.mdp.OvercookedState.from_dict(json.loads(rows[t + 1].state))
+            assert np.array_equal(states[t + 1], pack_ref(cl, exp, S)), (layout, t)
+            assert sparse[t].sum() == rows[t].reward, (layout, t)
+        holder = refboot.LitePlannerHolder(ns, m)
+        obs_states, obs_lossless, obs_feat = [], [], {0: [], 1: [], 2: [], 3: []}
+        for t in range(0, len(rows), 9):
+            st = L.unpack_state(cl, states[t])
+            ref_st = ns.mdp.OvercookedState.from_dict(jsonable(st.to_dict()))
+            obs_states.append(states[t])
+            obs_lossless.append(np.stack(m.lossless_state_encoding(ref_st, horizon=400)).astype(np.int16))
+            for npots in obs_feat:
+                obs_feat[npots].append(np.stack(m.featurize_state(ref_st, holder, num_pots=npots)))
+        out = dict(layout=layout, params=json.dumps({}), horizon=400, states=states[None], actions=acts[None],
+                   sparse=sparse[None], shaped=shaped[None], events=events[None],
+                   to_dict_sample=json.dumps({"0": json.loads(rows[0].state), "200": json.loads(rows[200].state)}),
+                   obs_states=np.stack(obs_states), obs_lossless=np.stack(obs_lossless))
+        for npots, v in obs_feat.items():
+            out["obs_feat_%d" % npots] = np.stack(v).astype(np.int16)
+        np.savez_compressed(os.path.join(GOLD, "trace_human2020_%s.npz" % layout), **out)
+        print("trace_human2020_%s: %d recorded transitions, sparse sum %d, deliveries %d" % (
+            layout, len(rows), int(sparse.sum()), int(((events >> 15) & 1).sum())))
+
+
 def gen_potential(ns):
     """potential_function (overcooked_mdp.py:2920-3250, gamma 0.99 and 0.9) of the reference on the observation
     states of every trace fixture, plus the MotionPlanner costs it consumes — pins the potential oracle/kernel."""
     out = {}
-    for name, layout, params, eps, steps in TRACE_LAYOUTS:
+    import glob
+
+    cases = [(n, l, p) for n, l, p, _, _ in TRACE_LAYOUTS]
+    for path in sorted(glob.glob(os.path.join(GOLD, "trace_human2020_*.npz"))):
+        nm = os.path.basename(path)[len("trace_"):-4]
+        cases.append((nm, nm[len("human2020_"):], {}))
+    for name, layout, params in cases:
         d = np.load(os.path.join(GOLD, "trace_%s.npz" % name))
         m = refboot.make_mdp(ns, layout, **params)
         refboot.use_mdp(ns, m)
@@ -300,6 +352,8 @@ def main():
         gen_greedy_cramped_room(ns)
     if not only or "luts" in only:
         gen_planner_luts(ns)
+    if not only or "human" in only:
+        gen_human_2020(ns)
     if not only or "potential" in only:
         gen_potential(ns)
     print("done in %.1fs" % (time.time() - t0))
