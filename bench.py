@@ -352,10 +352,9 @@ def main():
     value = tot_steps / (max_ms * 1e-3)
 
     # ---- e2e: the same workload through the public host-buffer API ----
-    e2e = None
-    if not args.no_e2e:
-        pipe = HostRolloutPipeline(env, T, chunk=50)
-        h_actions = torch.empty((T, n_envs, 2), dtype=torch.int32, pin_memory=True)
+    def run_e2e(narrow):
+        pipe = HostRolloutPipeline(env, T, chunk=50, narrow=narrow)
+        h_actions = torch.empty((T, n_envs, 2), dtype=pipe.act_dtype, pin_memory=True)
         h_actions.copy_(actions)
         env.reset()
         for _ in range(2):
@@ -370,11 +369,19 @@ def main():
         e2e_ms = (time.perf_counter() - t0) * 1e3
         D.barrier()
         _, e2e_max_ms, _ = D.reduce_counters(0, e2e_ms, 0, device=dev)
-        e2e = {"value": float(n_envs) * T * k_e2e * world / (e2e_max_ms * 1e-3), "unit": "env-steps/s",
-               "h2d_bytes_per_step": pipe.h2d_bytes_per_step * T, "d2h_bytes_per_step": pipe.d2h_bytes_per_step * T,
-               "steps": k_e2e, "ms_per_step": e2e_max_ms / k_e2e,
-               "api": "overcooked_ai_b200.batched.HostRolloutPipeline.run (pinned host actions in, pinned host rewards/done/events out, 50-transition chunks)",
-               "checksum_sparse": int(h_out[0].sum().item())}
+        return {"value": float(n_envs) * T * k_e2e * world / (e2e_max_ms * 1e-3), "unit": "env-steps/s",
+                "h2d_bytes_per_step": pipe.h2d_bytes_per_step * T, "d2h_bytes_per_step": pipe.d2h_bytes_per_step * T,
+                "steps": k_e2e, "ms_per_step": e2e_max_ms / k_e2e,
+                "api": "overcooked_ai_b200.batched.HostRolloutPipeline(narrow=%s).run: pinned host actions (%s) in, pinned host "
+                       "sparse/shaped/done/events (%s) out, 50-transition chunks, H2D / fused rollout kernel / D2H on three streams"
+                       % (narrow, "uint8" if narrow else "int32", "int16/int8/uint8/int32" if narrow else "int32"),
+                "checksum_sparse": int(h_out[0].sum(dtype=torch.int64).item())}
+
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(env.narrow_ok())
+        if env.narrow_ok():
+            e2e["int32_formats"] = run_e2e(False)  # the same pipeline with the 32-bit-everything formats
 
     # ---- the per-transition kernel K1 (400 launches from one CUDA graph), measured in the same run ----
     k1_steps = max(2, min(args.steps, 5))

@@ -187,6 +187,13 @@ typedef struct ovc_cost_lut_entry {
  * prologue (barrier init, layout-table fetch) overlaps the tail of the previous kernel in the stream;
  * every read of state / actions happens after griddepcontrol.wait, so results are unchanged. */
 #define OVC_F_PDL 2
+/* narrow host-transfer formats (same values, fewer bytes over PCIe: 15 instead of 32 per env-step):
+ *   OVC_F_ACT_U8      `actions` is uint8[..][2] instead of int32[..][2]
+ *   OVC_F_OUT_NARROW  `sparse` is int16[..], `shaped` is int8[..][2], `done` is uint8[..]; `events` stays
+ *                     int32[..][2].  The host must make sure the layout's rewards fit (the Python layer
+ *                     checks deliver_value <= 32767 and shaping rewards <= 127 before it sets the flag). */
+#define OVC_F_ACT_U8 4
+#define OVC_F_OUT_NARROW 8
 /* bits 8-11 select the record I/O strategy of the step kernel (0 = library default):
  *   1 = 2-D tensor-map TMA tile with hardware swizzle, 2 = 1-D bulk TMA (linear tile),
  *   3 = direct vectorised global loads/stores (no staging).  All produce identical results. */
@@ -209,7 +216,7 @@ const char *ovc_last_error(void);
  *   layouts        ovc_layout_t[n_layouts]
  *   start_records  int32[n_layouts][S], the packed standard start state per layout (auto reset)
  *   state          int32[n_envs][S], updated in place
- *   actions        int32[n_envs][2], values 0..5
+ *   actions        int32[n_envs][2], values 0..5   (uint8[n_envs][2] with OVC_F_ACT_U8)
  *   sparse         int32[n_envs]      sum over both agents of the delivery reward (env.step's r)
  *   shaped         int32[n_envs][2]   shaped_reward_by_agent
  *   done           int32[n_envs]      1 iff new timestep >= horizon

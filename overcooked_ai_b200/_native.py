@@ -13,6 +13,8 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libovc_b200.so")
 ABI_VERSION = 1
 F_AUTO_RESET = 1
 F_PDL = 2
+F_ACT_U8 = 4
+F_OUT_NARROW = 8
 F_IO_SHIFT = 8
 IO_DEFAULT, IO_TMA_TENSOR, IO_TMA_BULK, IO_DIRECT = 0, 1, 2, 3
 DT_F32, DT_U8, DT_I32 = 0, 1, 2

@@ -126,27 +126,49 @@ class BatchedOvercookedEnv(object):
             events.data_ptr(), self.n_envs, self.state_words, self.horizon, self._flags(), self._stream()))
         return sparse, shaped, done, events
 
+    def narrow_ok(self):
+        """True if every layout's rewards fit the narrow transfer formats (int16 sparse, int8 shaped)."""
+        return all(int(l.deliver_value.max()) * 2 <= 32767 and max(
+            int(l.reward_shaping_params[k]) for k in ("PLACEMENT_IN_POT_REW", "DISH_PICKUP_REWARD", "SOUP_PICKUP_REWARD")) <= 127
+            for l in self.layouts)
+
+    def alloc_rollout_out(self, T, narrow=False, pin=False):
+        """Output tensors for rollout(): (sparse[T,N], shaped[T,N,2], done[T,N], events[T,N,2]); int32, or with
+        ``narrow`` int16 / int8 / uint8 / int32 (15 instead of 32 bytes per env-step across PCIe with uint8 actions)."""
+        N = self.n_envs
+        dts = (torch.int16, torch.int8, torch.uint8, torch.int32) if narrow else (torch.int32,) * 4
+        shapes = ((T, N), (T, N, 2), (T, N), (T, N, 2))
+        if pin:
+            return tuple(torch.empty(sh, dtype=dt, pin_memory=True) for sh, dt in zip(shapes, dts))
+        return tuple(torch.empty(sh, dtype=dt, device=self.device) for sh, dt in zip(shapes, dts))
+
     def rollout(self, actions, out=None):
         """T transitions in one launch (state stays on chip between them).
 
-        actions  int32 CUDA tensor [T, N, 2];  out: optional (sparse[T,N], shaped[T,N,2], done[T,N], events[T,N,2])
+        actions  int32 or uint8 CUDA tensor [T, N, 2]
+        out      optional (sparse[T,N], shaped[T,N,2], done[T,N], events[T,N,2]): all int32, or the narrow set of
+                 alloc_rollout_out(narrow=True).
         Equivalent to T calls of step() with the same actions.
         """
-        assert actions.dtype == torch.int32 and actions.is_cuda and actions.is_contiguous() and actions.dim() == 3
+        assert actions.dtype in (torch.int32, torch.uint8) and actions.is_cuda and actions.is_contiguous() and actions.dim() == 3
         T = actions.shape[0]
         assert actions.shape[1] == self.n_envs and actions.shape[2] == 2
         if out is None:
-            out = (
-                torch.empty((T, self.n_envs), dtype=torch.int32, device=self.device),
-                torch.empty((T, self.n_envs, 2), dtype=torch.int32, device=self.device),
-                torch.empty((T, self.n_envs), dtype=torch.int32, device=self.device),
-                torch.empty((T, self.n_envs, 2), dtype=torch.int32, device=self.device),
-            )
+            out = self.alloc_rollout_out(T)
         sparse, shaped, done, events = out
+        flags = self._flags()
+        if actions.dtype == torch.uint8:
+            flags |= _native.F_ACT_U8
+        if sparse.dtype == torch.int16:
+            assert shaped.dtype == torch.int8 and done.dtype == torch.uint8 and events.dtype == torch.int32
+            assert self.narrow_ok(), "rewards of these layouts do not fit the narrow formats"
+            flags |= _native.F_OUT_NARROW
+        else:
+            assert sparse.dtype == shaped.dtype == done.dtype == events.dtype == torch.int32
         _native.check(self._lib.ovc_rollout(
             self.tables.data_ptr(), self.n_layouts, self.start_records.data_ptr(), self.state.data_ptr(),
             actions.data_ptr(), sparse.data_ptr(), shaped.data_ptr(), done.data_ptr(), events.data_ptr(),
-            self.n_envs, T, self.state_words, self.horizon, self._flags(), self._stream()))
+            self.n_envs, T, self.state_words, self.horizon, flags, self._stream()))
         return out
 
     # ---------------------------------------------------------------------------------------------
@@ -262,20 +284,21 @@ class HostRolloutPipeline(object):
     host->device and 24 bytes device->host.
     """
 
-    def __init__(self, env, n_steps, chunk=50):
-        self.env, self.T, self.chunk = env, int(n_steps), int(chunk)
+    def __init__(self, env, n_steps, chunk=50, narrow=False):
+        """narrow=True: uint8 actions in, int16 sparse / int8 shaped / uint8 done / int32 events out — the same
+        values in 2 + 13 instead of 8 + 24 bytes per env-step."""
+        self.env, self.T, self.chunk, self.narrow = env, int(n_steps), int(chunk), bool(narrow)
         N, dev = env.n_envs, env.device
         self.s_h2d, self.s_comp, self.s_d2h = (torch.cuda.Stream(dev) for _ in range(3))
-        mk = lambda *shape: torch.empty(shape, dtype=torch.int32, device=dev)
-        self.d_act = [mk(chunk, N, 2) for _ in range(2)]
-        self.d_out = [(mk(chunk, N), mk(chunk, N, 2), mk(chunk, N), mk(chunk, N, 2)) for _ in range(2)]
-        pin = lambda *shape: torch.empty(shape, dtype=torch.int32, pin_memory=True)
-        self.h_out = (pin(self.T, N), pin(self.T, N, 2), pin(self.T, N), pin(self.T, N, 2))
-        self.h2d_bytes_per_step = N * 2 * 4
-        self.d2h_bytes_per_step = N * (1 + 2 + 1 + 2) * 4
+        self.act_dtype = torch.uint8 if narrow else torch.int32
+        self.d_act = [torch.empty((chunk, N, 2), dtype=self.act_dtype, device=dev) for _ in range(2)]
+        self.d_out = [env.alloc_rollout_out(chunk, narrow=narrow) for _ in range(2)]
+        self.h_out = env.alloc_rollout_out(self.T, narrow=narrow, pin=True)
+        self.h2d_bytes_per_step = N * 2 * self.d_act[0].element_size()
+        self.d2h_bytes_per_step = sum(N * (2 if o.dim() == 3 else 1) * o.element_size() for o in self.h_out)
 
     def run(self, actions_host):
-        assert actions_host.dtype == torch.int32 and actions_host.is_pinned() and tuple(actions_host.shape) == (self.T, self.env.n_envs, 2)
+        assert actions_host.dtype == self.act_dtype and actions_host.is_pinned() and tuple(actions_host.shape) == (self.T, self.env.n_envs, 2)
         env = self.env
         cur = torch.cuda.current_stream(env.device)
         for s in (self.s_h2d, self.s_comp, self.s_d2h):

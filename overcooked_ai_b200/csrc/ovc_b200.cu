@@ -146,10 +146,24 @@ struct StepArgs {
 };
 
 __device__ __forceinline__ void write_outputs(const StepArgs &a, long long idx, const StepOut &o) {
-    a.sparse[idx] = o.sparse;
-    a.done[idx] = o.done;
-    reinterpret_cast<int2 *>(a.shaped)[idx] = make_int2(o.shaped0, o.shaped1);
+    if (a.flags & OVC_F_OUT_NARROW) {  // uniform branch: int16 / int8x2 / uint8 for host transfer
+        reinterpret_cast<short *>(a.sparse)[idx] = (short)o.sparse;
+        reinterpret_cast<unsigned char *>(a.done)[idx] = (unsigned char)o.done;
+        reinterpret_cast<char2 *>(a.shaped)[idx] = make_char2((signed char)o.shaped0, (signed char)o.shaped1);
+    } else {
+        a.sparse[idx] = o.sparse;
+        a.done[idx] = o.done;
+        reinterpret_cast<int2 *>(a.shaped)[idx] = make_int2(o.shaped0, o.shaped1);
+    }
     reinterpret_cast<int2 *>(a.events)[idx] = make_int2((int)o.ev0, (int)o.ev1);
+}
+
+__device__ __forceinline__ int2 load_action(const StepArgs &a, long long idx) {
+    if (a.flags & OVC_F_ACT_U8) {
+        const uchar2 u = reinterpret_cast<const uchar2 *>(a.actions)[idx];
+        return make_int2(u.x, u.y);
+    }
+    return reinterpret_cast<const int2 *>(a.actions)[idx];
 }
 
 // Shared-memory plan of one CTA (dynamic, 1024-byte aligned so the TMA swizzle pattern lines up with
@@ -174,7 +188,7 @@ step_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
         const TblG tb{reinterpret_cast<const char *>(a.layouts)};
         for (int t = 0; t < T; t++) {
             const long long idx = (long long)t * a.n_envs + env;
-            const int2 act = reinterpret_cast<const int2 *>(a.actions)[idx];
+            const int2 act = load_action(a, idx);
             StepOut o;
             step_core(r, tb, a.start_records, S, act.x, act.y, a.horizon, a.flags, o);
             write_outputs(a, idx, o);
@@ -208,7 +222,7 @@ step_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
     }
     // the first action fetch overlaps the tile load
     int2 act = make_int2(OVC_A_STAY, OVC_A_STAY);
-    if (live) act = reinterpret_cast<const int2 *>(a.actions)[env];
+    if (live) act = load_action(a, env);
     __syncthreads();  // barrier initialised and visible before anyone polls it
     mbar_wait(bar, 0);
 
@@ -218,7 +232,7 @@ step_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
             for (int t = 0; t < T; t++) {
                 const long long idx = (long long)t * a.n_envs + env;
                 int2 nxt = act;
-                if (t + 1 < T) nxt = reinterpret_cast<const int2 *>(a.actions)[idx + a.n_envs];  // prefetch
+                if (t + 1 < T) nxt = load_action(a, idx + a.n_envs);  // prefetch
                 StepOut o;
                 step_core(r, tb, a.start_records, S, act.x, act.y, a.horizon, a.flags, o);
                 write_outputs(a, idx, o);
@@ -342,8 +356,11 @@ static int step_impl(const void *layouts, int n_layouts, const int32_t *start_re
     if (rc) return rc;
     if (!actions || !sparse || !shaped || !done || !events || !start_records)
         return fail(OVC_E_BADARG, "null pointer argument%s", "");
-    if ((((uintptr_t)actions | (uintptr_t)shaped | (uintptr_t)events) & 7) != 0)
+    if ((((flags & OVC_F_ACT_U8) ? 0 : (uintptr_t)actions) | ((flags & OVC_F_OUT_NARROW) ? 0 : (uintptr_t)shaped) |
+         (uintptr_t)events) & 7)
         return fail(OVC_E_BADARG, "actions / shaped / events must be 8-byte aligned%s", "");
+    if ((((flags & OVC_F_ACT_U8) ? (uintptr_t)actions : 0) | ((flags & OVC_F_OUT_NARROW) ? ((uintptr_t)shaped | (uintptr_t)sparse) : 0)) & 1)
+        return fail(OVC_E_BADARG, "narrow actions / shaped / sparse must be 2-byte aligned%s", "");
     if (n_steps < 1) return fail(OVC_E_BADARG, "n_steps must be >= 1%s", "");
     if (n_envs == 0) return OVC_OK;
     int io = (flags & OVC_F_IO_MASK) >> OVC_F_IO_SHIFT;

@@ -342,3 +342,27 @@ def test_potential_kernel_vs_oracle_mixed_layouts():
     want = cpu.potential(env._tab_host, pt, cst, gpow, st)
     got = _np(env.potential(0.99))
     assert np.array_equal(got, want) and len(np.unique(got)) > 50
+
+
+def test_narrow_transfer_formats_and_host_pipeline():
+    """uint8 actions in / int16-int8-uint8 outputs: the same values as the int32 formats; the host pipeline
+    (pinned host buffers, chunked, three streams) equals one device-side rollout."""
+    from overcooked_ai_b200.batched import HostRolloutPipeline
+
+    n, T = 3001, 130
+    rng = np.random.RandomState(31)
+    acts = _random_actions(rng, T, n, 0.4)
+    env_a = BatchedOvercookedEnv("cramped_room", n, horizon=50, auto_reset=True)
+    env_b = BatchedOvercookedEnv("cramped_room", n, horizon=50, auto_reset=True)
+    assert env_a.narrow_ok()
+    want = env_a.rollout(torch.from_numpy(acts).cuda())
+    for narrow in (True, False):
+        env_b.reset()
+        pipe = HostRolloutPipeline(env_b, T, chunk=32, narrow=narrow)
+        h_act = torch.from_numpy(acts.astype(np.uint8 if narrow else np.int32)).pin_memory()
+        got = pipe.run(h_act)
+        torch.cuda.synchronize()
+        assert got[0].dtype == (torch.int16 if narrow else torch.int32) and got[0].is_pinned()
+        for g, w in zip(got, want):
+            assert np.array_equal(g.numpy().astype(np.int64), _np(w).astype(np.int64))
+        assert torch.equal(env_b.state, env_a.state)
