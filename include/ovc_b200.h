@@ -28,7 +28,7 @@
  *   word 3        bits 0-7   layout id (index into the layout table)
  *                 bits 8-15  number of loose dishes on counters (derived cache, kept by every
  *                            kernel; pack() computes it)
- *                 bits 16-31 reserved, zero
+ *                 bits 16-31 episode counter of the random-start generator (0 unless random starts are used)
  *   word 4+k      object on object-capable cell k, 22-bit object code (0 = empty).
  *                 Cells are ordered: the layout's pots (terrain row-major order, = the order of
  *                 get_pot_locations(), :1799) first, then its counters 'X' (row-major).
@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define OVC_ABI_VERSION 1
+#define OVC_ABI_VERSION 2
 
 /* ---- action indices: Action.INDEX_TO_ACTION, actions.py:47-57 ---- */
 #define OVC_A_NORTH 0
@@ -133,7 +133,8 @@ typedef struct ovc_layout {
     int32_t rew_dish_pickup;
     int32_t rew_soup_pickup;
     int32_t state_words; /* smallest supported S that holds this layout */
-    int32_t reserved[7];
+    int32_t n_free;      /* number of floor cells (valid player positions) */
+    int32_t reserved[6];
     /* recipe tables, index r = n_onion*4 + n_tomato (r == 0: empty pot) */
     int32_t cook_time[16];     /* Recipe.time, :163-188 */
     int32_t deliver_value[16]; /* get_recipe_value, :1581-1602 (bonus and all_orders applied) */
@@ -141,7 +142,8 @@ typedef struct ovc_layout {
     /* cell[y<<4|x]: bits 0-2 terrain code, bits 8-15 object slot (OVC_NO_SLOT if none) */
     uint16_t cell[256];
     uint8_t slot_pos[128]; /* slot -> pos byte */
-} ovc_layout_t;
+    uint8_t free_pos[128]; /* floor cells in terrain row-major order (get_valid_player_positions, :1733) */
+} ovc_layout_t;           /* 1024 bytes */
 
 /* ---- per-(layout, cell, orientation) lookup for featurize_state; see ovc_featurize ---- */
 typedef struct ovc_feat_lut_entry {
@@ -174,6 +176,21 @@ typedef struct ovc_cost_lut_entry {
     uint8_t pad[3];
 } ovc_cost_lut_entry_t; /* 8 bytes */
 #define OVC_COST_INF 255
+
+/* ---- random start states: get_random_start_state_fn (overcooked_mdp.py:1307-1369) ----
+ * The reference draws from numpy's global generator, which a device engine cannot reproduce; the engine
+ * uses Philox4x32-10 keyed by `seed`, counter (env index, episode counter, draw block), mirrored bit for
+ * bit by the CPU oracle.  Draw plan per reset: block 0 = {joint position, p0 holds?, p0 object, p0 n},
+ * block 1 = {p0 m, p1 holds?, p1 object, p1 n}, block 2 = {p1 m, -, -, -}, block 3+k = pot k {filled?, n, m,
+ * cooking?}.  "u < p" is `draw < threshold` with threshold = p * 2^32; randint(lo, hi) is lo + mulhi(draw, hi-lo);
+ * the object is a dish / onion / soup with probability 0.2 / 0.6 / 0.2 (:1351-1353), a held soup is finished,
+ * a pot soup has n in 1..3 onions then m in 0..3-n tomatoes and is cooking (tick 0) or idle.
+ * Passed by HOST pointer (NULL = standard start states). */
+typedef struct ovc_random_start {
+    uint64_t seed;
+    uint32_t obj_threshold;   /* rnd_obj_prob_thresh * 2^32 (0: no random objects, as :1325-1326) */
+    int32_t random_start_pos; /* non-zero: a uniformly drawn ordered pair of distinct floor cells (:1311-1315) */
+} ovc_random_start_t;
 
 /* ---- error codes ---- */
 #define OVC_OK 0
@@ -225,7 +242,7 @@ const char *ovc_last_error(void);
 int ovc_step(const void *layouts, int n_layouts, const int32_t *start_records, int32_t *state,
              const int32_t *actions, int32_t *sparse, int32_t *shaped, int32_t *done,
              int32_t *events, int64_t n_envs, int state_words, int horizon, int flags,
-             void *stream);
+             const ovc_random_start_t *random_start, void *stream);
 
 /*
  * T consecutive transitions in ONE launch (the record stays on chip between transitions).
@@ -235,16 +252,17 @@ int ovc_step(const void *layouts, int n_layouts, const int32_t *start_records, i
 int ovc_rollout(const void *layouts, int n_layouts, const int32_t *start_records, int32_t *state,
                 const int32_t *actions, int32_t *sparse, int32_t *shaped, int32_t *done,
                 int32_t *events, int64_t n_envs, int n_steps, int state_words, int horizon,
-                int flags, void *stream);
+                int flags, const ovc_random_start_t *random_start, void *stream);
 
 /*
  * OvercookedEnv.reset (overcooked_env.py:288-319) for the envs whose mask[i] != 0 (all if mask
  * is NULL): state[i] = start_records[layout]; layout = env_layout[i] if env_layout != NULL, else
- * the id already stored in the record.
+ * the id already stored in the record.  With `random_start` the record is drawn instead (see above) and the
+ * episode counter of the record advances; auto-reset inside ovc_step / ovc_rollout does the same.
  */
-int ovc_reset(const int32_t *start_records, int n_layouts, int32_t *state,
+int ovc_reset(const void *layouts, int n_layouts, const int32_t *start_records, int32_t *state,
               const int32_t *env_layout, const int32_t *mask, int64_t n_envs, int state_words,
-              void *stream);
+              const ovc_random_start_t *random_start, void *stream);
 
 /*
  * lossless_state_encoding (:2385-2561) for envs [0, n_envs) that all share one layout shape:

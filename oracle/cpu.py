@@ -44,7 +44,32 @@ def _i32(a):
     return a
 
 
-def step(tables, starts, state, actions, horizon=400, flags=0, n_threads=1):
+class RandomStart(ctypes.Structure):
+    """ovc_random_start_t"""
+    _fields_ = [("seed", ctypes.c_uint64), ("obj_threshold", ctypes.c_uint32), ("random_start_pos", ctypes.c_int32)]
+
+
+def random_start(seed, rnd_obj_prob_thresh=0.0, random_start_pos=False):
+    thr = min(int(rnd_obj_prob_thresh * 4294967296.0), 0xFFFFFFFF)
+    return RandomStart(int(seed) & 0xFFFFFFFFFFFFFFFF, thr, int(bool(random_start_pos)))
+
+
+def _rs(rs):
+    return ctypes.byref(rs) if rs is not None else None
+
+
+def reset_random(tables, starts, state, rs, env_layout=None, mask=None):
+    assert state.dtype == np.int32 and state.flags.c_contiguous
+    n, S = state.shape
+    tables, starts = np.ascontiguousarray(tables), _i32(starts)
+    el = None if env_layout is None else _i32(env_layout)
+    mk = None if mask is None else _i32(mask)
+    rc = lib().ovo_reset_random(_p(tables), ctypes.c_int(len(tables)), _p(starts), _p(state), None if el is None else _p(el),
+                                None if mk is None else _p(mk), ctypes.c_int64(n), ctypes.c_int(S), _rs(rs))
+    assert rc == 0
+
+
+def step(tables, starts, state, actions, horizon=400, flags=0, n_threads=1, rs=None):
     """One transition in place on ``state`` [N,S] int32.  Returns sparse[N], shaped[N,2], done[N], events[N,2]."""
     assert state.dtype == np.int32 and state.flags.c_contiguous
     n, S = state.shape
@@ -57,12 +82,12 @@ def step(tables, starts, state, actions, horizon=400, flags=0, n_threads=1):
     starts = _i32(starts)
     rc = lib().ovo_step(_p(tables), ctypes.c_int(len(tables)), _p(starts), _p(state), _p(actions), _p(sparse),
                         _p(shaped), _p(done), _p(events), ctypes.c_int64(n), ctypes.c_int(S), ctypes.c_int(horizon),
-                        ctypes.c_int(flags), ctypes.c_int(n_threads))
+                        ctypes.c_int(flags), ctypes.c_int(n_threads), _rs(rs))
     assert rc == 0
     return sparse, shaped, done, events
 
 
-def rollout(tables, starts, state, actions, horizon=400, flags=0, n_threads=0):
+def rollout(tables, starts, state, actions, horizon=400, flags=0, n_threads=0, rs=None):
     """T transitions in place; actions [T,N,2].  Returns sparse[T,N], shaped[T,N,2], done[T,N], events[T,N,2]."""
     assert state.dtype == np.int32 and state.flags.c_contiguous
     n, S = state.shape
@@ -77,7 +102,7 @@ def rollout(tables, starts, state, actions, horizon=400, flags=0, n_threads=0):
     starts = _i32(starts)
     rc = lib().ovo_rollout(_p(tables), ctypes.c_int(len(tables)), _p(starts), _p(state), _p(actions), _p(sparse),
                            _p(shaped), _p(done), _p(events), ctypes.c_int64(n), ctypes.c_int(T), ctypes.c_int(S),
-                           ctypes.c_int(horizon), ctypes.c_int(flags), ctypes.c_int(n_threads))
+                           ctypes.c_int(horizon), ctypes.c_int(flags), ctypes.c_int(n_threads), _rs(rs))
     assert rc == 0
     return sparse, shaped, done, events
 

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libovc_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 F_AUTO_RESET = 1
 F_PDL = 2
 F_ACT_U8 = 4
@@ -18,6 +18,13 @@ F_OUT_NARROW = 8
 F_IO_SHIFT = 8
 IO_DEFAULT, IO_TMA_TENSOR, IO_TMA_BULK, IO_DIRECT = 0, 1, 2, 3
 DT_F32, DT_U8, DT_I32 = 0, 1, 2
+
+
+
+class RandomStart(ctypes.Structure):
+    """ovc_random_start_t (include/ovc_b200.h): random start states, passed by host pointer."""
+    _fields_ = [("seed", ctypes.c_uint64), ("obj_threshold", ctypes.c_uint32), ("random_start_pos", ctypes.c_int32)]
+
 
 _lib = None
 
@@ -42,9 +49,9 @@ def lib():
     L.ovc_layout_table_size.restype = ctypes.c_size_t
     L.ovc_feat_lut_entry_size.restype = ctypes.c_size_t
     L.ovc_last_error.restype = ctypes.c_char_p
-    L.ovc_step.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]
-    L.ovc_rollout.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]
-    L.ovc_reset.argtypes = [vp, i32, vp, vp, vp, i64, i32, vp]
+    L.ovc_step.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp, vp]
+    L.ovc_rollout.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp, vp]
+    L.ovc_reset.argtypes = [vp, i32, vp, vp, vp, vp, i64, i32, vp, vp]
     L.ovc_encode_lossless.argtypes = [vp, i32, vp, vp, vp, i32, i64, i32, i32, i32, i32, vp]
     L.ovc_featurize.argtypes = [vp, i32, vp, vp, vp, vp, i64, i32, i32, vp]
     L.ovc_potential.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, i64, i32, vp]

@@ -16,6 +16,8 @@ event words (the reference raises AssertionError, overcooked_env.py:255); with `
 an environment that reaches the horizon is put back to its start state in the same launch (its
 ``done`` output is still 1 for that transition), which is what rollout collection wants.
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -40,7 +42,8 @@ def _as_layouts(layouts, mdp_params):
 
 class BatchedOvercookedEnv(object):
     def __init__(self, layouts, n_envs, horizon=400, device="cuda", auto_reset=False, state_words=None,
-                 io=_native.IO_DEFAULT, env_layout=None, mdp_params=None, pdl=False):
+                 io=_native.IO_DEFAULT, env_layout=None, mdp_params=None, pdl=False,
+                 random_start_pos=False, rnd_obj_prob_thresh=0.0, seed=0):
         """
         layouts      layout name / CompiledLayout / OvercookedGridworld, or a list of them (mixed batch)
         n_envs       number of environments on THIS device
@@ -48,6 +51,10 @@ class BatchedOvercookedEnv(object):
         env_layout   optional int array [n_envs] of layout indices; default: contiguous, near-equal
                      segments, one per layout (a warp then sees one layout)
         io           record I/O strategy of the step kernel (_native.IO_*); 0 = library default
+        random_start_pos, rnd_obj_prob_thresh, seed
+                     start every episode from the reference's randomised start states
+                     (get_random_start_state_fn, overcooked_mdp.py:1307-1369) instead of the standard one;
+                     drawn on the device with a counter-based generator (see ovc_random_start_t)
         """
         self._lib = _native.lib()
         if not torch.cuda.is_available():
@@ -85,6 +92,10 @@ class BatchedOvercookedEnv(object):
             self.shaped = torch.zeros((self.n_envs, 2), dtype=torch.int32, device=self.device)
             self.done = torch.zeros(self.n_envs, dtype=torch.int32, device=self.device)
             self.events = torch.zeros((self.n_envs, 2), dtype=torch.int32, device=self.device)
+        self._rs = None
+        if random_start_pos or rnd_obj_prob_thresh > 0:
+            thr = min(int(float(rnd_obj_prob_thresh) * 4294967296.0), 0xFFFFFFFF)
+            self._rs = _native.RandomStart(int(seed) & 0xFFFFFFFFFFFFFFFF, thr, int(bool(random_start_pos)))
         self._lut = None
         self._segments = None
         self._p_tables, self._p_starts, self._p_state = self.tables.data_ptr(), self.start_records.data_ptr(), self.state.data_ptr()
@@ -95,6 +106,9 @@ class BatchedOvercookedEnv(object):
         return ((_native.F_AUTO_RESET if self.auto_reset else 0) | (_native.F_PDL if self.pdl else 0)
                 | (self.io << _native.F_IO_SHIFT))
 
+    def _rs_ptr(self):
+        return ctypes.byref(self._rs) if self._rs is not None else None
+
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
@@ -104,8 +118,9 @@ class BatchedOvercookedEnv(object):
         if mask is not None:
             assert mask.dtype == torch.int32 and mask.is_cuda and mask.is_contiguous() and mask.numel() == self.n_envs
         _native.check(self._lib.ovc_reset(
-            self.start_records.data_ptr(), self.n_layouts, self.state.data_ptr(), self.env_layout.data_ptr(),
-            0 if mask is None else mask.data_ptr(), self.n_envs, self.state_words, self._stream()))
+            self.tables.data_ptr(), self.n_layouts, self.start_records.data_ptr(), self.state.data_ptr(),
+            self.env_layout.data_ptr(), 0 if mask is None else mask.data_ptr(), self.n_envs, self.state_words,
+            self._rs_ptr(), self._stream()))
 
     def step(self, actions, out=None):
         """One joint transition of every environment.
@@ -123,7 +138,7 @@ class BatchedOvercookedEnv(object):
         _native.check(self._lib.ovc_step(
             self._p_tables, self.n_layouts, self._p_starts, self._p_state,
             actions.data_ptr(), sparse.data_ptr(), shaped.data_ptr(), done.data_ptr(),
-            events.data_ptr(), self.n_envs, self.state_words, self.horizon, self._flags(), self._stream()))
+            events.data_ptr(), self.n_envs, self.state_words, self.horizon, self._flags(), self._rs_ptr(), self._stream()))
         return sparse, shaped, done, events
 
     def narrow_ok(self):
@@ -168,7 +183,7 @@ class BatchedOvercookedEnv(object):
         _native.check(self._lib.ovc_rollout(
             self.tables.data_ptr(), self.n_layouts, self.start_records.data_ptr(), self.state.data_ptr(),
             actions.data_ptr(), sparse.data_ptr(), shaped.data_ptr(), done.data_ptr(), events.data_ptr(),
-            self.n_envs, T, self.state_words, self.horizon, flags, self._stream()))
+            self.n_envs, T, self.state_words, self.horizon, flags, self._rs_ptr(), self._stream()))
         return out
 
     # ---------------------------------------------------------------------------------------------

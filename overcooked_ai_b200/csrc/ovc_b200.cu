@@ -143,6 +143,8 @@ struct StepArgs {
     int n_layouts;
     int n_steps;  // rollout only
     int horizon, flags;
+    int has_rs;
+    ovc_random_start_t rs;
 };
 
 __device__ __forceinline__ void write_outputs(const StepArgs &a, long long idx, const StepOut &o) {
@@ -167,7 +169,7 @@ __device__ __forceinline__ int2 load_action(const StepArgs &a, long long idx) {
 }
 
 // Shared-memory plan of one CTA (dynamic, 1024-byte aligned so the TMA swizzle pattern lines up with
-// the tile offsets): [ tile: TILE*S*4 bytes ][ layout tables: n_tbl*896 bytes ][ mbarrier: 8 bytes ].
+// the tile offsets): [ tile: TILE*S*4 bytes ][ layout tables: n_tbl*1024 bytes ][ mbarrier: 8 bytes ].
 constexpr int MAX_SMEM_LAYOUTS = 8;
 
 // One CTA = one tile of TILE records.  n_steps == 1: the step kernel K1; n_steps > 1: the fused rollout K5.
@@ -190,7 +192,7 @@ step_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
             const long long idx = (long long)t * a.n_envs + env;
             const int2 act = load_action(a, idx);
             StepOut o;
-            step_core(r, tb, a.start_records, S, act.x, act.y, a.horizon, a.flags, o);
+            step_core(r, tb, a.start_records, S, act.x, act.y, a.horizon, a.flags, a.has_rs ? &a.rs : nullptr, env, o);
             write_outputs(a, idx, o);
         }
         return;
@@ -234,7 +236,7 @@ step_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
                 int2 nxt = act;
                 if (t + 1 < T) nxt = load_action(a, idx + a.n_envs);  // prefetch
                 StepOut o;
-                step_core(r, tb, a.start_records, S, act.x, act.y, a.horizon, a.flags, o);
+                step_core(r, tb, a.start_records, S, act.x, act.y, a.horizon, a.flags, a.has_rs ? &a.rs : nullptr, env, o);
                 write_outputs(a, idx, o);
                 act = nxt;
             }
@@ -265,6 +267,23 @@ __global__ void reset_kernel(const int32_t *__restrict__ start_records, int n_la
     int lid = env_layout ? env_layout[env] : (state[env * S + 3] & 0xFF);
     if (lid < 0 || lid >= n_layouts) lid = 0;
     reinterpret_cast<int4 *>(state)[i] = __ldg(reinterpret_cast<const int4 *>(start_records) + (long long)lid * cpr + c);
+}
+
+// Random start states: one thread per environment draws its record (get_random_start_state_fn :1307-1369).
+__global__ void reset_random_kernel(const ovc_layout_t *__restrict__ layouts, int n_layouts,
+                                    const int32_t *__restrict__ start_records, int32_t *__restrict__ state,
+                                    const int32_t *__restrict__ env_layout, const int32_t *__restrict__ mask,
+                                    long long n_envs, int S, const ovc_random_start_t rs) {
+    const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= n_envs) return;
+    if (mask && mask[env] == 0) return;
+    int32_t *rec = state + env * S;
+    const unsigned old = (unsigned)rec[3];
+    int lid = env_layout ? env_layout[env] : (int)(old & 0xFF);
+    if (lid < 0 || lid >= n_layouts) lid = 0;
+    const ovc_layout_t *L = layouts + lid;
+    random_start_record([&](int w, int32_t v) { rec[w] = v; }, S, start_records + (size_t)lid * S, L->cook_time, L->free_pos,
+                        L->n_free, L->n_pots, lid, rs, (uint64_t)env, ((old >> 16) + 1u) & 0xFFFFu);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -351,7 +370,8 @@ static int check_common(const void *layouts, int n_layouts, const void *state, l
 
 static int step_impl(const void *layouts, int n_layouts, const int32_t *start_records, int32_t *state,
                      const int32_t *actions, int32_t *sparse, int32_t *shaped, int32_t *done, int32_t *events,
-                     long long n_envs, int n_steps, int S, int horizon, int flags, void *stream) {
+                     long long n_envs, int n_steps, int S, int horizon, int flags, const ovc_random_start_t *rs,
+                     void *stream) {
     int rc = check_common(layouts, n_layouts, state, n_envs, S);
     if (rc) return rc;
     if (!actions || !sparse || !shaped || !done || !events || !start_records)
@@ -368,7 +388,7 @@ static int step_impl(const void *layouts, int n_layouts, const int32_t *start_re
     if (io < 1 || io > 3) return fail(OVC_E_BADARG, "unknown record I/O strategy%s %lld", "", io);
     if (io == 1 && (n_envs * (S / (S == 16 ? 16 : 32))) > 0x7FFFFFFFLL) io = 2;  // tensor coordinates are int32
     StepArgs a{(const ovc_layout_t *)layouts, start_records, state, actions, sparse, shaped, done, events,
-               n_envs, n_layouts, n_steps, horizon, flags};
+               n_envs, n_layouts, n_steps, horizon, flags, rs != nullptr, rs ? *rs : ovc_random_start_t{0, 0, 0}};
     cudaStream_t st = (cudaStream_t)stream;
     switch (S) {
     case 16: return launch_step<16>(a, io, st);
@@ -395,27 +415,35 @@ const char *ovc_last_error(void) { return ovc::g_err; }
 
 int ovc_step(const void *layouts, int n_layouts, const int32_t *start_records, int32_t *state, const int32_t *actions,
              int32_t *sparse, int32_t *shaped, int32_t *done, int32_t *events, int64_t n_envs, int state_words,
-             int horizon, int flags, void *stream) {
+             int horizon, int flags, const ovc_random_start_t *random_start, void *stream) {
     return ovc::step_impl(layouts, n_layouts, start_records, state, actions, sparse, shaped, done, events, n_envs, 1,
-                          state_words, horizon, flags, stream);
+                          state_words, horizon, flags, random_start, stream);
 }
 
 int ovc_rollout(const void *layouts, int n_layouts, const int32_t *start_records, int32_t *state,
                 const int32_t *actions, int32_t *sparse, int32_t *shaped, int32_t *done, int32_t *events,
-                int64_t n_envs, int n_steps, int state_words, int horizon, int flags, void *stream) {
+                int64_t n_envs, int n_steps, int state_words, int horizon, int flags,
+                const ovc_random_start_t *random_start, void *stream) {
     return ovc::step_impl(layouts, n_layouts, start_records, state, actions, sparse, shaped, done, events, n_envs,
-                          n_steps, state_words, horizon, flags, stream);
+                          n_steps, state_words, horizon, flags, random_start, stream);
 }
 
-int ovc_reset(const int32_t *start_records, int n_layouts, int32_t *state, const int32_t *env_layout,
-              const int32_t *mask, int64_t n_envs, int state_words, void *stream) {
-    int rc = ovc::check_common(start_records, n_layouts, state, n_envs, state_words);
+int ovc_reset(const void *layouts, int n_layouts, const int32_t *start_records, int32_t *state, const int32_t *env_layout,
+              const int32_t *mask, int64_t n_envs, int state_words, const ovc_random_start_t *random_start, void *stream) {
+    int rc = ovc::check_common(layouts, n_layouts, state, n_envs, state_words);
     if (rc) return rc;
+    if (!start_records) return ovc::fail(OVC_E_BADARG, "null pointer argument%s", "");
     if (n_envs == 0) return OVC_OK;
-    const long long chunks = (long long)n_envs * (state_words / 4);
     const int threads = 256;
-    ovc::reset_kernel<<<(unsigned)((chunks + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
-        start_records, n_layouts, state, env_layout, mask, n_envs, state_words);
+    if (random_start) {
+        ovc::reset_random_kernel<<<(unsigned)((n_envs + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+            (const ovc_layout_t *)layouts, n_layouts, start_records, state, env_layout, mask, n_envs, state_words,
+            *random_start);
+    } else {
+        const long long chunks = (long long)n_envs * (state_words / 4);
+        ovc::reset_kernel<<<(unsigned)((chunks + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+            start_records, n_layouts, state, env_layout, mask, n_envs, state_words);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return ovc::cuda_fail(e, "reset kernel launch");
     return OVC_OK;

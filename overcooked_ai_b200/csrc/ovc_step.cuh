@@ -13,6 +13,7 @@
 #include <stdint.h>
 
 #include "../../include/ovc_b200.h"
+#include "ovc_rng.cuh"
 
 #include <stddef.h>
 
@@ -27,6 +28,7 @@ struct TblG {
     __device__ __forceinline__ int i32(int off) const { return __ldg(reinterpret_cast<const int *>(base + off)); }
     __device__ __forceinline__ unsigned u16(int off) const { return __ldg(reinterpret_cast<const unsigned short *>(base + off)); }
     __device__ __forceinline__ unsigned u8(int off) const { return __ldg(reinterpret_cast<const unsigned char *>(base + off)); }
+    __device__ __forceinline__ const char *ptr(int off) const { return base + off; }
 };
 struct TblS {
     const char *base;  // derived from the __shared__ array, so these compile to LDS
@@ -34,6 +36,7 @@ struct TblS {
     __device__ __forceinline__ int i32(int off) const { return *reinterpret_cast<const int *>(base + off); }
     __device__ __forceinline__ unsigned u16(int off) const { return *reinterpret_cast<const unsigned short *>(base + off); }
     __device__ __forceinline__ unsigned u8(int off) const { return *reinterpret_cast<const unsigned char *>(base + off); }
+    __device__ __forceinline__ const char *ptr(int off) const { return base + off; }
 };
 #define OVC_OFF(field) ((int)offsetof(ovc_layout_t, field))
 
@@ -172,7 +175,8 @@ __device__ __forceinline__ void interact_one(R &r, const TB &L, unsigned &p_me,
 template <class R, class TB>
 __device__ __forceinline__ void step_core(R &r, const TB &layouts,
                                           const int32_t *__restrict__ start_records, int S, int a0, int a1,
-                                          int horizon, int flags, StepOut &o) {
+                                          int horizon, int flags, const ovc_random_start_t *rs, long long env_index,
+                                          StepOut &o) {
     int4 h = r.ld4(0);
     const int t = h.x;
     if (horizon > 0 && t >= horizon) {  // stepping a finished env: untouched + flagged (overcooked_env.py:255)
@@ -278,9 +282,17 @@ __device__ __forceinline__ void step_core(R &r, const TB &layouts,
     o.ev0 = ev[0], o.ev1 = ev[1];
     o.done = horizon > 0 && tn >= horizon;  // is_done overcooked_env.py:321-325
     if (o.done && (flags & OVC_F_AUTO_RESET)) {
-        const int4 *__restrict__ src = reinterpret_cast<const int4 *>(start_records + (size_t)(misc & 0xFF) * S);
+        const int32_t *__restrict__ start = start_records + (size_t)(misc & 0xFF) * S;
+        if (rs) {  // next episode starts from a drawn state (get_random_start_state_fn :1307-1369)
+            random_start_record([&](int w, int32_t v) { r.stw(w, v); }, S, start,
+                                reinterpret_cast<const int32_t *>(L.ptr(OVC_OFF(cook_time))),
+                                reinterpret_cast<const uint8_t *>(L.ptr(OVC_OFF(free_pos))), L.i32(OVC_OFF(n_free)), n_pots,
+                                (int)(misc & 0xFF), *rs, (uint64_t)env_index, ((misc >> 16) + 1u) & 0xFFFFu);
+        } else {
+            const int4 *__restrict__ src = reinterpret_cast<const int4 *>(start);
 #pragma unroll 4
-        for (int c = 0; c < S / 4; c++) r.st4(c, __ldg(src + c));
+            for (int c = 0; c < S / 4; c++) r.st4(c, __ldg(src + c));
+        }
     } else {
         r.st4(0, make_int4(tn, (int)p[0], (int)p[1], (int)misc));
     }

@@ -65,12 +65,12 @@ LAYOUT_DTYPE = np.dtype(
     [
         ("width", "<i4"), ("height", "<i4"), ("n_pots", "<i4"), ("n_slots", "<i4"), ("flags", "<i4"),
         ("rew_placement_in_pot", "<i4"), ("rew_dish_pickup", "<i4"), ("rew_soup_pickup", "<i4"),
-        ("state_words", "<i4"), ("reserved", "<i4", (7,)),
+        ("state_words", "<i4"), ("n_free", "<i4"), ("reserved", "<i4", (6,)),
         ("cook_time", "<i4", (16,)), ("deliver_value", "<i4", (16,)), ("best_value", "<i4", (16,)),
-        ("cell", "<u2", (256,)), ("slot_pos", "u1", (128,)),
+        ("cell", "<u2", (256,)), ("slot_pos", "u1", (128,)), ("free_pos", "u1", (128,)),
     ]
 )
-assert LAYOUT_DTYPE.itemsize == 896
+assert LAYOUT_DTYPE.itemsize == 1024
 
 FEAT_LUT_DTYPE = np.dtype(
     [("d_onion", "i1", (2,)), ("d_tomato", "i1", (2,)), ("d_dish", "i1", (2,)), ("d_serve", "i1", (2,)),
@@ -313,6 +313,14 @@ class CompiledLayout(object):
         for i, p in enumerate(self.slot_positions):
             sp[i] = pos_byte(p)
         rec["slot_pos"] = sp
+        free = self.terrain_pos_dict[" "]
+        if len(free) > 128:
+            raise ValueError("layout %r has %d floor cells (max 128)" % (self.layout_name, len(free)))
+        rec["n_free"] = len(free)
+        fp = np.zeros(128, np.uint8)
+        for i, p in enumerate(free):
+            fp[i] = pos_byte(p)
+        rec["free_pos"] = fp
         return rec
 
     # -- planner distances ------------------------------------------------------------------------
@@ -584,7 +592,7 @@ def unpack_state(layout, rec):
 
 
 def build_tables(layouts, state_words=None):
-    """Stack compiled layouts: (table bytes as uint8 [n, 896], start records int32 [n, S], S)."""
+    """Stack compiled layouts: (table bytes as uint8 [n, 1024], start records int32 [n, S], S)."""
     S = max(l.state_words for l in layouts) if state_words is None else state_words
     assert S in SUPPORTED_STATE_WORDS and all(l.state_words <= S for l in layouts)
     assert len(layouts) <= 256

@@ -288,10 +288,10 @@ def test_cuda_graph_capture_of_step(pdl):
 def test_bad_arguments_are_reported():
     lib = _native.lib()
     env = BatchedOvercookedEnv("cramped_room", 8)
-    rc = lib.ovc_step(env.tables.data_ptr(), 1, env.start_records.data_ptr(), env.state.data_ptr(), 0, 0, 0, 0, 0, 8, 16, 400, 0, 0)
+    rc = lib.ovc_step(env.tables.data_ptr(), 1, env.start_records.data_ptr(), env.state.data_ptr(), 0, 0, 0, 0, 0, 8, 16, 400, 0, None, 0)
     assert rc == -1 and b"null" in lib.ovc_last_error()
     rc = lib.ovc_step(env.tables.data_ptr(), 1, env.start_records.data_ptr(), env.state.data_ptr(), env.state.data_ptr(),
-                      env.sparse.data_ptr(), env.shaped.data_ptr(), env.done.data_ptr(), env.events.data_ptr(), 8, 24, 400, 0, 0)
+                      env.sparse.data_ptr(), env.shaped.data_ptr(), env.done.data_ptr(), env.events.data_ptr(), 8, 24, 400, 0, None, 0)
     assert rc == -1 and b"state_words" in lib.ovc_last_error()
 
 
@@ -366,3 +366,36 @@ def test_narrow_transfer_formats_and_host_pipeline():
         for g, w in zip(got, want):
             assert np.array_equal(g.numpy().astype(np.int64), _np(w).astype(np.int64))
         assert torch.equal(env_b.state, env_a.state)
+
+
+@pytest.mark.parametrize("random_pos,thresh", [(True, 0.0), (False, 0.7), (True, 0.5)])
+def test_random_start_states_vs_oracle_mirror(random_pos, thresh):
+    """get_random_start_state_fn on the device (reset + auto-reset inside step / rollout): bit-exact against the
+    CPU mirror of the documented generator; episodes differ from each other and between environments."""
+    n, horizon, T = 4099, 15, 50
+    env = BatchedOvercookedEnv(["cramped_room", "counter_circuit"], n, horizon=horizon, auto_reset=True,
+                               random_start_pos=random_pos, rnd_obj_prob_thresh=thresh, seed=77)
+    rs = cpu.random_start(77, thresh, random_pos)
+    ref = np.zeros((n, env.state_words), np.int32)
+    cpu.reset_random(env._tab_host, env._starts_host, ref, rs, env_layout=env.env_layout_host)
+    assert np.array_equal(_np(env.state), ref)
+    first = ref.copy()
+    rng = np.random.RandomState(8)
+    acts = _random_actions(rng, T, n, 0.35)
+    want = cpu.rollout(env._tab_host, env._starts_host, ref, acts, horizon=horizon, flags=1, n_threads=4, rs=rs)
+    d = torch.from_numpy(acts).cuda()
+    for t in range(20):
+        got = env.step(d[t])
+        for g, w in zip(got, want):
+            assert np.array_equal(_np(g), w[t]), t
+    got = env.rollout(d[20:].contiguous())
+    for g, w in zip(got, want):
+        assert np.array_equal(_np(g), w[20:])
+    assert np.array_equal(_np(env.state), ref)
+    assert ((ref[:, 3] >> 16) & 0xFFFF == 1 + T // horizon).all()
+    # a masked reset redraws exactly the masked envs, with a new episode number
+    mask = (rng.rand(n) < 0.3).astype(np.int32)
+    env.reset(torch.from_numpy(mask).cuda())
+    cpu.reset_random(env._tab_host, env._starts_host, ref, rs, mask=mask)
+    assert np.array_equal(_np(env.state), ref)
+    assert len(np.unique(first[:, 1:3], axis=0)) > 10

@@ -26,8 +26,8 @@ def test_native_library_loads_and_exports_every_declared_symbol():
     lib = _native.lib()
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.ovc_abi_version() == 1
-    assert lib.ovc_layout_table_size() == L.LAYOUT_DTYPE.itemsize == 896
+    assert lib.ovc_abi_version() == 2
+    assert lib.ovc_layout_table_size() == L.LAYOUT_DTYPE.itemsize == 1024
     assert lib.ovc_feat_lut_entry_size() == L.FEAT_LUT_DTYPE.itemsize == 12
 
 
@@ -91,7 +91,7 @@ def test_state_words_and_slots():
 
 def test_start_records():
     tab, starts, S = L.build_tables([L.compile_layout(n) for n in ("cramped_room", "counter_circuit")])
-    assert S == 32 and tab.shape == (2, 896) and starts.shape == (2, 32)
+    assert S == 32 and tab.shape == (2, 1024) and starts.shape == (2, 32)
     # cramped_room: P0 (1,2) P1 (3,1) facing north, nothing held, t = 0
     assert starts[0, :4].tolist() == [0, (2 << 4) | 1, (1 << 4) | 3, 0] and not starts[0, 4:].any()
     assert starts[1, 3] == 1

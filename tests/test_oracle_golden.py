@@ -166,3 +166,48 @@ def test_potential_function_bit_exact(gamma_idx, gamma):
         assert np.array_equal(phi, g[name + "__phi"][:, gamma_idx]), name
         n_states += len(phi)
     assert n_states > 10000
+
+
+def test_random_start_states_are_valid_and_follow_the_reference_distribution():
+    """The engine's counter-based get_random_start_state_fn (overcooked_mdp.py:1307-1369): every drawn state
+    passes the reference's validity rules (pack_state re-checks them), and the marginals match what the
+    reference's procedure implies: P(player holds something) = t with dish / onion / soup split 0.2 / 0.6 / 0.2,
+    P(pot filled) = t, P(filled pot already cooking) = t, ingredient counts n uniform on 1..3 and m on 0..3-n,
+    joint positions uniform over ordered pairs of distinct floor cells."""
+    t = 0.6
+    cl = L.compile_layout("counter_circuit")
+    tab, starts, S = L.build_tables([cl])
+    n = 200000
+    state = np.zeros((n, S), np.int32)
+    cpu.reset_random(tab, starts, state, cpu.random_start(5, t, True))
+    held = (state[:, 1:3].astype(np.uint32) >> 10) & 7
+    assert abs((held != 0).mean() - t) < 0.01
+    for typ, p in ((L.O_DISH, 0.2), (L.O_ONION, 0.6), (L.O_SOUP, 0.2)):
+        assert abs((held == typ).sum() / (held != 0).sum() - p) < 0.01
+    pots = state[:, 4:4 + cl.n_pots].astype(np.uint32)
+    filled = (pots & 7) == L.O_SOUP
+    assert abs(filled.mean() - t) < 0.01
+    assert abs((((pots >> 8) & 0x3FFF) == 1)[filled].mean() - t) < 0.01
+    n_ing = ((pots >> 3) & 3)[filled]
+    n_tom = np.array([bin(int(x)).count("1") for x in ((pots >> 5) & 7)[filled][:20000]])
+    n_on = n_ing[:20000] - n_tom
+    for k in (1, 2, 3):
+        assert abs((n_on == k).mean() - 1 / 3) < 0.02
+    pos = state[:, 1:3] & 0xFF
+    assert (pos[:, 0] != pos[:, 1]).all()
+    F = len(cl.terrain_pos_dict[" "])
+    pairs, counts = np.unique(pos, axis=0, return_counts=True)
+    assert len(pairs) == F * (F - 1) and counts.min() > 0.8 * n / (F * (F - 1))
+    assert not state[:, 4 + cl.n_pots:].any() and (state[:, 0] == 0).all()
+    # validity: every 400th state round-trips through pack_state (which asserts the reference's rules)
+    for rec in state[::400]:
+        st = L.unpack_state(cl, rec)
+        back = L.pack_state(cl, st, 0, S)
+        assert np.array_equal(back[:3], rec[:3]) and np.array_equal(back[4:], rec[4:])
+        for p in st.players:
+            if p.held_object is not None and p.held_object.name == "soup":
+                assert p.held_object.is_ready
+    # no randomisation requested -> the standard start, like the reference (:1316-1326)
+    state2 = np.zeros((8, S), np.int32)
+    cpu.reset_random(tab, starts, state2, cpu.random_start(5, 0.0, False))
+    assert np.array_equal(state2[:, :3], np.repeat(starts[:, :3], 8, 0))
