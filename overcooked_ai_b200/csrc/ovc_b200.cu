@@ -173,7 +173,7 @@ __device__ __forceinline__ int2 load_action(const StepArgs &a, long long idx) {
 constexpr int MAX_SMEM_LAYOUTS = 8;
 
 // One CTA = one tile of TILE records.  n_steps == 1: the step kernel K1; n_steps > 1: the fused rollout K5.
-template <int S, int IO>
+template <int S, int IO, bool RS>
 __global__ void __launch_bounds__(Cfg<S>::TILE)
 step_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
     using C = Cfg<S>;
@@ -192,7 +192,7 @@ step_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
             const long long idx = (long long)t * a.n_envs + env;
             const int2 act = load_action(a, idx);
             StepOut o;
-            step_core(r, tb, a.start_records, S, act.x, act.y, a.horizon, a.flags, a.has_rs ? &a.rs : nullptr, env, o);
+            step_core<RS>(r, tb, a.start_records, S, act.x, act.y, a.horizon, a.flags, RS ? &a.rs : nullptr, env, o);
             write_outputs(a, idx, o);
         }
         return;
@@ -203,7 +203,7 @@ step_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
     const int n_tbl = a.n_layouts <= MAX_SMEM_LAYOUTS ? a.n_layouts : 0;  // 0: tables stay in global memory
     const uint32_t tbl_bytes = (uint32_t)n_tbl * (uint32_t)sizeof(ovc_layout_t);
     char *tbl = smem + C::TILE_BYTES;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + C::TILE_BYTES + MAX_SMEM_LAYOUTS * sizeof(ovc_layout_t));
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + C::TILE_BYTES + tbl_bytes);  // host sizes the buffer the same way
     const long long rem = a.n_envs - env0;
     const uint32_t live_bytes = (uint32_t)((rem < C::TILE ? rem : C::TILE) * S * 4);
 
@@ -236,7 +236,7 @@ step_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
                 int2 nxt = act;
                 if (t + 1 < T) nxt = load_action(a, idx + a.n_envs);  // prefetch
                 StepOut o;
-                step_core(r, tb, a.start_records, S, act.x, act.y, a.horizon, a.flags, a.has_rs ? &a.rs : nullptr, env, o);
+                step_core<RS>(r, tb, a.start_records, S, act.x, act.y, a.horizon, a.flags, RS ? &a.rs : nullptr, env, o);
                 write_outputs(a, idx, o);
                 act = nxt;
             }
@@ -334,7 +334,8 @@ static cudaError_t launch_one(const CUtensorMap &tmap, const StepArgs &a, unsign
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (a.flags & OVC_F_PDL) ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, step_kernel<S, IO>, tmap, a);
+    if (a.has_rs) return cudaLaunchKernelEx(&cfg, step_kernel<S, IO, true>, tmap, a);
+    return cudaLaunchKernelEx(&cfg, step_kernel<S, IO, false>, tmap, a);
 }
 
 template <int S>
@@ -343,7 +344,8 @@ static int launch_step(const StepArgs &a, int io, cudaStream_t st) {
     const unsigned grid = (unsigned)((a.n_envs + C::TILE - 1) / C::TILE);
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
-    const size_t smem = io == 3 ? 0 : C::TILE_BYTES + MAX_SMEM_LAYOUTS * sizeof(ovc_layout_t) + 16;
+    const int n_tbl = a.n_layouts <= MAX_SMEM_LAYOUTS ? a.n_layouts : 0;
+    const size_t smem = io == 3 ? 0 : C::TILE_BYTES + (size_t)n_tbl * sizeof(ovc_layout_t) + 16;
     cudaError_t e;
     if (io == 1) {
         int rc = make_tmap<S>(&tmap, a.state, a.n_envs);

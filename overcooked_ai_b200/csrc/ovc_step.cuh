@@ -172,7 +172,9 @@ __device__ __forceinline__ void interact_one(R &r, const TB &L, unsigned &p_me,
     ev_me = e;
 }
 
-template <class R, class TB>
+// RS: compiled with the random-start path (get_random_start_state_fn :1307-1369).  It is a separate
+// instantiation because the generator's registers would otherwise weigh on every transition.
+template <bool RS, class R, class TB>
 __device__ __forceinline__ void step_core(R &r, const TB &layouts,
                                           const int32_t *__restrict__ start_records, int S, int a0, int a1,
                                           int horizon, int flags, const ovc_random_start_t *rs, long long env_index,
@@ -283,7 +285,7 @@ __device__ __forceinline__ void step_core(R &r, const TB &layouts,
     o.done = horizon > 0 && tn >= horizon;  // is_done overcooked_env.py:321-325
     if (o.done && (flags & OVC_F_AUTO_RESET)) {
         const int32_t *__restrict__ start = start_records + (size_t)(misc & 0xFF) * S;
-        if (rs) {  // next episode starts from a drawn state (get_random_start_state_fn :1307-1369)
+        if (RS && rs) {
             random_start_record([&](int w, int32_t v) { r.stw(w, v); }, S, start,
                                 reinterpret_cast<const int32_t *>(L.ptr(OVC_OFF(cook_time))),
                                 reinterpret_cast<const uint8_t *>(L.ptr(OVC_OFF(free_pos))), L.i32(OVC_OFF(n_free)), n_pots,
