@@ -123,9 +123,12 @@ struct GlobalRec {
     __device__ __forceinline__ void stw(int w, int v) { rec[w] = v; }
 };
 
+#ifndef OVC_TILE16
+#define OVC_TILE16 128
+#endif
 template <int S>
 struct Cfg {
-    static constexpr int TILE = S <= 32 ? 128 : 64;         // environments (= threads) per CTA
+    static constexpr int TILE = S <= 16 ? OVC_TILE16 : S <= 32 ? 128 : 64;  // environments (= threads) per CTA
     static constexpr int ROW_WORDS = S == 16 ? 16 : 32;     // tensor-map row: 64 B or 128 B
     static constexpr int ROWS_PER_ENV = S / ROW_WORDS;      // 1, 1, 2, 4
     static constexpr int BOX_ROWS = TILE * ROWS_PER_ENV;    // <= 256
