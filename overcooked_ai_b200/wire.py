@@ -1,0 +1,93 @@
+"""Wire / on-disk formats <-> packed tensors, in bulk.
+
+The reference speaks three formats around the hot path:
+  * ``OvercookedState.to_dict()`` JSON (overcooked_mdp.py:998-1015; soups :615-663) — the demo server, the
+    human-trial CSVs (``state`` column) and ``AgentEvaluator.save_traj_as_json`` (benchmarking.py:431-502);
+  * joint actions as direction lists / ``"interact"`` (``joint_action`` column, actions.py:47-52);
+  * trajectory dicts (overcooked_trajectory.py:14-44): ``ep_states / ep_actions / ep_rewards / ep_dones /
+    ep_infos / ep_returns / ep_lengths / mdp_params / env_params / metadatas``.
+These helpers move whole batches between those and the engine's ``state[N, S]`` / ``actions[T, N, 2]``
+tensors, so recorded games can be replayed on the device and device rollouts can be handed to tools that
+expect the reference's files.  Host side only; nothing here is on the per-step path.
+"""
+import json
+
+import numpy as np
+
+from overcooked_ai_b200 import layout as L
+from overcooked_ai_b200.actions import Action
+from overcooked_ai_b200.state import OvercookedState
+
+
+def records_from_dicts(layout, state_dicts, layout_id=0, state_words=None):
+    """List of ``to_dict()`` dicts (or JSON strings) -> int32 [N, S] records."""
+    S = layout.state_words if state_words is None else state_words
+    out = np.zeros((len(state_dicts), S), np.int32)
+    for i, d in enumerate(state_dicts):
+        if isinstance(d, str):
+            d = json.loads(d)
+        out[i] = L.pack_state(layout, OvercookedState.from_dict(d), layout_id, S)
+    return out
+
+
+def dicts_from_records(layout, records):
+    """int32 [N, S] records -> list of ``to_dict()`` dicts (JSON-ready: tuples become lists)."""
+    return [json.loads(json.dumps(L.unpack_state(layout, r).to_dict())) for r in np.asarray(records)]
+
+
+def action_indices(joint_actions):
+    """Reference joint actions (tuples / lists of direction pairs, "interact", any capitalisation; or their JSON
+    strings) -> int32 [N, 2] action indices."""
+    out = np.zeros((len(joint_actions), 2), np.int32)
+    for i, ja in enumerate(joint_actions):
+        if isinstance(ja, str):
+            ja = json.loads(ja)
+        for p in range(2):
+            a = ja[p]
+            a = a.lower() if isinstance(a, str) else tuple(a)
+            out[i, p] = Action.to_index(a)
+    return out
+
+
+def joint_actions_from_indices(idx):
+    """int [N, 2] -> list of reference joint-action tuples."""
+    return [tuple(Action.INDEX_TO_ACTION[int(a)] for a in row) for row in np.asarray(idx)]
+
+
+def trajectories_from_rollout(layout, states, actions, sparse, done, mdp_params=None, env_params=None):
+    """Device rollout outputs -> the reference's trajectory dict (overcooked_trajectory.py:14-44).
+
+    states   int32 [T+1, N, S] (state before each transition, plus the final one) or [T, N, S]
+    actions  int   [T, N, 2];  sparse int [T, N];  done int [T, N]
+    One trajectory per environment, cut at its first ``done`` (or T).  ``ep_states`` holds OvercookedState
+    objects like the reference's (``to_dict`` them for JSON); ``ep_infos`` carries empty dicts.
+    """
+    states, actions, sparse, done = (np.asarray(x) for x in (states, actions, sparse, done))
+    T, N = actions.shape[:2]
+    traj = {k: [] for k in ("ep_states", "ep_actions", "ep_rewards", "ep_dones", "ep_infos", "ep_returns", "ep_lengths",
+                            "mdp_params", "env_params")}
+    traj["metadatas"] = {}
+    for e in range(N):
+        ends = np.nonzero(done[:, e])[0]
+        length = int(ends[0]) + 1 if len(ends) else T
+        traj["ep_states"].append([L.unpack_state(layout, states[t, e]) for t in range(length)])
+        traj["ep_actions"].append(joint_actions_from_indices(actions[:length, e]))
+        traj["ep_rewards"].append([int(r) for r in sparse[:length, e]])
+        traj["ep_dones"].append([bool(d) for d in done[:length, e]])
+        traj["ep_infos"].append([{} for _ in range(length)])
+        traj["ep_returns"].append(int(sparse[:length, e].sum()))
+        traj["ep_lengths"].append(length)
+        traj["mdp_params"].append(mdp_params if mdp_params is not None else {"layout_name": layout.layout_name})
+        traj["env_params"].append(env_params if env_params is not None else {"horizon": length})
+    for k in ("ep_returns", "ep_lengths"):
+        traj[k] = np.array(traj[k])
+    return traj
+
+
+def replay_table(layout, state_dicts, joint_actions, rewards=None):
+    """A recorded game (rows of state JSON + joint action, e.g. a human-trial CSV) as tensors ready for the
+    engine: (records int32 [N, S], actions int32 [N, 2], rewards int64 [N] or None)."""
+    rec = records_from_dicts(layout, state_dicts)
+    act = action_indices(joint_actions)
+    rew = None if rewards is None else np.asarray(rewards).astype(np.int64)
+    return rec, act, rew

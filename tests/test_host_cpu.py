@@ -158,3 +158,42 @@ def test_sharding_world_size_2_gloo():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "DIST_OK" in out.stdout
+
+
+def test_wire_formats_round_trip_with_reference_dicts():
+    """to_dict JSON / joint-action lists / trajectory dicts <-> packed tensors (wire.py), on the reference's own
+    dict samples stored in the fixtures (incl. real human-trial rows)."""
+    import glob
+    import json
+
+    from overcooked_ai_b200 import wire
+
+    for path in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "trace_human2020_*.npz"))):
+        d = np.load(path)
+        cl = L.compile_layout(str(d["layout"]))
+        sample = json.loads(str(d["to_dict_sample"]))
+        dicts = [sample[k] for k in sorted(sample)]
+        rec = wire.records_from_dicts(cl, [json.dumps(x) for x in dicts])
+        assert rec.shape == (len(dicts), cl.state_words)
+        assert np.array_equal(rec[0], d["states"][0, 0])
+        back = wire.dicts_from_records(cl, rec)
+        for a, b in zip(back, dicts):
+            a["objects"].sort(key=lambda o: o["position"]), b["objects"].sort(key=lambda o: o["position"])
+            assert a == b
+    acts = wire.action_indices(['[[0, 0], "INTERACT"]', [[0, -1], [1, 0]], ("interact", (0, 1))])
+    assert acts.tolist() == [[4, 5], [0, 2], [5, 1]]
+    assert wire.joint_actions_from_indices(acts)[1] == ((0, -1), (1, 0))
+    # trajectory dict of a recorded game: keys and shapes of overcooked_trajectory.py
+    d = np.load(os.path.join(ROOT, "tests", "golden", "greedy_cramped_room.npz"))
+    cl = L.compile_layout("cramped_room")
+    states = d["states"].transpose(1, 0, 2)  # [T, E, S]
+    actions = d["actions"].transpose(1, 0, 2)
+    sparse = d["sparse"].sum(-1).T
+    done = np.zeros_like(sparse)
+    done[-1] = 1
+    tr = wire.trajectories_from_rollout(cl, states, actions, sparse, done)
+    assert set(tr) == {"ep_states", "ep_actions", "ep_rewards", "ep_dones", "ep_infos", "ep_returns", "ep_lengths",
+                       "mdp_params", "env_params", "metadatas"}
+    assert tr["ep_returns"].tolist() == [180] * 5 and tr["ep_lengths"].tolist() == [400] * 5
+    assert tr["ep_states"][0][0] == cl.get_standard_start_state() and tr["ep_dones"][2][-1] is True
+    assert tr["ep_actions"][0][0] == tuple(Action.INDEX_TO_ACTION[a] for a in d["actions"][0, 0])
