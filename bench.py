@@ -257,7 +257,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--extra", action="store_true", help="also time the remaining modes")
-    ap.add_argument("--pdl", action="store_true", help="programmatic dependent launch between K1 launches (step / graph modes)")
+    ap.add_argument("--no-pdl", action="store_true", help="disable programmatic dependent launch between K1 launches")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -286,7 +286,7 @@ def main():
     if args.envs:
         n_envs = args.envs
     T = horizon
-    env = BatchedOvercookedEnv(layouts, n_envs, horizon=horizon, device=dev, auto_reset=True, io=args.io, pdl=args.pdl)
+    env = BatchedOvercookedEnv(layouts, n_envs, horizon=horizon, device=dev, auto_reset=True, io=args.io, pdl=not args.no_pdl)
     S = env.state_words
     gen = torch.Generator(device=dev)
     gen.manual_seed(seed + rank)

@@ -42,7 +42,7 @@ def _as_layouts(layouts, mdp_params):
 
 class BatchedOvercookedEnv(object):
     def __init__(self, layouts, n_envs, horizon=400, device="cuda", auto_reset=False, state_words=None,
-                 io=_native.IO_DEFAULT, env_layout=None, mdp_params=None, pdl=False,
+                 io=_native.IO_DEFAULT, env_layout=None, mdp_params=None, pdl=True,
                  random_start_pos=False, rnd_obj_prob_thresh=0.0, seed=0):
         """
         layouts      layout name / CompiledLayout / OvercookedGridworld, or a list of them (mixed batch)
@@ -51,6 +51,8 @@ class BatchedOvercookedEnv(object):
         env_layout   optional int array [n_envs] of layout indices; default: contiguous, near-equal
                      segments, one per layout (a warp then sees one layout)
         io           record I/O strategy of the step kernel (_native.IO_*); 0 = library default
+        pdl          launch the step kernel with programmatic dependent launch: back-to-back transitions overlap
+                     the next launch's prologue with the current kernel (3.58 -> 3.20 us per launch at 65 536 envs)
         random_start_pos, rnd_obj_prob_thresh, seed
                      start every episode from the reference's randomised start states
                      (get_random_start_state_fn, overcooked_mdp.py:1307-1369) instead of the standard one;

@@ -219,7 +219,6 @@ step_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
     // Programmatic dependent launch: everything above touches only constants, so it may overlap the
     // previous kernel of the stream; state and actions are read after the dependency resolves.
     // (Both instructions are no-ops when the kernel was launched without the PDL attribute.)
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (threadIdx.x == 0) {
         if (IO == 1) tma_load_2d(tile, &tmap, 0, (int)(env0 * C::ROWS_PER_ENV), bar);  // out-of-range rows: zero fill, still counted
@@ -230,6 +229,10 @@ step_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
     if (live) act = load_action(a, env);
     __syncthreads();  // barrier initialised and visible before anyone polls it
     mbar_wait(bar, 0);
+    // Programmatic dependent launch: once the tile has landed, the next kernel of the stream may be
+    // scheduled; its prologue (barrier init, tensor-map prefetch, table fetch) then overlaps this
+    // kernel's compute, and its griddepcontrol.wait holds it until this grid has completed.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (live) {
         SmemRec<S, IO == 1 ? C::SWZ : 0> r{tile, (uint32_t)threadIdx.x * S * 4};
