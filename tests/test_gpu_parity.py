@@ -399,3 +399,29 @@ def test_random_start_states_vs_oracle_mirror(random_pos, thresh):
     cpu.reset_random(env._tab_host, env._starts_host, ref, rs, mask=mask)
     assert np.array_equal(_np(env.state), ref)
     assert len(np.unique(first[:, 1:3], axis=0)) > 10
+
+
+def test_more_than_eight_layouts_uses_global_tables():
+    """With more than 8 layouts the kernel reads the layout table from global memory instead of staging it in
+    shared memory; old_dynamics and new-dynamics layouts mix in one batch."""
+    names = ["cramped_room", "asymmetric_advantages", "coordination_ring", "forced_coordination", "counter_circuit",
+             "bottleneck", "centre_pots", "random0", "random3", "scenario1_s", "schelling_s"]
+    layouts = [L.compile_layout(n) for n in names] + [L.compile_layout("cramped_room", old_dynamics=True)]
+    n = len(layouts) * 300 + 5
+    env = BatchedOvercookedEnv(layouts, n, horizon=40, auto_reset=True)
+    assert env.n_layouts == 12 and env.state_words == 32
+    rng = np.random.RandomState(12)
+    acts = _random_actions(rng, 100, n, 0.4)
+    ref_state = _np(env.state).copy()
+    want = cpu.rollout(env._tab_host, env._starts_host, ref_state, acts, horizon=40, flags=1, n_threads=4)
+    d = torch.from_numpy(acts).cuda()
+    for t in range(30):
+        got = env.step(d[t])
+        for g, w in zip(got, want):
+            assert np.array_equal(_np(g), w[t]), t
+    got = env.rollout(d[30:].contiguous())
+    for g, w in zip(got, want):
+        assert np.array_equal(_np(g), w[30:])
+    assert np.array_equal(_np(env.state), ref_state)
+    f = _np(env.featurize_state(2))
+    assert np.array_equal(f.astype(np.float64), cpu.featurize(env._tab_host, lut_bytes(env.layouts), ref_state, 2))
