@@ -261,6 +261,9 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
+    # stdout carries exactly one JSON line: keep NCCL's own banner ("NCCL version ...", printed when the
+    # environment sets NCCL_DEBUG) on stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -446,4 +449,13 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    finally:
+        try:
+            import torch.distributed as _d
+
+            if _d.is_available() and _d.is_initialized():
+                _d.destroy_process_group()
+        except Exception:
+            pass
