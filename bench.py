@@ -44,6 +44,17 @@ WORKLOADS = {
     "config5": (["cramped_room"], 32768, 400),
 }
 METRIC = "env-steps/sec (joint transitions)"
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line of this run, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def algorithmic_bytes_per_env_step(S):
@@ -178,7 +189,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_policy_pipeline(args, rank, world, local):
@@ -241,7 +252,7 @@ def run_policy_pipeline(args, rank, world, local):
                      "algorithmic_bytes_per_env_step": algorithmic_bytes_per_env_step(S) + enc_bytes},
         "sparse_reward_sum": tot_reward,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -261,9 +272,12 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
-    # stdout carries exactly one JSON line: keep NCCL's own banner ("NCCL version ...", printed when the
-    # environment sets NCCL_DEBUG) on stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout must carry exactly one JSON line, but NCCL printf()s its version banner to fd 1 at communicator
+    # creation: park the real stdout, point fd 1 at stderr for the run, emit the JSON line on the real one.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -445,7 +459,7 @@ def main():
         line["other_modes"] = extra
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(layouts, horizon)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 if __name__ == "__main__":
