@@ -1,0 +1,73 @@
+"""Live differential tests against the UNMODIFIED reference (build container only; skipped where
+/root/reference is absent, e.g. on the GPU box).  Every bundled 2-player layout, fresh random traces each
+run of the seed list: the C oracle vs the reference's own get_state_transition / lossless_state_encoding /
+featurize_state / potential_function.  This is what keeps the oracle pinned beyond the stored fixtures."""
+import json
+
+import numpy as np
+import pytest
+
+from oracle import cpu, refboot
+from overcooked_ai_b200 import layout as L
+from overcooked_ai_b200.state import OvercookedState
+
+pytestmark = pytest.mark.reference
+
+ALL_LAYOUTS = []
+for _n in L.layout_names():
+    try:
+        L.compile_layout(_n)
+        ALL_LAYOUTS.append(_n)
+    except ValueError:
+        pass
+
+
+def _events_mask(ns, infos, agent):
+    m = 0
+    for i, name in enumerate(ns.mdp.EVENT_TYPES):
+        if infos["event_infos"][name][agent]:
+            m |= 1 << i
+    return m
+
+
+@pytest.mark.parametrize("name", ALL_LAYOUTS)
+def test_layout_against_live_reference(name):
+    ns = refboot.boot()
+    m = refboot.make_mdp(ns, name)
+    refboot.use_mdp(ns, m)
+    cl = L.compile_layout(name)
+    tab, starts, S = L.build_tables([cl])
+    small = cl.width * cl.height <= 50
+    if small:
+        holder = refboot.LitePlannerHolder(ns, m)
+        lut = cl.feature_lut().view(np.uint8).reshape(1, -1)
+        pt, cst, gpow = L.build_potential_tables([cl], 0.99)
+    seed = sum(map(ord, name))
+    np.random.seed(seed)
+    rng = np.random.RandomState(seed)
+    fn = m.get_random_start_state_fn(random_start_pos=True, rnd_obj_prob_thresh=0.6)
+    n_obs = 0
+    for ep in range(6):
+        st = fn() if ep else m.get_standard_start_state()
+        for t in range(60):
+            a = rng.randint(0, 6, size=2)
+            if rng.rand() < 0.4:
+                a[rng.randint(2)] = 5
+            rec = L.pack_state(cl, OvercookedState.from_dict(st.to_dict()), 0, S)[None].copy()
+            if t % 10 == 0:
+                enc = cpu.encode_lossless(tab, rec, cl.width, cl.height, 400)[0]
+                assert np.array_equal(enc, np.stack(m.lossless_state_encoding(st, horizon=400))), (name, ep, t)
+                if small:
+                    f = cpu.featurize(tab, lut, rec, 2)[0]
+                    assert np.array_equal(f, np.stack(m.featurize_state(st, holder, num_pots=2))), (name, ep, t)
+                    phi = cpu.potential(tab, pt, cst, gpow, rec)[0]
+                    assert phi == m.potential_function(st, holder.motion_planner, gamma=0.99), (name, ep, t)
+                n_obs += 1
+            ja = tuple(ns.actions.Action.INDEX_TO_ACTION[int(x)] for x in a)
+            st, infos = m.get_state_transition(st, ja)
+            sp, sh, dn, ev = cpu.step(tab, starts, rec, a[None].astype(np.int32), horizon=0)
+            want = L.pack_state(cl, OvercookedState.from_dict(st.to_dict()), 0, S)
+            assert np.array_equal(rec[0], want), (name, ep, t, ja)
+            assert sp[0] == sum(infos["sparse_reward_by_agent"]) and sh[0].tolist() == list(infos["shaped_reward_by_agent"])
+            assert [int(ev[0, 0]) & 0x1FFFFFF, int(ev[0, 1]) & 0x1FFFFFF] == [_events_mask(ns, infos, 0), _events_mask(ns, infos, 1)]
+    assert n_obs == 36
