@@ -425,3 +425,41 @@ def test_more_than_eight_layouts_uses_global_tables():
     assert np.array_equal(_np(env.state), ref_state)
     f = _np(env.featurize_state(2))
     assert np.array_equal(f.astype(np.float64), cpu.featurize(env._tab_host, lut_bytes(env.layouts), ref_state, 2))
+
+
+def _all_two_player_layouts():
+    out = []
+    for n in L.layout_names():
+        try:
+            L.compile_layout(n)
+            out.append(n)
+        except ValueError:
+            pass
+    return out
+
+
+@pytest.mark.parametrize("name", _all_two_player_layouts())
+def test_every_bundled_layout_vs_oracle(name):
+    """All 44 bundled 2-player layouts: random start states, 90 transitions across a horizon, every output,
+    final state, all three observation kernels — against the oracle."""
+    n, horizon, T = 517, 35, 90
+    env = BatchedOvercookedEnv(name, n, horizon=horizon, auto_reset=True, random_start_pos=True, rnd_obj_prob_thresh=0.5,
+                               seed=sum(map(ord, name)))
+    rs = cpu.random_start(sum(map(ord, name)), 0.5, True)
+    ref = np.zeros((n, env.state_words), np.int32)
+    cpu.reset_random(env._tab_host, env._starts_host, ref, rs)
+    assert np.array_equal(_np(env.state), ref)
+    rng = np.random.RandomState(len(name))
+    acts = _random_actions(rng, T, n, 0.4)
+    want = cpu.rollout(env._tab_host, env._starts_host, ref, acts, horizon=horizon, flags=1, n_threads=2, rs=rs)
+    got = env.rollout(torch.from_numpy(acts).cuda())
+    for g, w in zip(got, want):
+        assert np.array_equal(_np(g), w)
+    assert np.array_equal(_np(env.state), ref)
+    l = env.layouts[0]
+    enc = env.lossless_state_encoding(dtype=torch.uint8)
+    assert np.array_equal(_np(enc).astype(np.int32), cpu.encode_lossless(env._tab_host, ref, l.width, l.height, horizon))
+    f = _np(env.featurize_state(2))
+    assert np.array_equal(f.astype(np.float64), cpu.featurize(env._tab_host, lut_bytes([l]), ref, 2))
+    pt, cst, gpow = L.build_potential_tables([l], 0.99)
+    assert np.array_equal(_np(env.potential(0.99)), cpu.potential(env._tab_host, pt, cst, gpow, ref))
