@@ -221,6 +221,7 @@ typedef struct ovc_random_start {
 #define OVC_DT_F32 0
 #define OVC_DT_U8 1
 #define OVC_DT_I32 2
+#define OVC_DT_BF16 3 /* bfloat16: exact for the plane values up to 256 (cook times beyond that round) */
 
 int ovc_abi_version(void);
 size_t ovc_layout_table_size(void); /* sizeof(ovc_layout_t): the host packer checks it */

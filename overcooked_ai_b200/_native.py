@@ -17,7 +17,7 @@ F_ACT_U8 = 4
 F_OUT_NARROW = 8
 F_IO_SHIFT = 8
 IO_DEFAULT, IO_TMA_TENSOR, IO_TMA_BULK, IO_DIRECT = 0, 1, 2, 3
-DT_F32, DT_U8, DT_I32 = 0, 1, 2
+DT_F32, DT_U8, DT_I32, DT_BF16 = 0, 1, 2, 3
 
 
 

@@ -24,7 +24,8 @@ import torch
 from overcooked_ai_b200 import _native
 from overcooked_ai_b200 import layout as L
 
-_TORCH_DT = {torch.float32: _native.DT_F32, torch.uint8: _native.DT_U8, torch.int32: _native.DT_I32}
+_TORCH_DT = {torch.float32: _native.DT_F32, torch.uint8: _native.DT_U8, torch.int32: _native.DT_I32,
+             torch.bfloat16: _native.DT_BF16}
 
 
 def _as_layouts(layouts, mdp_params):

@@ -74,10 +74,10 @@ def test_lossless_reference_golden_pickle():
     env = BatchedOvercookedEnv("cramped_room", len(states), horizon=400)
     env.state.copy_(torch.from_numpy(states))
     want = d["lossless"].reshape(-1, 2, 5, 4, 26)
-    for dt in (torch.float32, torch.uint8, torch.int32):
+    for dt in (torch.float32, torch.uint8, torch.int32, torch.bfloat16):
         enc = env.lossless_state_encoding(dtype=dt)
         assert enc.dtype == dt and tuple(enc.shape) == (len(states), 2, 5, 4, 26)
-        assert np.array_equal(_np(enc).astype(np.int32), want.astype(np.int32))
+        assert np.array_equal(_np(enc.float()).astype(np.int32), want.astype(np.int32))
 
 
 @pytest.mark.parametrize("num_pots", [0, 1, 2])

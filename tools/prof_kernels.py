@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 from overcooked_ai_b200.batched import BatchedOvercookedEnv  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--which", default="k5", choices=["k1", "k5", "k2", "k2u8", "k3"])
+ap.add_argument("--which", default="k5", choices=["k1", "k5", "k2", "k2u8", "k3", "k6"])
 ap.add_argument("--n", type=int, default=65536)
 ap.add_argument("--layouts", default="cramped_room")
 ap.add_argument("--reps", type=int, default=4)
@@ -29,7 +29,11 @@ elif args.which == "k1":
         env.step(acts[t])
 else:
     env.rollout(acts[:150])
-    if args.which == "k3":
+    if args.which == "k6":
+        o = env.potential(0.99)
+        for _ in range(args.reps):
+            env.potential(0.99, out=o)
+    elif args.which == "k3":
         o = env.featurize_state(2)
         for _ in range(args.reps):
             env.featurize_state(2, out=o)
