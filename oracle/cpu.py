@@ -87,17 +87,22 @@ def step(tables, starts, state, actions, horizon=400, flags=0, n_threads=1, rs=N
     return sparse, shaped, done, events
 
 
-def rollout(tables, starts, state, actions, horizon=400, flags=0, n_threads=0, rs=None):
+def alloc_rollout_out(T, n):
+    """Output arrays for rollout(), pages already touched (so a timed call does not pay first-touch faults)."""
+    out = (np.empty((T, n), np.int32), np.empty((T, n, 2), np.int32), np.empty((T, n), np.int32), np.empty((T, n, 2), np.int32))
+    for o in out:
+        o.fill(0)
+    return out
+
+
+def rollout(tables, starts, state, actions, horizon=400, flags=0, n_threads=0, rs=None, out=None):
     """T transitions in place; actions [T,N,2].  Returns sparse[T,N], shaped[T,N,2], done[T,N], events[T,N,2]."""
     assert state.dtype == np.int32 and state.flags.c_contiguous
     n, S = state.shape
     actions = _i32(actions)
     T = actions.shape[0]
     assert actions.shape == (T, n, 2)
-    sparse = np.zeros((T, n), np.int32)
-    shaped = np.zeros((T, n, 2), np.int32)
-    done = np.zeros((T, n), np.int32)
-    events = np.zeros((T, n, 2), np.int32)
+    sparse, shaped, done, events = out if out is not None else alloc_rollout_out(T, n)
     tables = np.ascontiguousarray(tables)
     starts = _i32(starts)
     rc = lib().ovo_rollout(_p(tables), ctypes.c_int(len(tables)), _p(starts), _p(state), _p(actions), _p(sparse),
