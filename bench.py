@@ -370,8 +370,9 @@ def main():
     value = tot_steps / (max_ms * 1e-3)
 
     # ---- e2e: the same workload through the public host-buffer API ----
-    def run_e2e(narrow):
-        pipe = HostRolloutPipeline(env, T, chunk=50, narrow=narrow)
+    def run_e2e(fmt):
+        narrow = fmt != "int32"
+        pipe = HostRolloutPipeline(env, T, chunk=50, narrow=narrow, packed=fmt == "packed")
         h_actions = torch.empty((T, n_envs, 2), dtype=pipe.act_dtype, pin_memory=True)
         h_actions.copy_(actions)
         env.reset()
@@ -390,16 +391,21 @@ def main():
         return {"value": float(n_envs) * T * k_e2e * world / (e2e_max_ms * 1e-3), "unit": "env-steps/s",
                 "h2d_bytes_per_step": pipe.h2d_bytes_per_step * T, "d2h_bytes_per_step": pipe.d2h_bytes_per_step * T,
                 "steps": k_e2e, "ms_per_step": e2e_max_ms / k_e2e,
-                "api": "overcooked_ai_b200.batched.HostRolloutPipeline(narrow=%s).run: pinned host actions (%s) in, pinned host "
-                       "sparse/shaped/done/events (%s) out, 50-transition chunks, H2D / fused rollout kernel / D2H on three streams"
-                       % (narrow, "uint8" if narrow else "int32", "int16/int8/uint8/int32" if narrow else "int32"),
+                "api": "overcooked_ai_b200.batched.HostRolloutPipeline(%s).run: pinned host actions (%s) in, pinned host %s out, "
+                       "50-transition chunks, H2D / fused rollout kernel / D2H on three streams"
+                       % (fmt, "uint8" if narrow else "int32",
+                          {"packed": "sparse int16 + shaped int8x2 + both agents' event codes and done in one int16 (lossless, wire.decode_event_codes)",
+                           "narrow": "sparse int16 / shaped int8 / done uint8 / events int32", "int32": "sparse/shaped/done/events int32"}[fmt]),
                 "checksum_sparse": int(h_out[0].sum(dtype=torch.int64).item())}
 
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(env.narrow_ok())
         if env.narrow_ok():
-            e2e["int32_formats"] = run_e2e(False)  # the same pipeline with the 32-bit-everything formats
+            e2e = run_e2e("packed")
+            e2e["narrow_formats"] = run_e2e("narrow")  # the same pipeline with int32 event masks (13 B out)
+            e2e["int32_formats"] = run_e2e("int32")    # and with 32-bit-everything formats (8 B in, 24 B out)
+        else:
+            e2e = run_e2e("int32")
 
     # ---- the per-transition kernel K1 (400 launches from one CUDA graph), measured in the same run ----
     k1_steps = max(2, min(args.steps, 5))

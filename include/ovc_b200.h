@@ -211,6 +211,18 @@ typedef struct ovc_random_start {
  *                     checks deliver_value <= 32767 and shaping rewards <= 127 before it sets the flag). */
 #define OVC_F_ACT_U8 4
 #define OVC_F_OUT_NARROW 8
+/*   OVC_F_OUT_PACKED  (6 bytes per env-step) `sparse` int16[..], `shaped` int8[..][2], `events` is uint16[..]
+ *                     holding both agents' event CODES, `done` is not written (may be NULL):
+ *                       bits 0-4 agent 0 code, bits 5-9 agent 1 code, bit 10 done, bit 11 stepped-a-finished-env.
+ *                     An agent produces at most one interaction per transition, so its 25 event bits + delivered
+ *                     recipe take one of 32 values:
+ *                       0 nothing | 1,2 onion_pickup (useful) | 3,4 tomato_pickup | 5,6 dish_pickup | 7 soup_pickup
+ *                       8,9 onion_drop (useful) | 10,11 tomato_drop | 12,13 dish_drop | 14 soup_drop
+ *                       15-18 potting_onion, 19-22 potting_tomato: + {0 optimal+viable, 1 viable, 2 catastrophic,
+ *                       3 optimal+useless} | 23-31 soup_delivery of the recipe with rank 0..8 in the order
+ *                       (n_onion,n_tomato) = (0,1),(0,2),(0,3),(1,0),(1,1),(1,2),(2,0),(2,1),(3,0)  [index n_onion*4+n_tomato ascending]
+ *                     The host expands codes back to the int32 masks with a 32-entry table (wire.decode_event_codes). */
+#define OVC_F_OUT_PACKED 16
 /* bits 8-11 select the record I/O strategy of the step kernel (0 = library default):
  *   1 = 2-D tensor-map TMA tile with hardware swizzle, 2 = 1-D bulk TMA (linear tile),
  *   3 = direct vectorised global loads/stores (no staging).  All produce identical results. */

@@ -15,6 +15,7 @@ F_AUTO_RESET = 1
 F_PDL = 2
 F_ACT_U8 = 4
 F_OUT_NARROW = 8
+F_OUT_PACKED = 16
 F_IO_SHIFT = 8
 IO_DEFAULT, IO_TMA_TENSOR, IO_TMA_BULK, IO_DIRECT = 0, 1, 2, 3
 DT_F32, DT_U8, DT_I32, DT_BF16 = 0, 1, 2, 3

@@ -150,10 +150,15 @@ class BatchedOvercookedEnv(object):
             int(l.reward_shaping_params[k]) for k in ("PLACEMENT_IN_POT_REW", "DISH_PICKUP_REWARD", "SOUP_PICKUP_REWARD")) <= 127
             for l in self.layouts)
 
-    def alloc_rollout_out(self, T, narrow=False, pin=False):
+    def alloc_rollout_out(self, T, narrow=False, pin=False, packed=False):
         """Output tensors for rollout(): (sparse[T,N], shaped[T,N,2], done[T,N], events[T,N,2]); int32, or with
-        ``narrow`` int16 / int8 / uint8 / int32 (15 instead of 32 bytes per env-step across PCIe with uint8 actions)."""
+        ``narrow`` int16 / int8 / uint8 / int32 (13 bytes per env-step), or with ``packed`` (6 bytes per env-step)
+        (sparse int16 [T,N], shaped int8 [T,N,2], None, evcode int16 [T,N]) where evcode carries both agents' 5-bit
+        event codes + done (include/ovc_b200.h OVC_F_OUT_PACKED; expand with wire.decode_event_codes)."""
         N = self.n_envs
+        if packed:
+            mk = (lambda sh, dt: torch.empty(sh, dtype=dt, pin_memory=True)) if pin else (lambda sh, dt: torch.empty(sh, dtype=dt, device=self.device))
+            return (mk((T, N), torch.int16), mk((T, N, 2), torch.int8), None, mk((T, N), torch.int16))
         dts = (torch.int16, torch.int8, torch.uint8, torch.int32) if narrow else (torch.int32,) * 4
         shapes = ((T, N), (T, N, 2), (T, N), (T, N, 2))
         if pin:
@@ -177,7 +182,11 @@ class BatchedOvercookedEnv(object):
         flags = self._flags()
         if actions.dtype == torch.uint8:
             flags |= _native.F_ACT_U8
-        if sparse.dtype == torch.int16:
+        if done is None:  # packed: 6 bytes per env-step
+            assert sparse.dtype == torch.int16 and shaped.dtype == torch.int8 and events.dtype == torch.int16 and events.dim() == 2
+            assert self.narrow_ok(), "rewards of these layouts do not fit the narrow formats"
+            flags |= _native.F_OUT_PACKED
+        elif sparse.dtype == torch.int16:
             assert shaped.dtype == torch.int8 and done.dtype == torch.uint8 and events.dtype == torch.int32
             assert self.narrow_ok(), "rewards of these layouts do not fit the narrow formats"
             flags |= _native.F_OUT_NARROW
@@ -185,7 +194,7 @@ class BatchedOvercookedEnv(object):
             assert sparse.dtype == shaped.dtype == done.dtype == events.dtype == torch.int32
         _native.check(self._lib.ovc_rollout(
             self.tables.data_ptr(), self.n_layouts, self.start_records.data_ptr(), self.state.data_ptr(),
-            actions.data_ptr(), sparse.data_ptr(), shaped.data_ptr(), done.data_ptr(), events.data_ptr(),
+            actions.data_ptr(), sparse.data_ptr(), shaped.data_ptr(), 0 if done is None else done.data_ptr(), events.data_ptr(),
             self.n_envs, T, self.state_words, self.horizon, flags, self._rs_ptr(), self._stream()))
         return out
 
@@ -302,18 +311,20 @@ class HostRolloutPipeline(object):
     host->device and 24 bytes device->host.
     """
 
-    def __init__(self, env, n_steps, chunk=50, narrow=False):
+    def __init__(self, env, n_steps, chunk=50, narrow=False, packed=False):
         """narrow=True: uint8 actions in, int16 sparse / int8 shaped / uint8 done / int32 events out — the same
-        values in 2 + 13 instead of 8 + 24 bytes per env-step."""
-        self.env, self.T, self.chunk, self.narrow = env, int(n_steps), int(chunk), bool(narrow)
+        values in 2 + 13 instead of 8 + 24 bytes per env-step.  packed=True: uint8 actions in, int16 sparse / int8
+        shaped / int16 event codes (+done) out — 2 + 6 bytes per env-step, lossless (wire.decode_event_codes)."""
+        narrow = narrow or packed
+        self.env, self.T, self.chunk, self.narrow, self.packed = env, int(n_steps), int(chunk), bool(narrow), bool(packed)
         N, dev = env.n_envs, env.device
         self.s_h2d, self.s_comp, self.s_d2h = (torch.cuda.Stream(dev) for _ in range(3))
         self.act_dtype = torch.uint8 if narrow else torch.int32
         self.d_act = [torch.empty((chunk, N, 2), dtype=self.act_dtype, device=dev) for _ in range(2)]
-        self.d_out = [env.alloc_rollout_out(chunk, narrow=narrow) for _ in range(2)]
-        self.h_out = env.alloc_rollout_out(self.T, narrow=narrow, pin=True)
+        self.d_out = [env.alloc_rollout_out(chunk, narrow=narrow, packed=packed) for _ in range(2)]
+        self.h_out = env.alloc_rollout_out(self.T, narrow=narrow, pin=True, packed=packed)
         self.h2d_bytes_per_step = N * 2 * self.d_act[0].element_size()
-        self.d2h_bytes_per_step = sum(N * (2 if o.dim() == 3 else 1) * o.element_size() for o in self.h_out)
+        self.d2h_bytes_per_step = sum(N * (2 if o.dim() == 3 else 1) * o.element_size() for o in self.h_out if o is not None)
 
     def run(self, actions_host):
         assert actions_host.dtype == self.act_dtype and actions_host.is_pinned() and tuple(actions_host.shape) == (self.T, self.env.n_envs, 2)
@@ -337,7 +348,7 @@ class HostRolloutPipeline(object):
                 self.s_comp.wait_event(ev_in)
                 if ev_d2h_done[b] is not None:
                     self.s_comp.wait_event(ev_d2h_done[b])  # d_out[b] is free again
-                out = tuple(o[:tc] for o in self.d_out[b])
+                out = tuple(None if o is None else o[:tc] for o in self.d_out[b])
                 env.rollout(self.d_act[b][:tc], out=out)
                 ev_c = torch.cuda.Event()
                 ev_c.record(self.s_comp)
@@ -345,7 +356,8 @@ class HostRolloutPipeline(object):
             with torch.cuda.stream(self.s_d2h):
                 self.s_d2h.wait_event(ev_c)
                 for h, d in zip(self.h_out, out):
-                    h[t0:t0 + tc].copy_(d, non_blocking=True)
+                    if h is not None:
+                        h[t0:t0 + tc].copy_(d, non_blocking=True)
                 ev_o = torch.cuda.Event()
                 ev_o.record(self.s_d2h)
                 ev_d2h_done[b] = ev_o

@@ -150,7 +150,38 @@ struct StepArgs {
     ovc_random_start_t rs;
 };
 
+// 25-bit event mask (+ delivered recipe in bits 25-28) of ONE agent -> 5-bit code (see OVC_F_OUT_PACKED)
+__device__ __forceinline__ unsigned event_code(unsigned ev) {
+    if ((ev & 0x1FFFFFFu) == 0) return 0;
+    if (ev & (1u << OVC_EV_SOUP_DELIVERY)) {
+        const unsigned row = (ev >> OVC_EV_RECIPE_SHIFT) & 15u;  // rows 1,2,3,4,5,6,8,9,12 -> ranks 0..8
+        return 23u + (unsigned)((0x0008007605432100ull >> (row * 4)) & 15u);
+    }
+    if (ev & ((1u << OVC_EV_POTTING_ONION) | (1u << OVC_EV_POTTING_TOMATO))) {
+        const unsigned tom = (ev >> OVC_EV_POTTING_TOMATO) & 1u;
+        const unsigned viable = (ev >> (OVC_EV_VIABLE_ONION_POTTING + tom)) & 1u, optimal = (ev >> (OVC_EV_OPTIMAL_ONION_POTTING + tom)) & 1u;
+        const unsigned cata = (ev >> (OVC_EV_CATASTROPHIC_ONION_POTTING + tom)) & 1u;
+        return 15u + tom * 4u + (viable ? (optimal ? 0u : 1u) : (cata ? 2u : 3u));
+    }
+    if (ev & (1u << OVC_EV_SOUP_PICKUP)) return 7;
+    if (ev & (1u << OVC_EV_SOUP_DROP)) return 14;
+    if (ev & (1u << OVC_EV_ONION_PICKUP)) return 1u + ((ev >> OVC_EV_USEFUL_ONION_PICKUP) & 1u);
+    if (ev & (1u << OVC_EV_TOMATO_PICKUP)) return 3u + ((ev >> OVC_EV_USEFUL_TOMATO_PICKUP) & 1u);
+    if (ev & (1u << OVC_EV_DISH_PICKUP)) return 5u + ((ev >> OVC_EV_USEFUL_DISH_PICKUP) & 1u);
+    if (ev & (1u << OVC_EV_ONION_DROP)) return 8u + ((ev >> OVC_EV_USEFUL_ONION_DROP) & 1u);
+    if (ev & (1u << OVC_EV_TOMATO_DROP)) return 10u + ((ev >> OVC_EV_USEFUL_TOMATO_DROP) & 1u);
+    return 12u + ((ev >> OVC_EV_USEFUL_DISH_DROP) & 1u);  // dish_drop
+}
+
 __device__ __forceinline__ void write_outputs(const StepArgs &a, long long idx, const StepOut &o) {
+    if (a.flags & OVC_F_OUT_PACKED) {  // 6 bytes per env-step for host transfer
+        reinterpret_cast<short *>(a.sparse)[idx] = (short)o.sparse;
+        reinterpret_cast<char2 *>(a.shaped)[idx] = make_char2((signed char)o.shaped0, (signed char)o.shaped1);
+        reinterpret_cast<unsigned short *>(a.events)[idx] =
+            (unsigned short)(event_code(o.ev0) | (event_code(o.ev1) << 5) | ((unsigned)o.done << 10) |
+                             ((o.ev0 & OVC_EVF_STEPPED_DONE) ? 1u << 11 : 0u));
+        return;
+    }
     if (a.flags & OVC_F_OUT_NARROW) {  // uniform branch: int16 / int8x2 / uint8 for host transfer
         reinterpret_cast<short *>(a.sparse)[idx] = (short)o.sparse;
         reinterpret_cast<unsigned char *>(a.done)[idx] = (unsigned char)o.done;
@@ -382,12 +413,14 @@ static int step_impl(const void *layouts, int n_layouts, const int32_t *start_re
                      void *stream) {
     int rc = check_common(layouts, n_layouts, state, n_envs, S);
     if (rc) return rc;
-    if (!actions || !sparse || !shaped || !done || !events || !start_records)
+    if (!actions || !sparse || !shaped || (!done && !(flags & OVC_F_OUT_PACKED)) || !events || !start_records)
         return fail(OVC_E_BADARG, "null pointer argument%s", "");
-    if ((((flags & OVC_F_ACT_U8) ? 0 : (uintptr_t)actions) | ((flags & OVC_F_OUT_NARROW) ? 0 : (uintptr_t)shaped) |
-         (uintptr_t)events) & 7)
+    const bool small_out = flags & (OVC_F_OUT_NARROW | OVC_F_OUT_PACKED);
+    if ((((flags & OVC_F_ACT_U8) ? 0 : (uintptr_t)actions) | (small_out ? 0 : (uintptr_t)shaped) |
+         ((flags & OVC_F_OUT_PACKED) ? 0 : (uintptr_t)events)) & 7)
         return fail(OVC_E_BADARG, "actions / shaped / events must be 8-byte aligned%s", "");
-    if ((((flags & OVC_F_ACT_U8) ? (uintptr_t)actions : 0) | ((flags & OVC_F_OUT_NARROW) ? ((uintptr_t)shaped | (uintptr_t)sparse) : 0)) & 1)
+    if ((((flags & OVC_F_ACT_U8) ? (uintptr_t)actions : 0) | (small_out ? ((uintptr_t)shaped | (uintptr_t)sparse) : 0) |
+         ((flags & OVC_F_OUT_PACKED) ? (uintptr_t)events : 0)) & 1)
         return fail(OVC_E_BADARG, "narrow actions / shaped / sparse must be 2-byte aligned%s", "");
     if (n_steps < 1) return fail(OVC_E_BADARG, "n_steps must be >= 1%s", "");
     if (n_envs == 0) return OVC_OK;

@@ -91,3 +91,35 @@ def replay_table(layout, state_dicts, joint_actions, rewards=None):
     act = action_indices(joint_actions)
     rew = None if rewards is None else np.asarray(rewards).astype(np.int64)
     return rec, act, rew
+
+
+def _event_code_table():
+    """32 event codes (include/ovc_b200.h, OVC_F_OUT_PACKED) -> int32 event mask incl. the delivered-recipe bits."""
+    E = {n: i for i, n in enumerate(L.EVENT_TYPES)}
+    t = np.zeros(32, np.int64)
+    for k, obj in enumerate(("onion", "tomato", "dish")):
+        for useful in (0, 1):
+            t[1 + 2 * k + useful] = (1 << E[obj + "_pickup"]) | (useful << E["useful_" + obj + "_pickup"])
+            t[8 + 2 * k + useful] = (1 << E[obj + "_drop"]) | (useful << E["useful_" + obj + "_drop"])
+    t[7], t[14] = 1 << E["soup_pickup"], 1 << E["soup_drop"]
+    for k, obj in enumerate(("onion", "tomato")):
+        base = 1 << E["potting_" + obj]
+        combos = (("optimal", "viable"), ("viable",), ("catastrophic",), ("optimal", "useless"))
+        for c, names in enumerate(combos):
+            t[15 + 4 * k + c] = base | sum(1 << E["%s_%s_potting" % (nm, obj)] for nm in names)
+    rows = [r for r in range(1, 16) if (r >> 2) + (r & 3) <= 3]  # 1,2,3,4,5,6,8,9,12
+    for rank, row in enumerate(rows):
+        t[23 + rank] = (1 << E["soup_delivery"]) | (row << L.EV_RECIPE_SHIFT)
+    return t.astype(np.int32)
+
+
+EVENT_CODE_TABLE = _event_code_table()
+
+
+def decode_event_codes(evcode):
+    """int16 [...] packed event codes -> (events int32 [..., 2], done bool [...]) exactly as the int32 formats."""
+    ev = np.asarray(evcode).astype(np.int32)
+    events = np.stack([EVENT_CODE_TABLE[ev & 31], EVENT_CODE_TABLE[(ev >> 5) & 31]], -1)
+    stepped = ((ev >> 11) & 1).astype(bool)
+    events[stepped] = L.EVF_STEPPED_DONE
+    return events, ((ev >> 10) & 1).astype(bool)

@@ -356,6 +356,17 @@ def test_narrow_transfer_formats_and_host_pipeline():
     env_b = BatchedOvercookedEnv("cramped_room", n, horizon=50, auto_reset=True)
     assert env_a.narrow_ok()
     want = env_a.rollout(torch.from_numpy(acts).cuda())
+    from overcooked_ai_b200 import wire
+
+    env_b.reset()
+    pipe = HostRolloutPipeline(env_b, T, chunk=32, packed=True)
+    got = pipe.run(torch.from_numpy(acts.astype(np.uint8)).pin_memory())
+    torch.cuda.synchronize()
+    assert got[2] is None and got[3].dtype == torch.int16 and pipe.d2h_bytes_per_step == n * 6
+    ev, dn = wire.decode_event_codes(got[3].numpy())
+    assert np.array_equal(got[0].numpy(), _np(want[0])) and np.array_equal(got[1].numpy(), _np(want[1]))
+    assert np.array_equal(ev, _np(want[3])) and np.array_equal(dn, _np(want[2]) != 0)
+    assert torch.equal(env_b.state, env_a.state)
     for narrow in (True, False):
         env_b.reset()
         pipe = HostRolloutPipeline(env_b, T, chunk=32, narrow=narrow)
@@ -463,3 +474,30 @@ def test_every_bundled_layout_vs_oracle(name):
     assert np.array_equal(f.astype(np.float64), cpu.featurize(env._tab_host, lut_bytes([l]), ref, 2))
     pt, cst, gpow = L.build_potential_tables([l], 0.99)
     assert np.array_equal(_np(env.potential(0.99)), cpu.potential(env._tab_host, pt, cst, gpow, ref))
+
+
+def test_packed_event_codes_cover_every_event_pattern():
+    """OVC_F_OUT_PACKED: decoding the 5-bit event codes gives back exactly the int32 event masks on every
+    fixture transition (all 25 event types, deliveries of several recipes) and on finished-env steps."""
+    from overcooked_ai_b200 import wire
+
+    seen = set()
+    for path in TRACE_FILES:
+        tr = Trace(path)
+        s0, a, s1, sparse, shaped, events = tr.flat()
+        env = _env_for_trace(tr, len(s0), 0)
+        env.state.copy_(torch.from_numpy(s0))
+        full = env.rollout(torch.from_numpy(a[None]).cuda())
+        env.state.copy_(torch.from_numpy(s0))
+        out = env.alloc_rollout_out(1, packed=True)
+        env.rollout(torch.from_numpy(a[None].astype(np.uint8)).cuda(), out=out)
+        ev, dn = wire.decode_event_codes(_np(out[3]))
+        assert np.array_equal(ev, _np(full[3])) and np.array_equal(_np(out[0]), _np(full[0])) and np.array_equal(_np(out[1]), _np(full[1]))
+        seen |= set(np.unique(_np(out[3]).astype(np.int32) & 31).tolist()) | set(np.unique((_np(out[3]).astype(np.int32) >> 5) & 31).tolist())
+    assert len(seen) >= 24, sorted(seen)
+    env = BatchedOvercookedEnv("cramped_room", 64, horizon=3, auto_reset=False)
+    acts = torch.zeros((5, 64, 2), dtype=torch.uint8, device="cuda")
+    out = env.alloc_rollout_out(5, packed=True)
+    env.rollout(acts, out=out)
+    ev, dn = wire.decode_event_codes(_np(out[3]))
+    assert dn[2:].all() and not dn[:2].any() and (ev[3:] == L.EVF_STEPPED_DONE).all()
