@@ -278,8 +278,8 @@ class BatchedOvercookedEnv(object):
         return out
 
     # ---------------------------------------------------------------------------------------------
-    def sparse_by_agent(self, sparse_unused, events):
-        """Per-agent delivery reward from the event words (bits 25-28 carry the delivered recipe)."""
+    def sparse_by_agent(self, events):
+        """Per-agent delivery reward int32 [..., N, 2] from the event words (bits 25-28 carry the delivered recipe)."""
         val = torch.from_numpy(np.stack([l.deliver_value for l in self.layouts]).astype(np.int32)).to(events.device)
         rec = (events >> L.EV_RECIPE_SHIFT) & 15
         lid = self.env_layout.long().view(*([1] * (events.dim() - 2)), -1, 1).expand_as(rec)

@@ -29,8 +29,12 @@ namespace ovc {
 // ------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
 
-static int fail(int code, const char *fmt, const char *a = "", long long b = 0) {
-    snprintf(g_err, sizeof g_err, fmt, a, b);
+static int fail(int code, const char *msg) {
+    snprintf(g_err, sizeof g_err, "%s", msg);
+    return code;
+}
+static int fail(int code, const char *msg, long long value) {
+    snprintf(g_err, sizeof g_err, "%s (got %lld)", msg, value);
     return code;
 }
 static int cuda_fail(cudaError_t e, const char *what) {
@@ -348,7 +352,7 @@ template <int S>
 static int make_tmap(CUtensorMap *m, int32_t *state, long long n_envs) {
     using C = Cfg<S>;
     encode_tiled_fn enc = get_encode_fn();
-    if (!enc) return fail(OVC_E_CUDA, "cuTensorMapEncodeTiled entry point not available%s", "");
+    if (!enc) return fail(OVC_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[2] = {(cuuint64_t)C::ROW_WORDS, (cuuint64_t)(n_envs * C::ROWS_PER_ENV)};
     cuuint64_t strides[1] = {(cuuint64_t)C::ROW_WORDS * 4};
     cuuint32_t box[2] = {(cuuint32_t)C::ROW_WORDS, (cuuint32_t)C::BOX_ROWS};
@@ -356,7 +360,7 @@ static int make_tmap(CUtensorMap *m, int32_t *state, long long n_envs) {
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, state, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      S == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(OVC_E_CUDA, "cuTensorMapEncodeTiled failed%s (CUresult %lld)", "", (long long)r);
+    if (r != CUDA_SUCCESS) return fail(OVC_E_CUDA, "cuTensorMapEncodeTiled failed", (long long)r);
     return OVC_OK;
 }
 
@@ -398,12 +402,12 @@ static int launch_step(const StepArgs &a, int io, cudaStream_t st) {
 }
 
 static int check_common(const void *layouts, int n_layouts, const void *state, long long n_envs, int S) {
-    if (!layouts || !state) return fail(OVC_E_BADARG, "null pointer argument%s", "");
-    if (n_layouts <= 0 || n_layouts > 256) return fail(OVC_E_BADARG, "n_layouts must be 1..256%s (got %lld)", "", n_layouts);
-    if (n_envs < 0) return fail(OVC_E_BADARG, "negative n_envs%s", "");
+    if (!layouts || !state) return fail(OVC_E_BADARG, "null pointer argument");
+    if (n_layouts <= 0 || n_layouts > 256) return fail(OVC_E_BADARG, "n_layouts must be 1..256", (long long)(n_layouts));
+    if (n_envs < 0) return fail(OVC_E_BADARG, "negative n_envs");
     if (S != 16 && S != 32 && S != 64 && S != 128)
-        return fail(OVC_E_BADARG, "state_words must be 16, 32, 64 or 128%s (got %lld)", "", S);
-    if (((uintptr_t)state & 15) != 0) return fail(OVC_E_BADARG, "state must be 16-byte aligned%s", "");
+        return fail(OVC_E_BADARG, "state_words must be 16, 32, 64 or 128", (long long)(S));
+    if (((uintptr_t)state & 15) != 0) return fail(OVC_E_BADARG, "state must be 16-byte aligned");
     return OVC_OK;
 }
 
@@ -414,19 +418,19 @@ static int step_impl(const void *layouts, int n_layouts, const int32_t *start_re
     int rc = check_common(layouts, n_layouts, state, n_envs, S);
     if (rc) return rc;
     if (!actions || !sparse || !shaped || (!done && !(flags & OVC_F_OUT_PACKED)) || !events || !start_records)
-        return fail(OVC_E_BADARG, "null pointer argument%s", "");
+        return fail(OVC_E_BADARG, "null pointer argument");
     const bool small_out = flags & (OVC_F_OUT_NARROW | OVC_F_OUT_PACKED);
     if ((((flags & OVC_F_ACT_U8) ? 0 : (uintptr_t)actions) | (small_out ? 0 : (uintptr_t)shaped) |
          ((flags & OVC_F_OUT_PACKED) ? 0 : (uintptr_t)events)) & 7)
-        return fail(OVC_E_BADARG, "actions / shaped / events must be 8-byte aligned%s", "");
+        return fail(OVC_E_BADARG, "actions / shaped / events must be 8-byte aligned");
     if ((((flags & OVC_F_ACT_U8) ? (uintptr_t)actions : 0) | (small_out ? ((uintptr_t)shaped | (uintptr_t)sparse) : 0) |
          ((flags & OVC_F_OUT_PACKED) ? (uintptr_t)events : 0)) & 1)
-        return fail(OVC_E_BADARG, "narrow actions / shaped / sparse must be 2-byte aligned%s", "");
-    if (n_steps < 1) return fail(OVC_E_BADARG, "n_steps must be >= 1%s", "");
+        return fail(OVC_E_BADARG, "narrow actions / shaped / sparse must be 2-byte aligned");
+    if (n_steps < 1) return fail(OVC_E_BADARG, "n_steps must be >= 1");
     if (n_envs == 0) return OVC_OK;
     int io = (flags & OVC_F_IO_MASK) >> OVC_F_IO_SHIFT;
     if (io == 0) io = 1;
-    if (io < 1 || io > 3) return fail(OVC_E_BADARG, "unknown record I/O strategy%s %lld", "", io);
+    if (io < 1 || io > 3) return fail(OVC_E_BADARG, "unknown record I/O strategy", (long long)(io));
     if (io == 1 && (n_envs * (S / (S == 16 ? 16 : 32))) > 0x7FFFFFFFLL) io = 2;  // tensor coordinates are int32
     StepArgs a{(const ovc_layout_t *)layouts, start_records, state, actions, sparse, shaped, done, events,
                n_envs, n_layouts, n_steps, horizon, flags, rs != nullptr, rs ? *rs : ovc_random_start_t{0, 0, 0}};
@@ -473,7 +477,7 @@ int ovc_reset(const void *layouts, int n_layouts, const int32_t *start_records, 
               const int32_t *mask, int64_t n_envs, int state_words, const ovc_random_start_t *random_start, void *stream) {
     int rc = ovc::check_common(layouts, n_layouts, state, n_envs, state_words);
     if (rc) return rc;
-    if (!start_records) return ovc::fail(OVC_E_BADARG, "null pointer argument%s", "");
+    if (!start_records) return ovc::fail(OVC_E_BADARG, "null pointer argument");
     if (n_envs == 0) return OVC_OK;
     const int threads = 256;
     if (random_start) {

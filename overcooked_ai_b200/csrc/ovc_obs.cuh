@@ -159,13 +159,13 @@ static int gcd_int(int a, int b) { return b ? gcd_int(b, a % b) : a; }
 
 static int encode_lossless_impl(const ovc_layout_t *layouts, const int32_t *state, const int32_t *view_swap, void *out,
                                 int dtype, long long n_envs, int S, int W, int H, int horizon, cudaStream_t st) {
-    if (!out) return fail(OVC_E_BADARG, "null output pointer%s", "");
-    if (((uintptr_t)out & 15) != 0) return fail(OVC_E_BADARG, "output must be 16-byte aligned%s", "");
-    if (W < 1 || W > 16 || H < 1 || H > 16) return fail(OVC_E_BADARG, "grid shape out of range%s", "");
+    if (!out) return fail(OVC_E_BADARG, "null output pointer");
+    if (((uintptr_t)out & 15) != 0) return fail(OVC_E_BADARG, "output must be 16-byte aligned");
+    if (W < 1 || W > 16 || H < 1 || H > 16) return fail(OVC_E_BADARG, "grid shape out of range");
     if (n_envs == 0) return OVC_OK;
     const int esize = dtype == OVC_DT_U8 ? 1 : dtype == OVC_DT_BF16 ? 2 : 4;
     if (dtype != OVC_DT_F32 && dtype != OVC_DT_U8 && dtype != OVC_DT_I32 && dtype != OVC_DT_BF16)
-        return fail(OVC_E_BADARG, "unknown dtype%s %lld", "", dtype);
+        return fail(OVC_E_BADARG, "unknown dtype", (long long)(dtype));
     EncodeArgs a;
     a.layouts = layouts, a.state = state, a.view_swap = view_swap, a.out = out, a.n_envs = n_envs;
     a.S = S, a.W = W, a.H = H, a.horizon = horizon;
@@ -330,9 +330,9 @@ __global__ void __launch_bounds__(256) featurize_kernel(const FeatArgs a) {
 
 static int featurize_impl(const ovc_layout_t *layouts, const ovc_feat_lut_entry_t *lut, const int32_t *state,
                           const int32_t *view_swap, float *out, long long n_envs, int S, int num_pots, cudaStream_t st) {
-    if (!out || !lut) return fail(OVC_E_BADARG, "null pointer argument%s", "");
-    if (((uintptr_t)out & 15) != 0) return fail(OVC_E_BADARG, "output must be 16-byte aligned%s", "");
-    if (num_pots < 0 || num_pots > 16) return fail(OVC_E_BADARG, "num_pots out of range%s", "");
+    if (!out || !lut) return fail(OVC_E_BADARG, "null pointer argument");
+    if (((uintptr_t)out & 15) != 0) return fail(OVC_E_BADARG, "output must be 16-byte aligned");
+    if (num_pots < 0 || num_pots > 16) return fail(OVC_E_BADARG, "num_pots out of range");
     if (n_envs == 0) return OVC_OK;
     FeatArgs a;
     a.layouts = layouts, a.lut = lut, a.state = state, a.view_swap = view_swap, a.out = out, a.n_envs = n_envs, a.S = S;

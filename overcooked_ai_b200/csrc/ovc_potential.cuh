@@ -191,8 +191,8 @@ __global__ void __launch_bounds__(128) potential_kernel(const PotArgs a) {
 static int potential_impl(const ovc_layout_t *layouts, const ovc_potential_t *pt, const ovc_cost_lut_entry_t *cost,
                           const double *gpow, int n_pow, const int32_t *state, double *out, long long n_envs, int S,
                           cudaStream_t st) {
-    if (!pt || !cost || !gpow || !out) return fail(OVC_E_BADARG, "null pointer argument%s", "");
-    if (n_pow < 2) return fail(OVC_E_BADARG, "gamma power table too short%s", "");
+    if (!pt || !cost || !gpow || !out) return fail(OVC_E_BADARG, "null pointer argument");
+    if (n_pow < 2) return fail(OVC_E_BADARG, "gamma power table too short");
     if (n_envs == 0) return OVC_OK;
     PotArgs a{layouts, pt, cost, gpow, state, out, n_envs, S, n_pow};
     potential_kernel<<<(unsigned)((n_envs + 127) / 128), 128, 0, st>>>(a);

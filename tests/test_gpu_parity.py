@@ -40,7 +40,7 @@ def test_golden_transitions(path, io):
     assert np.array_equal(_np(sh), shaped)
     assert np.array_equal(_np(ev) & EVENT_MASK, events)
     assert not _np(dn).any()
-    by_agent = _np(env.sparse_by_agent(sp, ev))
+    by_agent = _np(env.sparse_by_agent(ev))
     assert np.array_equal(by_agent.reshape(tr.sparse2.shape), tr.sparse2)
 
 
