@@ -365,3 +365,49 @@ class HostRolloutPipeline(object):
         for s in (self.s_h2d, self.s_comp, self.s_d2h):
             cur.wait_stream(s)
         return self.h_out
+
+
+class EpisodeStats(object):
+    """Running per-environment episode statistics on the device — the batched form of OvercookedEnv.game_stats
+    (overcooked_env.py:308-319, 382-401) and of the ``episode`` entry of the info dict (:363-380).
+
+    The reference keeps, per event and agent, the LIST of timesteps at which it fired; its consumers only ever
+    take ``len()`` of those lists (rllib.py:480-483), so counts are kept: ``event_counts[N, 2, 25]``, plus
+    ``cumulative_sparse_rewards_by_agent[N, 2]``, ``cumulative_shaped_rewards_by_agent[N, 2]`` and ``ep_length[N]``.
+    ``update`` returns the finished environments' statistics (a dict of tensors, rows selected by ``done``) and
+    clears them for the next episode.
+    """
+
+    def __init__(self, env):
+        self.env = env
+        N, dev = env.n_envs, env.device
+        self.event_counts = torch.zeros((N, 2, 25), dtype=torch.int32, device=dev)
+        self.cumulative_sparse_rewards_by_agent = torch.zeros((N, 2), dtype=torch.int64, device=dev)
+        self.cumulative_shaped_rewards_by_agent = torch.zeros((N, 2), dtype=torch.int64, device=dev)
+        self.ep_length = torch.zeros(N, dtype=torch.int32, device=dev)
+        self._bits = torch.arange(25, device=dev, dtype=torch.int32)
+
+    def update(self, sparse, shaped, done, events):
+        """Feed the outputs of one step() (tensors [N], [N,2], [N], [N,2])."""
+        self.cumulative_sparse_rewards_by_agent += self.env.sparse_by_agent(events)
+        self.cumulative_shaped_rewards_by_agent += shaped
+        self.event_counts += (events.unsqueeze(-1) >> self._bits) & 1
+        self.ep_length += 1
+        d = done != 0
+        finished = None
+        if bool(d.any()):
+            idx = torch.nonzero(d).squeeze(1)
+            finished = {
+                "env_index": idx,
+                "ep_game_stats": self.event_counts[idx].clone(),
+                "ep_sparse_r_by_agent": self.cumulative_sparse_rewards_by_agent[idx].clone(),
+                "ep_shaped_r_by_agent": self.cumulative_shaped_rewards_by_agent[idx].clone(),
+                "ep_sparse_r": self.cumulative_sparse_rewards_by_agent[idx].sum(1),
+                "ep_shaped_r": self.cumulative_shaped_rewards_by_agent[idx].sum(1),
+                "ep_length": self.ep_length[idx].clone(),
+            }
+            self.event_counts[idx] = 0
+            self.cumulative_sparse_rewards_by_agent[idx] = 0
+            self.cumulative_shaped_rewards_by_agent[idx] = 0
+            self.ep_length[idx] = 0
+        return finished

@@ -111,3 +111,28 @@ def test_multi_agent_wrapper_use_phi_dense_reward():
         assert np.array_equal(_np(dones["__all__"]), dn != 0)
         ref[dn != 0] = env._starts_host[0]
         assert np.array_equal(_np(env.state), ref)
+
+
+def test_episode_stats_match_reference_game_stats_on_greedy_games():
+    """EpisodeStats == len() of the reference env's game_stats lists + cumulative rewards (overcooked_env.py:382-401),
+    on the 5 GreedyHumanModel games of the fixture (9 deliveries each)."""
+    from helpers import GOLD, Trace
+    from overcooked_ai_b200.batched import EpisodeStats
+
+    tr = Trace(GOLD + "/greedy_cramped_room.npz")
+    env = BatchedOvercookedEnv("cramped_room", tr.E, horizon=400, auto_reset=True)
+    stats = EpisodeStats(env)
+    acts = torch.from_numpy(np.ascontiguousarray(tr.actions.transpose(1, 0, 2))).cuda()
+    fin = None
+    for t in range(tr.T):
+        out = env.step(acts[t])
+        f = stats.update(*out)
+        assert (f is None) == (t < tr.T - 1)
+        fin = f or fin
+    assert fin["ep_length"].tolist() == [400] * 5 and fin["ep_sparse_r"].tolist() == [180] * 5
+    want_counts = np.stack([((tr.events[e][:, :, None] >> np.arange(25)) & 1).sum(0) for e in range(tr.E)])
+    assert np.array_equal(_np(fin["ep_game_stats"]), want_counts)
+    assert np.array_equal(_np(fin["ep_shaped_r_by_agent"]), tr.shaped.sum(1))
+    assert np.array_equal(_np(fin["ep_sparse_r_by_agent"]), tr.sparse2.sum(1))
+    assert int(fin["ep_game_stats"][:, :, 15].sum()) == 45  # soup_delivery
+    assert not stats.event_counts.any() and not stats.ep_length.any()
