@@ -84,7 +84,7 @@ class ClockSampler(object):
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -362,12 +362,20 @@ def main():
     if rank == 0:
         sampler.start()
     ms, launches = timed(passes[args.mode], args.steps, args.warmup)
-    clocks = sampler.stop() if rank == 0 else None
 
     steps_local = float(n_envs) * T * args.steps
     reward_local = float(out[0].sum().item())
     tot_steps, max_ms, tot_reward = D.reduce_counters(steps_local, ms, reward_local, device=dev)
     value = tot_steps / (max_ms * 1e-3)
+
+    # ---- the per-transition kernel K1 (400 launches from one CUDA graph), measured in the same run ----
+    k1_steps = max(2, min(args.steps, 5))
+    if args.mode == "graph":
+        k1_ms, k1_launches = ms, launches
+        k1_steps = args.steps
+    else:
+        k1_ms, k1_launches = timed(pass_graph, k1_steps, 3)
+    clocks = sampler.stop() if rank == 0 else None  # sampled (20 ms period) over the headline region and the K1 region
 
     # ---- e2e: the same workload through the public host-buffer API ----
     def run_e2e(fmt):
@@ -407,13 +415,6 @@ def main():
         else:
             e2e = run_e2e("int32")
 
-    # ---- the per-transition kernel K1 (400 launches from one CUDA graph), measured in the same run ----
-    k1_steps = max(2, min(args.steps, 5))
-    if args.mode == "graph":
-        k1_ms, k1_launches = ms, launches
-        k1_steps = args.steps
-    else:
-        k1_ms, k1_launches = timed(pass_graph, k1_steps, 3)
     extra = {}
     if args.extra:
         for m in ("step", "rollout"):
