@@ -113,6 +113,10 @@ class BatchedOvercookedEnv(object):
         return ctypes.byref(self._rs) if self._rs is not None else None
 
     def _stream(self):
+        # the C ABI launches on the calling thread's current device: make a mismatch loud instead of a fault
+        if torch.cuda.current_device() != self.device.index:
+            raise RuntimeError("this environment lives on %s but the current CUDA device is cuda:%d; wrap the call in "
+                               "torch.cuda.device(env.device) (one process per GPU sets it once)" % (self.device, torch.cuda.current_device()))
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def reset(self, mask=None):
