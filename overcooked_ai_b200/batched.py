@@ -102,7 +102,8 @@ class BatchedOvercookedEnv(object):
         self._lut = None
         self._segments = None
         self._p_tables, self._p_starts, self._p_state = self.tables.data_ptr(), self.start_records.data_ptr(), self.state.data_ptr()
-        self.reset()
+        with torch.cuda.device(self.device):
+            self.reset()
 
     # ---------------------------------------------------------------------------------------------
     def _flags(self):
