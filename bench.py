@@ -442,6 +442,15 @@ def main():
             "avg_launch_us": avg_launch_s * 1e6, "traffic": None,
             "note": "achieved = env_steps_per_launch x %d B (SURVEY 8d) / avg launch duration; avg launch duration = CUDA-event time of the timed region / launches (includes launch gaps)" % bytes_per,
         }
+        # secondary bound: warp-instruction issue.  Instructions per warp-transition come from the
+        # ncu captures under profiles/ (421 for K5, 445 for K1 on cramped_room); peak = SMs x 4 schedulers x SM clock.
+        wi = {16: (421, 445)}.get(S)
+        if wi and clocks and clocks.get("sm_mhz"):
+            per_wt = wi[0] if fused else wi[1]
+            issued = per_launch_env_steps / 32.0 * per_wt / avg_launch_s
+            peak_issue = 148 * 4 * clocks["sm_mhz"] * 1e6
+            r["issue_bound"] = {"warp_instructions_per_warp_transition": per_wt, "source": "profiles/r1_final_kernels_ncu_full.md",
+                                "achieved_warp_inst_per_s": issued, "peak_warp_inst_per_s": peak_issue, "frac": issued / peak_issue}
         if fused:
             r["streamed_GBps"] = per_launch_env_steps * 32 / avg_launch_s / 1e9
             r["note"] += "; the fused kernel keeps the record on chip between transitions, so only actions + outputs (32 B per env-step, streamed_GBps) cross HBM: a frac near or above 1 is traffic avoided by fusion, not bandwidth"
