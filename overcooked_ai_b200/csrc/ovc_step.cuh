@@ -213,6 +213,14 @@ __device__ __forceinline__ void step_core(R &r, const TB &layouts,
     int shaped[2] = {0, 0};
     unsigned ev[2] = {0u, 0u};
 
+    // terrain of each player's move target, fetched early (see resolve_movement below)
+    unsigned move_cell[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const int a = i == 0 ? a0 : a1;
+        move_cell[i] = L.u16(OVC_OFF(cell) + 2 * ((int)((p[i] & 0xFF) + dir_delta(a & 3)) & 0xFF));
+    }
+
     // ---- resolve_interacts :1446-1577: player 0 then player 1 on the same live record.  The body is
     //      emitted once and run as a loop of up to two trips: trip 0 handles, per environment, the first
     //      interacting player (player 0 if it interacts, else player 1); trip 1 handles player 1 where
@@ -236,7 +244,8 @@ __device__ __forceinline__ void step_core(R &r, const TB &layouts,
     }
 
     // ---- resolve_movement :1644-1727 from the pre-step positions; a blocked or collided player
-    //      still turns (quirk Q8) ----
+    //      still turns (quirk Q8).  (The two terrain lookups were issued before the interact section:
+    //      positions do not change there, and the loads then overlap the interact latency.) ----
     int npos[2];
 #pragma unroll
     for (int i = 0; i < 2; i++) {
@@ -244,8 +253,7 @@ __device__ __forceinline__ void step_core(R &r, const TB &layouts,
         npos[i] = pos;
         const int a = i == 0 ? a0 : a1;
         if (a < 4) {
-            const int tpos = (pos + dir_delta(a)) & 0xFF;
-            if ((L.u16(OVC_OFF(cell) + 2 * tpos) & 7) == OVC_T_FLOOR) npos[i] = tpos;
+            if ((move_cell[i] & 7) == OVC_T_FLOOR) npos[i] = (pos + dir_delta(a)) & 0xFF;
             p[i] = (p[i] & ~0x300u) | ((unsigned)a << 8);
         }
     }
