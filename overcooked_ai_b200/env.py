@@ -123,3 +123,47 @@ class OvercookedEnv(object):
         successor_state = self.state
         self.reset(False)
         return successor_state, done
+
+
+class Overcooked(object):
+    """The reference's gym wrapper (overcooked_env.py:782-909) over the drop-in env, single environment:
+    the primary agent's index is redrawn with ``np.random.choice([0, 1])`` at every reset exactly as the
+    reference does (so a seeded run assigns the same indices), actions arrive as (primary, other) action
+    INDICES and observations leave as (primary, other).  No gymnasium dependency: ``observation_space`` /
+    ``action_space`` are plain descriptions.  For many environments use vecenv.BatchedOvercookedGym."""
+
+    env_name = "Overcooked-v0"
+
+    def __init__(self, base_env, featurize_fn, baselines_reproducible=False):
+        if baselines_reproducible:
+            np.random.seed(0)  # overcooked_env.py:821-832
+        self.base_env = base_env
+        self.featurize_fn = featurize_fn
+        dummy = self.featurize_fn(self.base_env.mdp.get_standard_start_state())[0]
+        self.observation_space = {"shape": tuple(dummy.shape), "low": 0.0, "high": float("inf"), "dtype": np.float32}
+        self.action_space = {"n": 6}
+        self.reset()
+
+    def _both(self, state):
+        ob_p0, ob_p1 = self.featurize_fn(state)
+        return (ob_p0, ob_p1) if self.agent_idx == 0 else (ob_p1, ob_p0)
+
+    def step(self, action):
+        assert all(isinstance(a, (int, np.integer)) and 0 <= a < 6 for a in action), "%r (%s) invalid" % (action, type(action))
+        from overcooked_ai_b200.actions import Action
+
+        agent_action, other_agent_action = [Action.INDEX_TO_ACTION[a] for a in action]
+        joint_action = (agent_action, other_agent_action) if self.agent_idx == 0 else (other_agent_action, agent_action)
+        next_state, reward, done, env_info = self.base_env.step(joint_action)
+        env_info["policy_agent_idx"] = self.agent_idx
+        if "episode" in env_info:
+            env_info["episode"]["policy_agent_idx"] = self.agent_idx
+        obs = {"both_agent_obs": self._both(next_state), "overcooked_state": next_state, "other_agent_env_idx": 1 - self.agent_idx}
+        return obs, reward, done, env_info
+
+    def reset(self):
+        self.base_env.reset()
+        self.mdp = self.base_env.mdp
+        self.agent_idx = np.random.choice([0, 1])
+        return {"both_agent_obs": self._both(self.base_env.state), "overcooked_state": self.base_env.state,
+                "other_agent_env_idx": 1 - self.agent_idx}

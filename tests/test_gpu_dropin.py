@@ -167,3 +167,30 @@ def test_potential_function_and_display_phi():
     phi0 = env.potential()
     s1, r, done, info = env.step((n, interact), display_phi=True)
     assert info["phi_s"] == phi0 and info["phi_s_prime"] == env.potential()
+
+
+def test_gym_wrapper_single_env():
+    """overcooked_env.py:782-909 through the drop-in classes: seeded primary-agent draw, (primary, other) ordering."""
+    from overcooked_ai_b200.env import Overcooked
+
+    mdp = OvercookedGridworld.from_layout_name("cramped_room")
+    base = OvercookedEnv.from_mdp(mdp, horizon=6, info_level=0)
+    np.random.seed(3)
+    gym = Overcooked(base, base.lossless_state_encoding_mdp)
+    np.random.seed(3)
+    expect_idx = [int(np.random.choice([0, 1])) for _ in range(3)]
+    np.random.seed(3)
+    for k in range(3):
+        obs = gym.reset()
+        assert gym.agent_idx == expect_idx[k] and obs["other_agent_env_idx"] == 1 - gym.agent_idx
+        p0, p1 = base.lossless_state_encoding_mdp(base.state)
+        want = (p0, p1) if gym.agent_idx == 0 else (p1, p0)
+        assert np.array_equal(obs["both_agent_obs"][0], want[0]) and np.array_equal(obs["both_agent_obs"][1], want[1])
+        # the primary agent walks west, the other stays: it must be player `agent_idx` that moved
+        before = base.state.players[gym.agent_idx].position
+        obs, r, done, info = gym.step((3, 4))
+        moved = base.state.players[gym.agent_idx]
+        assert moved.orientation == Direction.WEST and info["policy_agent_idx"] == gym.agent_idx
+        assert base.state.players[1 - gym.agent_idx].orientation == Direction.NORTH
+    with pytest.raises(AssertionError):
+        gym.step((7, 0))
