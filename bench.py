@@ -210,6 +210,7 @@ def run_policy_pipeline(args, rank, world, local):
     if args.envs:
         n_envs = args.envs
     T = horizon
+    torch.backends.cudnn.benchmark = True
     env = BatchedOvercookedEnv(layouts, n_envs, horizon=horizon, device=dev, auto_reset=True)
     sp = SelfPlayRollout(env, use_graph=True)
 
@@ -244,8 +245,8 @@ def run_policy_pipeline(args, rank, world, local):
     line = {
         "metric": METRIC, "value": tot_steps / (max_ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int32 env / fp32 observations / bf16-autocast policy", "data": "synthetic",
-        "config": {"workload": "config5: %s, %d envs/GPU, self-play: K2 lossless encode fp32 -> torch CNN (RllibPPOModel-shaped, random init, shared) -> multinomial -> K1 step, whole transition in one CUDA graph"
+        "dtype": "int32 env / bf16 observations / bf16-autocast policy", "data": "synthetic",
+        "config": {"workload": "config5: %s, %d envs/GPU, self-play: K2 lossless encode bf16 -> torch CNN (RllibPPOModel-shaped, random init, shared) -> multinomial -> K1 step, whole transition in one CUDA graph"
                                % ("+".join(layouts), n_envs), "state_words": S, "parallelism": "env-index sharding x%d" % world},
         "clocks": clocks, "gpu_launches": 2 * T * args.steps,
         "env_only": {"ms_per_400_transitions": max_ms_env, "env_steps_per_s_per_gpu": n_envs * T / (max_ms_env * 1e-3),

@@ -46,7 +46,10 @@ class RllibShapedCNN(nn.Module):
 class SelfPlayRollout(object):
     """Policy-in-the-loop rollout: both agents of every environment act from the same network."""
 
-    def __init__(self, env, model=None, autocast_dtype=torch.bfloat16, use_graph=True, reward_shaping_factor=1.0):
+    def __init__(self, env, model=None, autocast_dtype=torch.bfloat16, use_graph=True, reward_shaping_factor=1.0,
+                 obs_dtype=None):
+        """obs_dtype: element type K2 writes (default: bfloat16 when the policy runs under bf16 autocast — the plane
+        values are exact in bf16 and the conversion pass disappears — else float32)."""
         assert len({(l.width, l.height) for l in env.layouts}) == 1, "one grid shape per rollout (group envs by layout)"
         self.env = env
         l = env.layouts[0]
@@ -56,7 +59,9 @@ class SelfPlayRollout(object):
         self.autocast_dtype = autocast_dtype
         self.factor = float(reward_shaping_factor)
         N = env.n_envs
-        self.obs = torch.empty((N, 2, self.W, self.H, 26), dtype=torch.float32, device=dev)
+        if obs_dtype is None:
+            obs_dtype = torch.bfloat16 if autocast_dtype == torch.bfloat16 else torch.float32
+        self.obs = torch.empty((N, 2, self.W, self.H, 26), dtype=obs_dtype, device=dev)
         self.actions = torch.zeros((N, 2), dtype=torch.int32, device=dev)
         self.ret_sparse = torch.zeros(N, dtype=torch.int64, device=dev)      # running episode return (sparse)
         self.ret_mixed = torch.zeros(N, dtype=torch.float32, device=dev)    # sparse + factor * shaped (rllib.py:328-329)
