@@ -241,7 +241,7 @@ def run_policy_pipeline(args, rank, world, local):
         return
     S = env.state_words
     l = env.layouts[0]
-    enc_bytes = 4 * S + 2 * l.width * l.height * 26 * 4
+    enc_bytes = 4 * S + 2 * l.width * l.height * 26 * sp.obs.element_size()
     line = {
         "metric": METRIC, "value": tot_steps / (max_ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
