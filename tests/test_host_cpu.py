@@ -197,3 +197,28 @@ def test_wire_formats_round_trip_with_reference_dicts():
     assert tr["ep_returns"].tolist() == [180] * 5 and tr["ep_lengths"].tolist() == [400] * 5
     assert tr["ep_states"][0][0] == cl.get_standard_start_state() and tr["ep_dones"][2][-1] is True
     assert tr["ep_actions"][0][0] == tuple(Action.INDEX_TO_ACTION[a] for a in d["actions"][0, 0])
+
+
+def test_event_code_table_covers_every_mask_the_engine_can_produce():
+    """wire.EVENT_CODE_TABLE (32 codes of the packed result format) contains every per-agent event mask that
+    occurs in the reference-generated fixtures, once each — so decoding the 5-bit codes is lossless."""
+    import glob
+
+    from oracle import cpu
+    from overcooked_ai_b200 import wire
+
+    table = wire.EVENT_CODE_TABLE.astype(np.int64)
+    assert len(set(table.tolist())) == 32 and table[0] == 0
+    seen = set()
+    for path in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "trace_*.npz"))):
+        d = np.load(path)
+        import json as _json
+
+        cl = L.compile_layout(str(d["layout"]), **(_json.loads(str(d["params"])) if "params" in d else {}))
+        tab, starts, S = L.build_tables([cl])
+        st = np.ascontiguousarray(d["states"][:, :-1].reshape(-1, S)).copy()
+        a = np.ascontiguousarray(d["actions"].reshape(-1, 2))
+        _, _, _, ev = cpu.step(tab, starts, st, a, horizon=0)
+        seen |= set(np.unique(ev.astype(np.int64) & 0x1FFFFFFF).tolist())
+    assert seen <= set(table.tolist()), sorted(seen - set(table.tolist()))
+    assert len(seen) >= 26
