@@ -38,6 +38,7 @@ struct EncodeArgs {
     int S, W, H, horizon;
     int E;          // environments per tile
     int obs_elems;  // 2*W*H*26
+    unsigned inv_items, inv_h;  // ceil(2^32 / d): n / d == __umulhi(n, inv) exactly while n * d < 2^32
 };
 
 // writes value v of plane c at cell (x,y) into BOTH players' views of one environment
@@ -96,16 +97,17 @@ __global__ void __launch_bounds__(256) encode_kernel(const EncodeArgs a) {
 
     // ---- phase B: scatter.  Work items per environment: W*H terrain cells, 2 players, n_slots
     //      object cells (an upper bound S-4 is used so the item count is layout independent).
-    //      (A division-free variant with a power-of-two lane group per environment measured slower:
-    //      the idle lanes cost more than the two integer divisions.) ----
+    //      The two integer divisions per item (item -> environment, cell -> column) are multiplications by
+    //      host-computed reciprocals.  (A variant with a power-of-two lane group per environment measured
+    //      slower: its idle lanes cost more than the divisions did.) ----
     const int items_per_env = WH + 2 + (a.S - 4);
     for (int it = threadIdx.x; it < ne * items_per_env; it += blockDim.x) {
-        const int el = it / items_per_env, k = it % items_per_env;
+        const int el = (int)__umulhi((unsigned)it, a.inv_items), k = it - el * items_per_env;
         const int32_t *__restrict__ rec = a.state + (env0 + el) * a.S;
         const ovc_layout_t *__restrict__ L = a.layouts + (__ldg(rec + 3) & 0xFF);
         T *obs = buf + (size_t)el * a.obs_elems;
         if (k < WH) {  // static terrain planes :2449-2465 and the urgency plane :2446-2447
-            const int x = k / a.H, y = k % a.H;
+            const int x = (int)__umulhi((unsigned)k, a.inv_h), y = k - x * a.H;
             const int terr = __ldg(&L->cell[(y << 4) | x]) & 7;
             // terrain code -> plane: X 11, O 12, T 13, D 14, P 10, S 15 (0 = none)
             const int plane = (int)((0x0F0A0E0D0C0B00ull >> (terr * 8)) & 0xFF);
@@ -170,6 +172,8 @@ static int encode_lossless_impl(const ovc_layout_t *layouts, const int32_t *stat
     a.layouts = layouts, a.state = state, a.view_swap = view_swap, a.out = out, a.n_envs = n_envs;
     a.S = S, a.W = W, a.H = H, a.horizon = horizon;
     a.obs_elems = 2 * W * H * N_PLANES;
+    a.inv_items = (unsigned)((0x100000000ull + (unsigned)(W * H + 2 + (S - 4)) - 1) / (unsigned)(W * H + 2 + (S - 4)));
+    a.inv_h = (unsigned)((0x100000000ull + (unsigned)H - 1) / (unsigned)H);
     const int obs_bytes = a.obs_elems * esize;
     // Tile buffer size.  Measured on B200 (tools/kbench.py, 262 144 envs, fp32): 16 KB 85 %, 24 KB 105 %,
     // 32 KB 104 %, 48 KB 82 %, 64 KB 79 %, 96 KB 61 % of the measured HBM copy peak — small tiles keep
