@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define OVC_ABI_VERSION 2
+#define OVC_ABI_VERSION 3
 
 /* ---- action indices: Action.INDEX_TO_ACTION, actions.py:47-57 ---- */
 #define OVC_A_NORTH 0
@@ -185,12 +185,18 @@ typedef struct ovc_cost_lut_entry {
  * cooking?}.  "u < p" is `draw < threshold` with threshold = p * 2^32; randint(lo, hi) is lo + mulhi(draw, hi-lo);
  * the object is a dish / onion / soup with probability 0.2 / 0.6 / 0.2 (:1351-1353), a held soup is finished,
  * a pot soup has n in 1..3 onions then m in 0..3-n tomatoes and is cooking (tick 0) or idle.
+ * Variable MDP (OvercookedEnv.reset(regen_mdp=True) with a generator over num_mdp > 1 layouts, overcooked_env.py:
+ * 288-302): with `random_layout` every (auto-)reset first redraws the environment's layout uniformly from the
+ * n_layouts of the table, id = mulhi(block 2 word 1, n_layouts) of the NEW episode, and then builds the start
+ * state (standard or random, as the other fields say) on that layout.
  * Passed by HOST pointer (NULL = standard start states). */
 typedef struct ovc_random_start {
     uint64_t seed;
     uint32_t obj_threshold;   /* rnd_obj_prob_thresh * 2^32 (0: no random objects, as :1325-1326) */
     int32_t random_start_pos; /* non-zero: a uniformly drawn ordered pair of distinct floor cells (:1311-1315) */
-} ovc_random_start_t;
+    int32_t random_layout;    /* non-zero: redraw the layout id at every reset (variable MDP) */
+    int32_t reserved;
+} ovc_random_start_t; /* 24 bytes */
 
 /* ---- error codes ---- */
 #define OVC_OK 0

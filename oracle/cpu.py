@@ -46,12 +46,13 @@ def _i32(a):
 
 class RandomStart(ctypes.Structure):
     """ovc_random_start_t"""
-    _fields_ = [("seed", ctypes.c_uint64), ("obj_threshold", ctypes.c_uint32), ("random_start_pos", ctypes.c_int32)]
+    _fields_ = [("seed", ctypes.c_uint64), ("obj_threshold", ctypes.c_uint32), ("random_start_pos", ctypes.c_int32),
+                ("random_layout", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
-def random_start(seed, rnd_obj_prob_thresh=0.0, random_start_pos=False):
+def random_start(seed, rnd_obj_prob_thresh=0.0, random_start_pos=False, random_layout=False):
     thr = min(int(rnd_obj_prob_thresh * 4294967296.0), 0xFFFFFFFF)
-    return RandomStart(int(seed) & 0xFFFFFFFFFFFFFFFF, thr, int(bool(random_start_pos)))
+    return RandomStart(int(seed) & 0xFFFFFFFFFFFFFFFF, thr, int(bool(random_start_pos)), int(bool(random_layout)), 0)
 
 
 def _rs(rs):

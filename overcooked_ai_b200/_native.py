@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libovc_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 F_AUTO_RESET = 1
 F_PDL = 2
 F_ACT_U8 = 4
@@ -24,7 +24,8 @@ DT_F32, DT_U8, DT_I32, DT_BF16 = 0, 1, 2, 3
 
 class RandomStart(ctypes.Structure):
     """ovc_random_start_t (include/ovc_b200.h): random start states, passed by host pointer."""
-    _fields_ = [("seed", ctypes.c_uint64), ("obj_threshold", ctypes.c_uint32), ("random_start_pos", ctypes.c_int32)]
+    _fields_ = [("seed", ctypes.c_uint64), ("obj_threshold", ctypes.c_uint32), ("random_start_pos", ctypes.c_int32),
+                ("random_layout", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 _lib = None

@@ -44,7 +44,7 @@ def _as_layouts(layouts, mdp_params):
 class BatchedOvercookedEnv(object):
     def __init__(self, layouts, n_envs, horizon=400, device="cuda", auto_reset=False, state_words=None,
                  io=_native.IO_DEFAULT, env_layout=None, mdp_params=None, pdl=True,
-                 random_start_pos=False, rnd_obj_prob_thresh=0.0, seed=0):
+                 random_start_pos=False, rnd_obj_prob_thresh=0.0, seed=0, random_layout=False):
         """
         layouts      layout name / CompiledLayout / OvercookedGridworld, or a list of them (mixed batch)
         n_envs       number of environments on THIS device
@@ -58,6 +58,11 @@ class BatchedOvercookedEnv(object):
                      start every episode from the reference's randomised start states
                      (get_random_start_state_fn, overcooked_mdp.py:1307-1369) instead of the standard one;
                      drawn on the device with a counter-based generator (see ovc_random_start_t)
+        random_layout
+                     variable MDP — OvercookedEnv(mdp_generator_fn, num_mdp > 1) whose reset draws a new MDP
+                     (overcooked_env.py:288-302): every (auto-)reset redraws the environment's layout uniformly
+                     from ``layouts`` (e.g. a pool from layout_generator.generate_layout_pool); ``layout_ids()``
+                     gives the current assignment, ``env_layout`` only the initial one
         """
         self._lib = _native.lib()
         if not torch.cuda.is_available():
@@ -96,9 +101,11 @@ class BatchedOvercookedEnv(object):
             self.done = torch.zeros(self.n_envs, dtype=torch.int32, device=self.device)
             self.events = torch.zeros((self.n_envs, 2), dtype=torch.int32, device=self.device)
         self._rs = None
-        if random_start_pos or rnd_obj_prob_thresh > 0:
+        self.random_layout = bool(random_layout)
+        if random_start_pos or rnd_obj_prob_thresh > 0 or random_layout:
             thr = min(int(float(rnd_obj_prob_thresh) * 4294967296.0), 0xFFFFFFFF)
-            self._rs = _native.RandomStart(int(seed) & 0xFFFFFFFFFFFFFFFF, thr, int(bool(random_start_pos)))
+            self._rs = _native.RandomStart(int(seed) & 0xFFFFFFFFFFFFFFFF, thr, int(bool(random_start_pos)),
+                                           int(self.random_layout), 0)
         self._lut = None
         self._segments = None
         self._p_tables, self._p_starts, self._p_state = self.tables.data_ptr(), self.start_records.data_ptr(), self.state.data_ptr()
@@ -143,6 +150,10 @@ class BatchedOvercookedEnv(object):
         assert actions.dtype == torch.int32 and actions.is_cuda and actions.is_contiguous()
         assert actions.numel() == 2 * self.n_envs
         sparse, shaped, done, events = (self.sparse, self.shaped, self.done, self.events) if out is None else out
+        if out is not None:
+            for o, n in zip(out, (1, 2, 1, 2)):
+                assert o.dtype == torch.int32 and o.is_cuda and o.is_contiguous() and o.numel() == n * self.n_envs, \
+                    "step(out=...) takes int32 CUDA tensors (sparse[N], shaped[N,2], done[N], events[N,2])"
         _native.check(self._lib.ovc_step(
             self._p_tables, self.n_layouts, self._p_starts, self._p_state,
             actions.data_ptr(), sparse.data_ptr(), shaped.data_ptr(), done.data_ptr(),
@@ -212,6 +223,13 @@ class BatchedOvercookedEnv(object):
             self._segments = [(cuts[i], cuts[i + 1], int(el[cuts[i]])) for i in range(len(cuts) - 1) if cuts[i] < cuts[i + 1]]
         return self._segments
 
+    def layout_ids(self):
+        """int32 [N]: the layout each environment is on NOW (the id lives in word 3 of its record)."""
+        return (self.state[:, 3] & 0xFF).to(torch.int32)
+
+    def _layout_ids_host(self):
+        return self.layout_ids().cpu().numpy() if self.random_layout else self.env_layout_host
+
     def obs_shape(self, layout_index=0):
         l = self.layouts[layout_index]
         return (l.width, l.height, 26)
@@ -220,7 +238,7 @@ class BatchedOvercookedEnv(object):
         """lossless_state_encoding (overcooked_mdp.py:2385-2561) of every environment, both players:
         tensor [N, 2, W, H, 26] (index order [x][y][channel], as the reference) when all layouts share
         one grid shape, else a list of such tensors, one per layout segment.  dtype float32 (what the
-        reference's RLlib consumer casts to), uint8 or int32.  ``view_swap`` (int32 CUDA tensor [N]):
+        reference's RLlib consumer casts to), bfloat16, uint8 or int32.  ``view_swap`` (int32 CUDA tensor [N]):
         where non-zero, ``out[env, 0]`` is player 1's view (primary-agent-first order of the gym wrapper)."""
         if view_swap is not None:
             assert view_swap.dtype == torch.int32 and view_swap.is_cuda and view_swap.is_contiguous() and view_swap.numel() == self.n_envs
@@ -228,6 +246,7 @@ class BatchedOvercookedEnv(object):
         if len(shapes) == 1:
             runs = [(0, self.n_envs, 0)]
         else:
+            assert not self.random_layout, "random_layout needs layouts of one grid shape (pad them, LayoutGenerator does)"
             runs = self.segments()
         outs = []
         for k, (b, e, li) in enumerate(runs):
@@ -236,6 +255,7 @@ class BatchedOvercookedEnv(object):
             if o is None:
                 o = torch.empty((e - b, 2, W, H, 26), dtype=dtype, device=self.device)
             assert o.is_cuda and o.is_contiguous() and o.numel() == (e - b) * 2 * W * H * 26
+            assert o.dtype in _TORCH_DT, "lossless_state_encoding writes float32, bfloat16, uint8 or int32, not %s" % o.dtype
             _native.check(self._lib.ovc_encode_lossless(
                 self.tables.data_ptr(), self.n_layouts, self.state.data_ptr() + 4 * self.state_words * b,
                 0 if view_swap is None else view_swap.data_ptr() + 4 * b, o.data_ptr(),
@@ -255,6 +275,8 @@ class BatchedOvercookedEnv(object):
         """featurize_state (overcooked_mdp.py:2579-2898; default NO_COUNTERS_PARAMS planner):
         float32 [N, 2, 2*(10*num_pots+28)]."""
         F = 2 * (10 * num_pots + 28)
+        if view_swap is not None:
+            assert view_swap.dtype == torch.int32 and view_swap.is_cuda and view_swap.is_contiguous() and view_swap.numel() == self.n_envs
         if out is None:
             out = torch.empty((self.n_envs, 2, F), dtype=torch.float32, device=self.device)
         assert out.dtype == torch.float32 and out.is_cuda and out.is_contiguous() and out.numel() == self.n_envs * 2 * F
@@ -283,25 +305,26 @@ class BatchedOvercookedEnv(object):
         return out
 
     # ---------------------------------------------------------------------------------------------
-    def sparse_by_agent(self, events):
-        """Per-agent delivery reward int32 [..., N, 2] from the event words (bits 25-28 carry the delivered recipe)."""
+    def sparse_by_agent(self, events, layout_ids=None):
+        """Per-agent delivery reward int32 [..., N, 2] from the event words (bits 25-28 carry the delivered recipe).
+        ``layout_ids`` (int [N]): the layouts the events were produced on; default the initial assignment — with
+        ``random_layout`` pass ``layout_ids()`` taken BEFORE the step (a finished environment has moved on)."""
         val = torch.from_numpy(np.stack([l.deliver_value for l in self.layouts]).astype(np.int32)).to(events.device)
         rec = (events >> L.EV_RECIPE_SHIFT) & 15
-        lid = self.env_layout.long().view(*([1] * (events.dim() - 2)), -1, 1).expand_as(rec)
+        ids = self.env_layout if layout_ids is None else layout_ids
+        lid = ids.long().view(*([1] * (events.dim() - 2)), -1, 1).expand_as(rec)
         return val[lid, rec.long()] * ((events >> 15) & 1)
 
     def get_states(self, indices=None):
         """Unpack records into OvercookedState objects (host; for debugging / the drop-in adapters)."""
         recs = self.state.cpu().numpy()
         idx = range(self.n_envs) if indices is None else indices
-        return [L.unpack_state(self.layouts[self.env_layout_host[i]], recs[i]) for i in idx]
+        return [L.unpack_state(self.layouts[int(recs[i][3]) & 0xFF], recs[i]) for i in idx]
 
     def set_states(self, states, indices=None):
         idx = list(range(self.n_envs)) if indices is None else list(indices)
-        recs = np.stack([
-            L.pack_state(self.layouts[self.env_layout_host[i]], s, int(self.env_layout_host[i]), self.state_words)
-            for i, s in zip(idx, states)
-        ])
+        lids = self._layout_ids_host()
+        recs = np.stack([L.pack_state(self.layouts[lids[i]], s, int(lids[i]), self.state_words) for i, s in zip(idx, states)])
         self.state[torch.as_tensor(idx, device=self.device)] = torch.from_numpy(recs).to(self.device)
 
 
@@ -313,7 +336,9 @@ class HostRolloutPipeline(object):
     stream) and copies sparse / shaped / done / events device->host (second copy stream), the three
     stages overlapped across chunks with double buffering.  Returns pinned host tensors
     (sparse[T,N], shaped[T,N,2], done[T,N], events[T,N,2]).  Per environment-step this moves 8 bytes
-    host->device and 24 bytes device->host.
+    host->device and 24 bytes device->host (2 + 13 with ``narrow``, 2 + 6 with ``packed``).
+    ``run`` is stream ordered like every other call here: the returned tensors are complete once the current
+    stream has been synchronised (``torch.cuda.current_stream().synchronize()``), not when ``run`` returns.
     """
 
     def __init__(self, env, n_steps, chunk=50, narrow=False, packed=False):
@@ -391,10 +416,13 @@ class EpisodeStats(object):
         self.cumulative_shaped_rewards_by_agent = torch.zeros((N, 2), dtype=torch.int64, device=dev)
         self.ep_length = torch.zeros(N, dtype=torch.int32, device=dev)
         self._bits = torch.arange(25, device=dev, dtype=torch.int32)
+        self._lid = env.layout_ids()  # layouts of the running episodes (they change at resets with random_layout)
 
     def update(self, sparse, shaped, done, events):
-        """Feed the outputs of one step() (tensors [N], [N,2], [N], [N,2])."""
-        self.cumulative_sparse_rewards_by_agent += self.env.sparse_by_agent(events)
+        """Feed the outputs of one step() (tensors [N], [N,2], [N], [N,2]); call it after EVERY step."""
+        self.cumulative_sparse_rewards_by_agent += self.env.sparse_by_agent(events, self._lid)
+        if self.env.random_layout:
+            self._lid = self.env.layout_ids()
         self.cumulative_shaped_rewards_by_agent += shaped
         self.event_counts += (events.unsqueeze(-1) >> self._bits) & 1
         self.ep_length += 1

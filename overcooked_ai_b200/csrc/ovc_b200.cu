@@ -230,7 +230,7 @@ step_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
             const long long idx = (long long)t * a.n_envs + env;
             const int2 act = load_action(a, idx);
             StepOut o;
-            step_core<RS>(r, tb, a.start_records, S, act.x, act.y, a.horizon, a.flags, RS ? &a.rs : nullptr, env, o);
+            step_core<RS>(r, tb, a.start_records, S, act.x, act.y, a.horizon, a.flags, RS ? &a.rs : nullptr, env, a.n_layouts, o);
             write_outputs(a, idx, o);
         }
         return;
@@ -277,7 +277,7 @@ step_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
                 int2 nxt = act;
                 if (t + 1 < T) nxt = load_action(a, idx + a.n_envs);  // prefetch
                 StepOut o;
-                step_core<RS>(r, tb, a.start_records, S, act.x, act.y, a.horizon, a.flags, RS ? &a.rs : nullptr, env, o);
+                step_core<RS>(r, tb, a.start_records, S, act.x, act.y, a.horizon, a.flags, RS ? &a.rs : nullptr, env, a.n_layouts, o);
                 write_outputs(a, idx, o);
                 act = nxt;
             }
@@ -321,10 +321,12 @@ __global__ void reset_random_kernel(const ovc_layout_t *__restrict__ layouts, in
     int32_t *rec = state + env * S;
     const unsigned old = (unsigned)rec[3];
     int lid = env_layout ? env_layout[env] : (int)(old & 0xFF);
+    const unsigned episode = ((old >> 16) + 1u) & 0xFFFFu;
+    if (rs.random_layout) lid = random_layout_id(rs, (uint64_t)env, episode, n_layouts);  // variable MDP
     if (lid < 0 || lid >= n_layouts) lid = 0;
     const ovc_layout_t *L = layouts + lid;
     random_start_record([&](int w, int32_t v) { rec[w] = v; }, S, start_records + (size_t)lid * S, L->cook_time, L->free_pos,
-                        L->n_free, L->n_pots, lid, rs, (uint64_t)env, ((old >> 16) + 1u) & 0xFFFFu);
+                        L->n_free, L->n_pots, lid, rs, (uint64_t)env, episode);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -44,6 +44,12 @@ __host__ __device__ __forceinline__ uint32_t random_held(const int32_t *cook_tim
     return soup_code(n, m, (uint32_t)cook_time[n * 4 + m] + 1u);  // finished soup: tick == cook time (:565-569)
 }
 
+// Variable MDP: the layout of the episode that starts now (block 2, word 1 of that episode's draws).
+__host__ __device__ __forceinline__ int random_layout_id(const ovc_random_start_t &rs, uint64_t env, uint32_t episode, int n_layouts) {
+    const Philox4 Cc = philox4x32_10(rs.seed, (uint32_t)env, (uint32_t)(env >> 32), episode, 2);
+    return (int)mulhi32(Cc.v[1], (uint32_t)n_layouts);
+}
+
 // Writes one freshly drawn start record (S words).  `start_rec` supplies the fixed start positions,
 // `cook_time` / `free_pos` / `n_free` / `n_pots` come from the layout; `episode` is the NEW episode counter.
 template <class Store>

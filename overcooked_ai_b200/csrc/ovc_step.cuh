@@ -178,7 +178,7 @@ template <bool RS, class R, class TB>
 __device__ __forceinline__ void step_core(R &r, const TB &layouts,
                                           const int32_t *__restrict__ start_records, int S, int a0, int a1,
                                           int horizon, int flags, const ovc_random_start_t *rs, long long env_index,
-                                          StepOut &o) {
+                                          int n_layouts, StepOut &o) {
     int4 h = r.ld4(0);
     const int t = h.x;
     if (horizon > 0 && t >= horizon) {  // stepping a finished env: untouched + flagged (overcooked_env.py:255)
@@ -294,10 +294,14 @@ __device__ __forceinline__ void step_core(R &r, const TB &layouts,
     if (o.done && (flags & OVC_F_AUTO_RESET)) {
         const int32_t *__restrict__ start = start_records + (size_t)(misc & 0xFF) * S;
         if (RS && rs) {
-            random_start_record([&](int w, int32_t v) { r.stw(w, v); }, S, start,
-                                reinterpret_cast<const int32_t *>(L.ptr(OVC_OFF(cook_time))),
-                                reinterpret_cast<const uint8_t *>(L.ptr(OVC_OFF(free_pos))), L.i32(OVC_OFF(n_free)), n_pots,
-                                (int)(misc & 0xFF), *rs, (uint64_t)env_index, ((misc >> 16) + 1u) & 0xFFFFu);
+            const unsigned episode = ((misc >> 16) + 1u) & 0xFFFFu;
+            int lid = (int)(misc & 0xFF);
+            if (rs->random_layout) lid = random_layout_id(*rs, (uint64_t)env_index, episode, n_layouts);  // variable MDP
+            const TB Ln = layouts.at((unsigned)lid);
+            random_start_record([&](int w, int32_t v) { r.stw(w, v); }, S, start_records + (size_t)lid * S,
+                                reinterpret_cast<const int32_t *>(Ln.ptr(OVC_OFF(cook_time))),
+                                reinterpret_cast<const uint8_t *>(Ln.ptr(OVC_OFF(free_pos))), Ln.i32(OVC_OFF(n_free)),
+                                Ln.i32(OVC_OFF(n_pots)), lid, *rs, (uint64_t)env_index, episode);
         } else {
             const int4 *__restrict__ src = reinterpret_cast<const int4 *>(start);
 #pragma unroll 4

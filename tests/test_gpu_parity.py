@@ -9,7 +9,7 @@ from helpers import EVENT_MASK, GOLD, TRACE_FILES, TRACE_IDS, Trace, lut_bytes
 from oracle import cpu
 from overcooked_ai_b200 import _native
 from overcooked_ai_b200 import layout as L
-from overcooked_ai_b200.batched import BatchedOvercookedEnv
+from overcooked_ai_b200.batched import BatchedOvercookedEnv, EpisodeStats
 
 pytestmark = pytest.mark.gpu
 
@@ -410,6 +410,67 @@ def test_random_start_states_vs_oracle_mirror(random_pos, thresh):
     cpu.reset_random(env._tab_host, env._starts_host, ref, rs, mask=mask)
     assert np.array_equal(_np(env.state), ref)
     assert len(np.unique(first[:, 1:3], axis=0)) > 10
+
+
+@pytest.mark.parametrize("pool_size,random_pos,thresh", [(5, False, 0.0), (12, True, 0.4)])
+def test_variable_mdp_layout_redraw_vs_oracle_mirror(pool_size, random_pos, thresh):
+    """Variable MDP (OvercookedEnv over a LayoutGenerator, overcooked_env.py:288-302): reset and the auto-reset
+    inside step / rollout redraw each environment's layout from a pool of generated layouts; bit-exact against
+    the CPU mirror, on the shared-memory table path (5 layouts) and the global one (12), observations included."""
+    from overcooked_ai_b200 import layout_generator as LG
+
+    np.random.seed(pool_size)
+    params = {"inner_shape": (6, 5), "prop_empty": 0.6, "prop_feats": 0.3, "display": False, "feature_types": ["P", "D", "S", "O", "T"],
+              "start_all_orders": [{"ingredients": ["onion", "tomato"]}, {"ingredients": ["onion", "onion", "onion"]}]}
+    pool = LG.generate_layout_pool(pool_size, params, outer_shape=(7, 6), skip_unsupported=True)
+    assert len({tuple("".join(r) for r in l.terrain_mtx) for l in pool}) == pool_size
+    n, horizon, T = 3001, 12, 40
+    env = BatchedOvercookedEnv(pool, n, horizon=horizon, auto_reset=True, random_layout=True,
+                               random_start_pos=random_pos, rnd_obj_prob_thresh=thresh, seed=5)
+    rs = cpu.random_start(5, thresh, random_pos, random_layout=True)
+    ref = np.zeros((n, env.state_words), np.int32)
+    cpu.reset_random(env._tab_host, env._starts_host, ref, rs)
+    assert np.array_equal(_np(env.state), ref)
+    ids0 = ref[:, 3] & 0xFF
+    assert len(np.unique(ids0)) == pool_size and np.array_equal(_np(env.layout_ids()), ids0)
+    rng = np.random.RandomState(2)
+    acts = _random_actions(rng, T, n, 0.4)
+    want = cpu.rollout(env._tab_host, env._starts_host, ref, acts, horizon=horizon, flags=1, n_threads=4, rs=rs)
+    d = torch.from_numpy(acts).cuda()
+    stats = EpisodeStats(env)
+    cum = np.zeros((n, 2), np.int64)
+    val = np.stack([l.deliver_value for l in pool])
+    lids = ids0.copy()
+    for t in range(15):
+        got = env.step(d[t])
+        for g, w in zip(got, want):
+            assert np.array_equal(_np(g), w[t]), t
+        ev = want[3][t]
+        cum += val[lids[:, None], (ev >> 25) & 15] * ((ev >> 15) & 1)
+        fin = stats.update(*got)
+        if fin is not None:
+            assert np.array_equal(_np(fin["ep_sparse_r_by_agent"]), cum[_np(fin["env_index"])])
+            cum[:] = 0
+        lids = _np(env.layout_ids()).astype(np.int64)
+    got = env.rollout(d[15:].contiguous())
+    for g, w in zip(got, want):
+        assert np.array_equal(_np(g), w[15:])
+    assert np.array_equal(_np(env.state), ref)
+    assert ((ref[:, 3] >> 16) & 0xFFFF == 1 + T // horizon).all() and ((ref[:, 3] & 0xFF) != ids0).mean() > 0.5
+    # observations of the mixed batch
+    W, H = pool[0].width, pool[0].height
+    assert np.array_equal(_np(env.lossless_state_encoding(dtype=torch.int32)),
+                          cpu.encode_lossless(env._tab_host, ref, W, H, horizon))
+    assert np.array_equal(_np(env.featurize_state(2)).astype(np.float64), cpu.featurize(env._tab_host, lut_bytes(pool), ref, 2))
+    # masked reset: new layouts for exactly the masked environments
+    mask = (rng.rand(n) < 0.5).astype(np.int32)
+    env.reset(torch.from_numpy(mask).cuda())
+    cpu.reset_random(env._tab_host, env._starts_host, ref, rs, mask=mask)
+    assert np.array_equal(_np(env.state), ref)
+    # host view of single environments follows the current layout
+    s = env.get_states([0, 1, n - 1])
+    for k, i in enumerate([0, 1, n - 1]):
+        assert s[k].player_positions == tuple((int(ref[i, 1 + j]) & 15, (int(ref[i, 1 + j]) >> 4) & 15) for j in range(2))
 
 
 def test_more_than_eight_layouts_uses_global_tables():

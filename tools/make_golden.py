@@ -338,6 +338,46 @@ def gen_potential(ns):
     np.savez_compressed(os.path.join(GOLD, "potential.npz"), **out)
 
 
+# (name, mdp_gen_params, outer_shape, seeds): the cases of tests/golden/layout_generator.npz
+LAYOUTGEN_CASES = [
+    ("default", {"inner_shape": (5, 4), "prop_empty": 0.95, "prop_feats": 0.1,
+                 "start_all_orders": [{"ingredients": ["onion", "onion", "onion"]}], "recipe_values": [20],
+                 "recipe_times": [20], "display": False}, (5, 4), range(12)),
+    ("ref_test_5x4", {"inner_shape": (5, 4), "prop_empty": 0.8, "prop_feats": 0.2,
+                      "start_all_orders": [{"ingredients": ["onion", "onion", "onion"]}], "recipe_values": [20],
+                      "recipe_times": [20], "display": False}, (5, 4), range(12)),  # overcooked_test.py:1318-1331
+    ("ref_test_6x5_tomato", {"prop_feats": 0.9, "feature_types": ["P", "D", "S", "O", "T"], "prop_empty": 0.1,
+                             "inner_shape": (6, 5), "display": False,
+                             "start_all_orders": [{"ingredients": ["onion", "onion", "onion"]}]}, (6, 5), range(12)),
+    ("padded_7x5_in_10x7", {"inner_shape": (7, 5), "prop_empty": 0.6, "prop_feats": 0.4,
+                            "start_all_orders": [{"ingredients": ["onion", "onion", "onion"]}],
+                            "display": False}, (10, 7), range(12)),
+    ("padded_named", {"layout_name": "cramped_room"}, (8, 6), range(6)),
+]
+
+
+def gen_layoutgen(ns):
+    """LayoutGenerator outputs of the reference under np.random.seed(k): terrain rows + start cells."""
+    import copy
+    import importlib
+
+    lg = importlib.import_module("overcooked_ai_py.mdp.layout_generator")
+    out = {}
+    for name, params, outer, seeds in LAYOUTGEN_CASES:
+        rows, starts = [], []
+        for k in seeds:
+            np.random.seed(k)
+            gen = lg.LayoutGenerator(lg.MDPParamsGenerator.from_fixed_param(copy.deepcopy(params)), outer_shape=outer)
+            m = gen.generate_padded_mdp()
+            rows.append(["".join(r) for r in m.terrain_mtx])
+            starts.append(list(m.start_player_positions))
+        out[name + "__terrain"] = np.array(rows)
+        out[name + "__starts"] = np.array(starts, dtype=np.int16)
+        out[name + "__case"] = np.array(json.dumps({"params": params, "outer_shape": list(outer), "seeds": list(seeds)}))
+        print("layoutgen %s: %d layouts, e.g. %s" % (name, len(rows), rows[0]))
+    np.savez_compressed(os.path.join(GOLD, "layout_generator.npz"), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ns = refboot.boot()
@@ -356,6 +396,8 @@ def main():
         gen_human_2020(ns)
     if not only or "potential" in only:
         gen_potential(ns)
+    if not only or "layoutgen" in only:
+        gen_layoutgen(ns)
     print("done in %.1fs" % (time.time() - t0))
 
 
