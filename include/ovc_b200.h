@@ -229,6 +229,16 @@ typedef struct ovc_random_start {
  *                       (n_onion,n_tomato) = (0,1),(0,2),(0,3),(1,0),(1,1),(1,2),(2,0),(2,1),(3,0)  [index n_onion*4+n_tomato ascending]
  *                     The host expands codes back to the int32 masks with a 32-entry table (wire.decode_event_codes). */
 #define OVC_F_OUT_PACKED 16
+/*   OVC_F_OUT_CODES   (2 bytes per env-step) only `events` is written, as uint16[..] (`sparse`, `shaped`, `done` may be
+ *                     NULL): the OVC_F_OUT_PACKED word plus bit 12 / bit 13 = agent 0 / agent 1 received a shaped
+ *                     reward in this transition.  Nothing is lost: an agent's rewards are functions of its code,
+ *                     that bit and the layout — sparse = deliver_value[recipe of codes 23-31]; shaped =
+ *                     PLACEMENT_IN_POT_REW for codes 15-22, DISH_PICKUP_REWARD for code 6 and SOUP_PICKUP_REWARD for
+ *                     code 7 when the bit is set (a dish / soup taken from a COUNTER logs the same event without
+ *                     the reward, hence the bit).  ovc_expand_codes_host rebuilds the dense arrays on the host.
+ *   OVC_F_ACT_PACKED  `actions` is uint8[..]: agent 0's action index in bits 0-3, agent 1's in bits 4-7. */
+#define OVC_F_OUT_CODES 32
+#define OVC_F_ACT_PACKED 64
 /* bits 8-11 select the record I/O strategy of the step kernel (0 = library default):
  *   1 = 2-D tensor-map TMA tile with hardware swizzle, 2 = 1-D bulk TMA (linear tile),
  *   3 = direct vectorised global loads/stores (no staging).  All produce identical results. */
@@ -272,6 +282,60 @@ int ovc_rollout(const void *layouts, int n_layouts, const int32_t *start_records
                 const int32_t *actions, int32_t *sparse, int32_t *shaped, int32_t *done,
                 int32_t *events, int64_t n_envs, int n_steps, int state_words, int horizon,
                 int flags, const ovc_random_start_t *random_start, void *stream);
+
+/*
+ * Rollout with HOST buffers: the native driver of the end-to-end path (what the reference's callers see is host
+ * memory: actions come from a host policy, rewards / events go to a host learner, overcooked_env.py:449-462).
+ * A pipeline object owns three CUDA streams and a few events, nothing else: the caller provides the device staging
+ * buffers (two sets, for double buffering) and pinned host buffers.  ovc_pipeline_run cuts the n_steps transitions
+ * into chunks of `chunk` and, per chunk, copies the actions host->device, runs ovc_rollout on them and copies the
+ * outputs device->host, the three stages on their own streams and overlapped across chunks AND across successive
+ * calls.  Element formats follow `flags` exactly as in ovc_rollout (OVC_F_ACT_U8 / OVC_F_ACT_PACKED,
+ * OVC_F_OUT_NARROW / OVC_F_OUT_PACKED / OVC_F_OUT_CODES); output pointers a format does not use may be NULL.
+ */
+typedef struct ovc_pipeline ovc_pipeline_t;
+typedef struct ovc_pipeline_desc {
+    const void *layouts;          /* as ovc_rollout */
+    int32_t n_layouts;
+    int32_t state_words;
+    const int32_t *start_records;
+    int32_t *state;
+    int64_t n_envs;
+    int32_t horizon;
+    int32_t flags;
+    int32_t chunk;                /* transitions per chunk, >= 1 */
+    int32_t has_random_start;
+    ovc_random_start_t random_start;
+    void *d_actions[2];           /* device staging: chunk * n_envs joint actions each */
+    void *d_sparse[2];            /* device staging of the outputs, chunk * n_envs env-steps each */
+    void *d_shaped[2];
+    void *d_done[2];
+    void *d_events[2];
+} ovc_pipeline_desc_t;
+
+int ovc_pipeline_create(const ovc_pipeline_desc_t *desc, ovc_pipeline_t **out);
+/* Enqueues one pass over host buffers [n_steps][n_envs](..) and returns immediately (everything is asynchronous).
+ * The pipeline first waits for the work already enqueued on `stream` (the caller's stream).  `join` != 0: `stream`
+ * then waits for the pass, so later work on it sees the results (stream-ordered call); join == 0: successive passes
+ * overlap, *ticket (nullable) identifies this pass for ovc_pipeline_wait. */
+int ovc_pipeline_run(ovc_pipeline_t *p, const void *h_actions, void *h_sparse, void *h_shaped, void *h_done,
+                     void *h_events, int n_steps, void *stream, int join, int64_t *ticket);
+int ovc_pipeline_wait(ovc_pipeline_t *p, int64_t ticket); /* blocks the HOST until that pass's last copy has landed */
+int ovc_pipeline_join(ovc_pipeline_t *p, void *stream);   /* `stream` waits for everything enqueued so far */
+void ovc_pipeline_destroy(ovc_pipeline_t *p);
+
+/*
+ * HOST function (no GPU work): expands OVC_F_OUT_CODES words into dense arrays, multi-threaded.
+ *   codes        uint16[n_steps][n_envs] in host memory
+ *   env_layout   int32[n_envs] layout of each environment, or NULL (every environment on layout 0)
+ *   reward_tbl   int32[n_layouts][2][32]: [l][0][code] = delivery reward, [l][1][code] = shaped reward of the code
+ *   sparse       int16[n_steps][n_envs] or NULL     shaped  int8[n_steps][n_envs][2] or NULL
+ *   done         uint8[n_steps][n_envs] or NULL     events  int32[n_steps][n_envs][2] or NULL (masks, as ovc_step's)
+ *   n_threads    <= 0: all online cores
+ */
+int ovc_expand_codes_host(const uint16_t *codes, int64_t n_steps, int64_t n_envs, const int32_t *env_layout,
+                          const int32_t *reward_tbl, int n_layouts, int16_t *sparse, int8_t *shaped, uint8_t *done,
+                          int32_t *events, int n_threads);
 
 /*
  * OvercookedEnv.reset (overcooked_env.py:288-319) for the envs whose mask[i] != 0 (all if mask

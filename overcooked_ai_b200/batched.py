@@ -166,14 +166,18 @@ class BatchedOvercookedEnv(object):
             int(l.reward_shaping_params[k]) for k in ("PLACEMENT_IN_POT_REW", "DISH_PICKUP_REWARD", "SOUP_PICKUP_REWARD")) <= 127
             for l in self.layouts)
 
-    def alloc_rollout_out(self, T, narrow=False, pin=False, packed=False):
+    def alloc_rollout_out(self, T, narrow=False, pin=False, packed=False, codes=False):
         """Output tensors for rollout(): (sparse[T,N], shaped[T,N,2], done[T,N], events[T,N,2]); int32, or with
         ``narrow`` int16 / int8 / uint8 / int32 (13 bytes per env-step), or with ``packed`` (6 bytes per env-step)
         (sparse int16 [T,N], shaped int8 [T,N,2], None, evcode int16 [T,N]) where evcode carries both agents' 5-bit
-        event codes + done (include/ovc_b200.h OVC_F_OUT_PACKED; expand with wire.decode_event_codes)."""
+        event codes + done (include/ovc_b200.h OVC_F_OUT_PACKED; expand with wire.decode_event_codes), or with
+        ``codes`` (2 bytes per env-step) (None, None, None, evcode int16 [T,N]): the same word plus one
+        "shaped reward granted" bit per agent, from which rewards follow by table (OVC_F_OUT_CODES; expand_codes)."""
         N = self.n_envs
+        mk = (lambda sh, dt: torch.empty(sh, dtype=dt, pin_memory=True)) if pin else (lambda sh, dt: torch.empty(sh, dtype=dt, device=self.device))
+        if codes:
+            return (None, None, None, mk((T, N), torch.int16))
         if packed:
-            mk = (lambda sh, dt: torch.empty(sh, dtype=dt, pin_memory=True)) if pin else (lambda sh, dt: torch.empty(sh, dtype=dt, device=self.device))
             return (mk((T, N), torch.int16), mk((T, N, 2), torch.int8), None, mk((T, N), torch.int16))
         dts = (torch.int16, torch.int8, torch.uint8, torch.int32) if narrow else (torch.int32,) * 4
         shapes = ((T, N), (T, N, 2), (T, N), (T, N, 2))
@@ -184,20 +188,35 @@ class BatchedOvercookedEnv(object):
     def rollout(self, actions, out=None):
         """T transitions in one launch (state stays on chip between them).
 
-        actions  int32 or uint8 CUDA tensor [T, N, 2]
-        out      optional (sparse[T,N], shaped[T,N,2], done[T,N], events[T,N,2]): all int32, or the narrow set of
-                 alloc_rollout_out(narrow=True).
+        actions  int32 or uint8 CUDA tensor [T, N, 2], or uint8 [T, N] with both agents' indices in one byte
+                 (agent 0 in bits 0-3, agent 1 in bits 4-7; wire.pack_actions)
+        out      optional (sparse[T,N], shaped[T,N,2], done[T,N], events[T,N,2]): all int32, or one of the narrower
+                 sets of alloc_rollout_out(narrow= / packed= / codes=).
         Equivalent to T calls of step() with the same actions.
         """
-        assert actions.dtype in (torch.int32, torch.uint8) and actions.is_cuda and actions.is_contiguous() and actions.dim() == 3
+        assert actions.dtype in (torch.int32, torch.uint8) and actions.is_cuda and actions.is_contiguous() and actions.dim() in (2, 3)
         T = actions.shape[0]
-        assert actions.shape[1] == self.n_envs and actions.shape[2] == 2
+        assert actions.shape[1] == self.n_envs
         if out is None:
             out = self.alloc_rollout_out(T)
         sparse, shaped, done, events = out
         flags = self._flags()
-        if actions.dtype == torch.uint8:
-            flags |= _native.F_ACT_U8
+        if actions.dim() == 2:
+            assert actions.dtype == torch.uint8, "one-byte joint actions are uint8 [T, N]"
+            flags |= _native.F_ACT_PACKED
+        else:
+            assert actions.shape[2] == 2
+            if actions.dtype == torch.uint8:
+                flags |= _native.F_ACT_U8
+        if sparse is None:  # codes: 2 bytes per env-step
+            assert shaped is None and done is None and events.dtype == torch.int16 and events.dim() == 2
+            assert tuple(events.shape) == (T, self.n_envs) and events.is_cuda and events.is_contiguous()
+            flags |= _native.F_OUT_CODES
+            _native.check(self._lib.ovc_rollout(
+                self.tables.data_ptr(), self.n_layouts, self.start_records.data_ptr(), self.state.data_ptr(),
+                actions.data_ptr(), 0, 0, 0, events.data_ptr(), self.n_envs, T, self.state_words, self.horizon, flags,
+                self._rs_ptr(), self._stream()))
+            return out
         if done is None:  # packed: 6 bytes per env-step
             assert sparse.dtype == torch.int16 and shaped.dtype == torch.int8 and events.dtype == torch.int16 and events.dim() == 2
             assert self.narrow_ok(), "rewards of these layouts do not fit the narrow formats"
@@ -212,6 +231,41 @@ class BatchedOvercookedEnv(object):
             self.tables.data_ptr(), self.n_layouts, self.start_records.data_ptr(), self.state.data_ptr(),
             actions.data_ptr(), sparse.data_ptr(), shaped.data_ptr(), 0 if done is None else done.data_ptr(), events.data_ptr(),
             self.n_envs, T, self.state_words, self.horizon, flags, self._rs_ptr(), self._stream()))
+        return out
+
+    def code_reward_table(self):
+        """int32 numpy [n_layouts, 2, 32]: delivery reward and shaped reward of each event code (OVC_F_OUT_CODES)."""
+        from overcooked_ai_b200 import wire
+
+        return wire.code_reward_table(self.layouts)
+
+    def expand_codes(self, evcode, sparse=True, shaped=True, done=True, events=False, n_threads=0, out=None):
+        """Dense host arrays from a HOST int16 [T, N] tensor of OVC_F_OUT_CODES words, on the host cores
+        (ovc_expand_codes_host): dict with the requested int16 sparse [T,N], int8 shaped [T,N,2], uint8 done [T,N],
+        int32 events [T,N,2].  With ``random_layout`` every layout of the pool must share one reward table."""
+        assert evcode.dtype == torch.int16 and not evcode.is_cuda and evcode.is_contiguous() and evcode.dim() == 2
+        T, N = evcode.shape
+        assert N == self.n_envs
+        tbl = self.code_reward_table()
+        lay = self.env_layout_host
+        if self.random_layout:
+            assert (tbl == tbl[:1]).all(), "random_layout with different reward tables: the codes alone do not name the layout"
+            lay = None
+        if out is None:
+            out = {}
+            if sparse:
+                out["sparse"] = torch.empty((T, N), dtype=torch.int16)
+            if shaped:
+                out["shaped"] = torch.empty((T, N, 2), dtype=torch.int8)
+            if done:
+                out["done"] = torch.empty((T, N), dtype=torch.uint8)
+            if events:
+                out["events"] = torch.empty((T, N, 2), dtype=torch.int32)
+        ptr = lambda k: out[k].data_ptr() if k in out else 0
+        tbl = np.ascontiguousarray(tbl, dtype=np.int32)
+        _native.check(self._lib.ovc_expand_codes_host(
+            evcode.data_ptr(), T, N, 0 if lay is None else lay.ctypes.data, tbl.ctypes.data, self.n_layouts,
+            ptr("sparse"), ptr("shaped"), ptr("done"), ptr("events"), int(n_threads)))
         return out
 
     # ---------------------------------------------------------------------------------------------
@@ -328,73 +382,109 @@ class BatchedOvercookedEnv(object):
         self.state[torch.as_tensor(idx, device=self.device)] = torch.from_numpy(recs).to(self.device)
 
 
+class PassTicket(object):
+    """Completion handle of one HostRolloutPipeline pass submitted with wait=False."""
+
+    def __init__(self, pipe, ticket):
+        self._pipe, self.ticket = pipe, ticket
+
+    def synchronize(self):
+        """Block the host until the pass's last device->host copy has landed."""
+        _native.check(self._pipe._lib.ovc_pipeline_wait(self._pipe._handle, self.ticket))
+
+
 class HostRolloutPipeline(object):
     """Rollout collection with HOST buffers: the end-to-end path a host-side policy / learner sees.
 
-    ``run(actions_host[T,N,2])`` copies the action trace host->device in chunks of ``chunk`` steps
-    (pinned memory, copy stream), advances the environments with the fused rollout kernel (compute
-    stream) and copies sparse / shaped / done / events device->host (second copy stream), the three
-    stages overlapped across chunks with double buffering.  Returns pinned host tensors
-    (sparse[T,N], shaped[T,N,2], done[T,N], events[T,N,2]).  Per environment-step this moves 8 bytes
-    host->device and 24 bytes device->host (2 + 13 with ``narrow``, 2 + 6 with ``packed``).
+    ``run(actions_host[T,N,2])`` hands pinned host buffers to the native driver (``ovc_pipeline_run``), which
+    copies the action trace host->device in chunks of ``chunk`` steps (copy stream), advances the environments with
+    the fused rollout kernel (compute stream) and copies sparse / shaped / done / events device->host (second copy
+    stream), the three stages overlapped across chunks with double buffering — and across successive passes with
+    ``wait=False``.  Returns pinned host tensors (sparse[T,N], shaped[T,N,2], done[T,N], events[T,N,2]).  Per
+    environment-step this moves 8 bytes host->device and 24 bytes device->host (2 + 13 with ``narrow``, 2 + 6 with
+    ``packed``, 1 + 2 with ``codes``).
     ``run`` is stream ordered like every other call here: the returned tensors are complete once the current
     stream has been synchronised (``torch.cuda.current_stream().synchronize()``), not when ``run`` returns.
     """
 
-    def __init__(self, env, n_steps, chunk=50, narrow=False, packed=False):
+    def __init__(self, env, n_steps, chunk=50, narrow=False, packed=False, codes=False, host_buffers=1):
         """narrow=True: uint8 actions in, int16 sparse / int8 shaped / uint8 done / int32 events out — the same
         values in 2 + 13 instead of 8 + 24 bytes per env-step.  packed=True: uint8 actions in, int16 sparse / int8
-        shaped / int16 event codes (+done) out — 2 + 6 bytes per env-step, lossless (wire.decode_event_codes)."""
-        narrow = narrow or packed
+        shaped / int16 event codes (+done) out — 2 + 6 bytes per env-step, lossless (wire.decode_event_codes).
+        codes=True: one byte of joint action in (wire.pack_actions, actions_host uint8 [T,N]), one int16 word of
+        event codes + done + reward-grant bits out — 1 + 2 bytes per env-step, lossless (env.expand_codes).
+        host_buffers: number of pinned output sets, used round robin by successive run() calls (2 lets a consumer
+        read pass i while pass i+1 is in flight, see run(wait=False))."""
+        narrow = narrow or packed or codes
         self.env, self.T, self.chunk, self.narrow, self.packed = env, int(n_steps), int(chunk), bool(narrow), bool(packed)
+        self.codes = bool(codes)
+        if narrow:
+            assert env.narrow_ok(), "rewards of these layouts do not fit the narrow formats"
         N, dev = env.n_envs, env.device
-        self.s_h2d, self.s_comp, self.s_d2h = (torch.cuda.Stream(dev) for _ in range(3))
+        self._lib = env._lib
         self.act_dtype = torch.uint8 if narrow else torch.int32
-        self.d_act = [torch.empty((chunk, N, 2), dtype=self.act_dtype, device=dev) for _ in range(2)]
-        self.d_out = [env.alloc_rollout_out(chunk, narrow=narrow, packed=packed) for _ in range(2)]
-        self.h_out = env.alloc_rollout_out(self.T, narrow=narrow, pin=True, packed=packed)
-        self.h2d_bytes_per_step = N * 2 * self.d_act[0].element_size()
+        self.act_shape = (N,) if codes else (N, 2)
+        with torch.cuda.device(dev):
+            self.d_act = [torch.empty((self.chunk,) + self.act_shape, dtype=self.act_dtype, device=dev) for _ in range(2)]
+            self.d_out = [env.alloc_rollout_out(self.chunk, narrow=narrow, packed=packed, codes=codes) for _ in range(2)]
+            self.h_outs = [env.alloc_rollout_out(self.T, narrow=narrow, pin=True, packed=packed, codes=codes)
+                           for _ in range(max(1, int(host_buffers)))]
+        self.h_out = self.h_outs[0]
+        self._runs = 0
+        self.h2d_bytes_per_step = N * (1 if codes else 2) * self.d_act[0].element_size()
         self.d2h_bytes_per_step = sum(N * (2 if o.dim() == 3 else 1) * o.element_size() for o in self.h_out if o is not None)
+        flags = env._flags() | (_native.F_ACT_PACKED if codes else _native.F_ACT_U8 if narrow else 0)
+        flags |= _native.F_OUT_CODES if codes else _native.F_OUT_PACKED if packed else _native.F_OUT_NARROW if narrow else 0
+        d = _native.PipelineDesc()
+        d.layouts, d.n_layouts, d.state_words = env.tables.data_ptr(), env.n_layouts, env.state_words
+        d.start_records, d.state, d.n_envs = env.start_records.data_ptr(), env.state.data_ptr(), N
+        d.horizon, d.flags, d.chunk = env.horizon, flags, self.chunk
+        d.has_random_start = int(env._rs is not None)
+        if env._rs is not None:
+            d.random_start = env._rs
+        ptr = lambda t: 0 if t is None else t.data_ptr()
+        for b in range(2):
+            d.d_actions[b] = self.d_act[b].data_ptr()
+            d.d_sparse[b], d.d_shaped[b], d.d_done[b], d.d_events[b] = (ptr(t) for t in self.d_out[b])
+        h = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            _native.check(self._lib.ovc_pipeline_create(ctypes.byref(d), ctypes.byref(h)))
+        self._handle = h
 
-    def run(self, actions_host):
-        assert actions_host.dtype == self.act_dtype and actions_host.is_pinned() and tuple(actions_host.shape) == (self.T, self.env.n_envs, 2)
-        env = self.env
-        cur = torch.cuda.current_stream(env.device)
-        for s in (self.s_h2d, self.s_comp, self.s_d2h):
-            s.wait_stream(cur)
-        ev_comp_done = [None, None]  # compute finished with d_act[b] / produced d_out[b]
-        ev_d2h_done = [None, None]   # d_out[b] has been copied out
-        k = 0
-        for t0 in range(0, self.T, self.chunk):
-            tc = min(self.chunk, self.T - t0)
-            b = k & 1
-            with torch.cuda.stream(self.s_h2d):
-                if ev_comp_done[b] is not None:
-                    self.s_h2d.wait_event(ev_comp_done[b])  # the kernel two chunks ago has consumed d_act[b]
-                self.d_act[b][:tc].copy_(actions_host[t0:t0 + tc], non_blocking=True)
-                ev_in = torch.cuda.Event()
-                ev_in.record(self.s_h2d)
-            with torch.cuda.stream(self.s_comp):
-                self.s_comp.wait_event(ev_in)
-                if ev_d2h_done[b] is not None:
-                    self.s_comp.wait_event(ev_d2h_done[b])  # d_out[b] is free again
-                out = tuple(None if o is None else o[:tc] for o in self.d_out[b])
-                env.rollout(self.d_act[b][:tc], out=out)
-                ev_c = torch.cuda.Event()
-                ev_c.record(self.s_comp)
-                ev_comp_done[b] = ev_c
-            with torch.cuda.stream(self.s_d2h):
-                self.s_d2h.wait_event(ev_c)
-                for h, d in zip(self.h_out, out):
-                    if h is not None:
-                        h[t0:t0 + tc].copy_(d, non_blocking=True)
-                ev_o = torch.cuda.Event()
-                ev_o.record(self.s_d2h)
-                ev_d2h_done[b] = ev_o
-            k += 1
-        for s in (self.s_h2d, self.s_comp, self.s_d2h):
-            cur.wait_stream(s)
-        return self.h_out
+    def run(self, actions_host, wait=True):
+        """wait=True: the current stream waits for the pass (stream-ordered like every other call); returns the
+        host tensors.  wait=False: returns (host tensors, PassTicket) without joining the current stream, so the
+        next run() starts its copies while this pass is still draining — the steady state of a collection
+        loop; ``ticket.synchronize()`` before reading, and ``join()`` before touching the env from the current
+        stream again."""
+        assert actions_host.dtype == self.act_dtype and actions_host.is_pinned() and actions_host.is_contiguous()
+        assert tuple(actions_host.shape) == (self.T,) + self.act_shape
+        h_out = self.h_outs[self._runs % len(self.h_outs)]
+        self._runs += 1
+        ptr = lambda t: 0 if t is None else t.data_ptr()
+        ticket = ctypes.c_int64(-1)
+        _native.check(self._lib.ovc_pipeline_run(
+            self._handle, actions_host.data_ptr(), ptr(h_out[0]), ptr(h_out[1]), ptr(h_out[2]), ptr(h_out[3]), self.T,
+            self.env._stream(), int(bool(wait)), ctypes.byref(ticket)))
+        self._last_actions = actions_host  # keep the source alive until the copies have run
+        if wait:
+            return h_out
+        return h_out, PassTicket(self, ticket.value)
+
+    def join(self):
+        """Make the current stream wait for everything the pipeline has in flight."""
+        _native.check(self._lib.ovc_pipeline_join(self._handle, self.env._stream()))
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            self._lib.ovc_pipeline_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class EpisodeStats(object):

@@ -177,8 +177,18 @@ __device__ __forceinline__ unsigned event_code(unsigned ev) {
     return 12u + ((ev >> OVC_EV_USEFUL_DISH_DROP) & 1u);  // dish_drop
 }
 
+// WIDE: the kernel instantiation for int32 actions and int32 outputs (the device-resident formats) — it carries
+// none of the format tests below, which cost 3 % of a fused-rollout transition when they sat in every instantiation.
+template <bool WIDE>
 __device__ __forceinline__ void write_outputs(const StepArgs &a, long long idx, const StepOut &o) {
-    if (a.flags & OVC_F_OUT_PACKED) {  // 6 bytes per env-step for host transfer
+    if (!WIDE && (a.flags & OVC_F_OUT_CODES)) {  // 2 bytes per env-step: rewards are functions of the codes + two grant bits
+        reinterpret_cast<unsigned short *>(a.events)[idx] =
+            (unsigned short)(event_code(o.ev0) | (event_code(o.ev1) << 5) | ((unsigned)o.done << 10) |
+                             ((o.ev0 & OVC_EVF_STEPPED_DONE) ? 1u << 11 : 0u) | (o.shaped0 != 0 ? 1u << 12 : 0u) |
+                             (o.shaped1 != 0 ? 1u << 13 : 0u));
+        return;
+    }
+    if (!WIDE && (a.flags & OVC_F_OUT_PACKED)) {  // 6 bytes per env-step for host transfer
         reinterpret_cast<short *>(a.sparse)[idx] = (short)o.sparse;
         reinterpret_cast<char2 *>(a.shaped)[idx] = make_char2((signed char)o.shaped0, (signed char)o.shaped1);
         reinterpret_cast<unsigned short *>(a.events)[idx] =
@@ -186,7 +196,7 @@ __device__ __forceinline__ void write_outputs(const StepArgs &a, long long idx, 
                              ((o.ev0 & OVC_EVF_STEPPED_DONE) ? 1u << 11 : 0u));
         return;
     }
-    if (a.flags & OVC_F_OUT_NARROW) {  // uniform branch: int16 / int8x2 / uint8 for host transfer
+    if (!WIDE && (a.flags & OVC_F_OUT_NARROW)) {  // uniform branch: int16 / int8x2 / uint8 for host transfer
         reinterpret_cast<short *>(a.sparse)[idx] = (short)o.sparse;
         reinterpret_cast<unsigned char *>(a.done)[idx] = (unsigned char)o.done;
         reinterpret_cast<char2 *>(a.shaped)[idx] = make_char2((signed char)o.shaped0, (signed char)o.shaped1);
@@ -198,8 +208,13 @@ __device__ __forceinline__ void write_outputs(const StepArgs &a, long long idx, 
     reinterpret_cast<int2 *>(a.events)[idx] = make_int2((int)o.ev0, (int)o.ev1);
 }
 
+template <bool WIDE>
 __device__ __forceinline__ int2 load_action(const StepArgs &a, long long idx) {
-    if (a.flags & OVC_F_ACT_U8) {
+    if (!WIDE && (a.flags & OVC_F_ACT_PACKED)) {
+        const unsigned u = reinterpret_cast<const unsigned char *>(a.actions)[idx];
+        return make_int2((int)(u & 15u), (int)(u >> 4));
+    }
+    if (!WIDE && (a.flags & OVC_F_ACT_U8)) {
         const uchar2 u = reinterpret_cast<const uchar2 *>(a.actions)[idx];
         return make_int2(u.x, u.y);
     }
@@ -211,7 +226,7 @@ __device__ __forceinline__ int2 load_action(const StepArgs &a, long long idx) {
 constexpr int MAX_SMEM_LAYOUTS = 8;
 
 // One CTA = one tile of TILE records.  n_steps == 1: the step kernel K1; n_steps > 1: the fused rollout K5.
-template <int S, int IO, bool RS>
+template <int S, int IO, bool RS, bool WIDE>
 __global__ void __launch_bounds__(Cfg<S>::TILE)
 step_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
     using C = Cfg<S>;
@@ -228,10 +243,10 @@ step_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
         const TblG tb{reinterpret_cast<const char *>(a.layouts)};
         for (int t = 0; t < T; t++) {
             const long long idx = (long long)t * a.n_envs + env;
-            const int2 act = load_action(a, idx);
+            const int2 act = load_action<WIDE>(a, idx);
             StepOut o;
             step_core<RS>(r, tb, a.start_records, S, act.x, act.y, a.horizon, a.flags, RS ? &a.rs : nullptr, env, a.n_layouts, o);
-            write_outputs(a, idx, o);
+            write_outputs<WIDE>(a, idx, o);
         }
         return;
     }
@@ -261,7 +276,7 @@ step_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
     }
     // the first action fetch overlaps the tile load
     int2 act = make_int2(OVC_A_STAY, OVC_A_STAY);
-    if (live) act = load_action(a, env);
+    if (live) act = load_action<WIDE>(a, env);
     __syncthreads();  // barrier initialised and visible before anyone polls it
     mbar_wait(bar, 0);
     // Programmatic dependent launch: once the tile has landed, the next kernel of the stream may be
@@ -275,10 +290,10 @@ step_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
             for (int t = 0; t < T; t++) {
                 const long long idx = (long long)t * a.n_envs + env;
                 int2 nxt = act;
-                if (t + 1 < T) nxt = load_action(a, idx + a.n_envs);  // prefetch
+                if (t + 1 < T) nxt = load_action<WIDE>(a, idx + a.n_envs);  // prefetch
                 StepOut o;
                 step_core<RS>(r, tb, a.start_records, S, act.x, act.y, a.horizon, a.flags, RS ? &a.rs : nullptr, env, a.n_layouts, o);
-                write_outputs(a, idx, o);
+                write_outputs<WIDE>(a, idx, o);
                 act = nxt;
             }
         };
@@ -377,8 +392,12 @@ static cudaError_t launch_one(const CUtensorMap &tmap, const StepArgs &a, unsign
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (a.flags & OVC_F_PDL) ? 1 : 0;
-    if (a.has_rs) return cudaLaunchKernelEx(&cfg, step_kernel<S, IO, true>, tmap, a);
-    return cudaLaunchKernelEx(&cfg, step_kernel<S, IO, false>, tmap, a);
+    const bool wide = !(a.flags & (OVC_F_ACT_U8 | OVC_F_ACT_PACKED | OVC_F_OUT_NARROW | OVC_F_OUT_PACKED | OVC_F_OUT_CODES));
+    if (a.has_rs)
+        return wide ? cudaLaunchKernelEx(&cfg, step_kernel<S, IO, true, true>, tmap, a)
+                    : cudaLaunchKernelEx(&cfg, step_kernel<S, IO, true, false>, tmap, a);
+    return wide ? cudaLaunchKernelEx(&cfg, step_kernel<S, IO, false, true>, tmap, a)
+                : cudaLaunchKernelEx(&cfg, step_kernel<S, IO, false, false>, tmap, a);
 }
 
 template <int S>
@@ -419,14 +438,18 @@ static int step_impl(const void *layouts, int n_layouts, const int32_t *start_re
                      void *stream) {
     int rc = check_common(layouts, n_layouts, state, n_envs, S);
     if (rc) return rc;
-    if (!actions || !sparse || !shaped || (!done && !(flags & OVC_F_OUT_PACKED)) || !events || !start_records)
+    const bool codes = flags & OVC_F_OUT_CODES;
+    if (!actions || !events || !start_records || (!codes && (!sparse || !shaped)) ||
+        (!done && !(flags & (OVC_F_OUT_PACKED | OVC_F_OUT_CODES))))
         return fail(OVC_E_BADARG, "null pointer argument");
-    const bool small_out = flags & (OVC_F_OUT_NARROW | OVC_F_OUT_PACKED);
-    if ((((flags & OVC_F_ACT_U8) ? 0 : (uintptr_t)actions) | (small_out ? 0 : (uintptr_t)shaped) |
-         ((flags & OVC_F_OUT_PACKED) ? 0 : (uintptr_t)events)) & 7)
+    if (codes) sparse = nullptr, shaped = nullptr, done = nullptr;
+    const bool small_out = flags & (OVC_F_OUT_NARROW | OVC_F_OUT_PACKED | OVC_F_OUT_CODES);
+    const bool small_ev = flags & (OVC_F_OUT_PACKED | OVC_F_OUT_CODES);
+    const bool small_act = flags & (OVC_F_ACT_U8 | OVC_F_ACT_PACKED);
+    if (((small_act ? 0 : (uintptr_t)actions) | (small_out ? 0 : (uintptr_t)shaped) | (small_ev ? 0 : (uintptr_t)events)) & 7)
         return fail(OVC_E_BADARG, "actions / shaped / events must be 8-byte aligned");
     if ((((flags & OVC_F_ACT_U8) ? (uintptr_t)actions : 0) | (small_out ? ((uintptr_t)shaped | (uintptr_t)sparse) : 0) |
-         ((flags & OVC_F_OUT_PACKED) ? (uintptr_t)events : 0)) & 1)
+         (small_ev ? (uintptr_t)events : 0)) & 1)
         return fail(OVC_E_BADARG, "narrow actions / shaped / sparse must be 2-byte aligned");
     if (n_steps < 1) return fail(OVC_E_BADARG, "n_steps must be >= 1");
     if (n_envs == 0) return OVC_OK;
@@ -449,6 +472,7 @@ static int step_impl(const void *layouts, int n_layouts, const int32_t *start_re
 
 #include "ovc_obs.cuh"
 #include "ovc_potential.cuh"
+#include "ovc_host.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // C ABI
@@ -522,5 +546,28 @@ int ovc_potential(const void *layouts, int n_layouts, const void *pot_tables, co
                                (cudaStream_t)stream);
 }
 size_t ovc_potential_table_size(void) { return sizeof(ovc_potential_t); }
+
+int ovc_pipeline_create(const ovc_pipeline_desc_t *desc, ovc_pipeline_t **out) { return ovc::pipeline_create(desc, out); }
+int ovc_pipeline_run(ovc_pipeline_t *p, const void *h_actions, void *h_sparse, void *h_shaped, void *h_done, void *h_events,
+                     int n_steps, void *stream, int join, int64_t *ticket) {
+    if (!p) return ovc::fail(OVC_E_BADARG, "null pipeline");
+    return ovc::pipeline_run(p, h_actions, h_sparse, h_shaped, h_done, h_events, n_steps, (cudaStream_t)stream, join, ticket);
+}
+int ovc_pipeline_wait(ovc_pipeline_t *p, int64_t ticket) {
+    if (!p) return ovc::fail(OVC_E_BADARG, "null pipeline");
+    return ovc::pipeline_wait(p, ticket);
+}
+int ovc_pipeline_join(ovc_pipeline_t *p, void *stream) {
+    if (!p) return ovc::fail(OVC_E_BADARG, "null pipeline");
+    return ovc::pipeline_join(p, (cudaStream_t)stream);
+}
+void ovc_pipeline_destroy(ovc_pipeline_t *p) { ovc::pipeline_destroy(p); }
+
+int ovc_expand_codes_host(const uint16_t *codes, int64_t n_steps, int64_t n_envs, const int32_t *env_layout,
+                          const int32_t *reward_tbl, int n_layouts, int16_t *sparse, int8_t *shaped, uint8_t *done,
+                          int32_t *events, int n_threads) {
+    return ovc::expand_codes_host(codes, n_steps, n_envs, env_layout, reward_tbl, n_layouts, sparse, shaped, done, events,
+                                  n_threads);
+}
 
 }  // extern "C"

@@ -116,6 +116,41 @@ def _event_code_table():
 EVENT_CODE_TABLE = _event_code_table()
 
 
+def pack_actions(actions):
+    """int array [..., 2] of action indices -> uint8 [...]: agent 0 in bits 0-3, agent 1 in bits 4-7 (OVC_F_ACT_PACKED)."""
+    a = np.asarray(actions)
+    assert a.shape[-1] == 2 and a.min() >= 0 and a.max() < 6
+    return (a[..., 0] | (a[..., 1] << 4)).astype(np.uint8)
+
+
+def code_reward_table(layouts):
+    """int32 [n_layouts, 2, 32]: [l][0][code] = delivery reward of the code's recipe on layout l, [l][1][code] = the
+    shaped reward an agent gets WITH that code when its grant bit is set (include/ovc_b200.h, OVC_F_OUT_CODES)."""
+    t = np.zeros((len(layouts), 2, 32), np.int32)
+    rows = [r for r in range(1, 16) if (r >> 2) + (r & 3) <= 3]
+    for i, l in enumerate(layouts):
+        for rank, row in enumerate(rows):
+            t[i, 0, 23 + rank] = int(l.deliver_value[row])
+        t[i, 1, 15:23] = int(l.reward_shaping_params["PLACEMENT_IN_POT_REW"])
+        t[i, 1, 6] = int(l.reward_shaping_params["DISH_PICKUP_REWARD"])
+        t[i, 1, 7] = int(l.reward_shaping_params["SOUP_PICKUP_REWARD"])
+    return t
+
+
+def decode_codes(evcode, reward_tbl, env_layout=None):
+    """numpy reference of ovc_expand_codes_host: int16 [..., N] OVC_F_OUT_CODES words ->
+    (sparse int64 [..., N], shaped int64 [..., N, 2], done bool, events int32 [..., N, 2])."""
+    w = np.asarray(evcode).astype(np.int32) & 0xFFFF
+    c = np.stack([w & 31, (w >> 5) & 31], -1)
+    lay = np.zeros(w.shape[-1], np.int64) if env_layout is None else np.asarray(env_layout).astype(np.int64)
+    lay = np.broadcast_to(lay, w.shape)[..., None]
+    grant = np.stack([(w >> 12) & 1, (w >> 13) & 1], -1)
+    sparse = reward_tbl[lay, 0, c].sum(-1).astype(np.int64)
+    shaped = (reward_tbl[lay, 1, c] * grant).astype(np.int64)
+    events, done = decode_event_codes(w & 0xFFF)
+    return sparse, shaped, done, events
+
+
 def decode_event_codes(evcode):
     """int16 [...] packed event codes -> (events int32 [..., 2], done bool [...]) exactly as the int32 formats."""
     ev = np.asarray(evcode).astype(np.int32)

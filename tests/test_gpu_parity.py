@@ -9,7 +9,7 @@ from helpers import EVENT_MASK, GOLD, TRACE_FILES, TRACE_IDS, Trace, lut_bytes
 from oracle import cpu
 from overcooked_ai_b200 import _native
 from overcooked_ai_b200 import layout as L
-from overcooked_ai_b200.batched import BatchedOvercookedEnv, EpisodeStats
+from overcooked_ai_b200.batched import BatchedOvercookedEnv, EpisodeStats, HostRolloutPipeline
 
 pytestmark = pytest.mark.gpu
 
@@ -377,6 +377,61 @@ def test_narrow_transfer_formats_and_host_pipeline():
         for g, w in zip(got, want):
             assert np.array_equal(g.numpy().astype(np.int64), _np(w).astype(np.int64))
         assert torch.equal(env_b.state, env_a.state)
+
+
+def test_code_words_and_one_byte_actions_carry_the_whole_result():
+    """OVC_F_OUT_CODES / OVC_F_ACT_PACKED: 1 byte in, 2 bytes out per env-step; expanding the words on the host
+    gives back sparse / shaped / done / events of the int32 formats, through rollout() and the host pipeline."""
+    from overcooked_ai_b200 import wire
+
+    n, T = 6007, 96
+    names = ["cramped_room", "counter_circuit", "asymmetric_advantages"]
+    rng = np.random.RandomState(4)
+    acts = _random_actions(rng, T, n, 0.45)
+    env_a = BatchedOvercookedEnv(names, n, horizon=40, auto_reset=True, rnd_obj_prob_thresh=0.6, seed=9)
+    env_b = BatchedOvercookedEnv(names, n, horizon=40, auto_reset=True, rnd_obj_prob_thresh=0.6, seed=9)
+    want = [_np(x) for x in env_a.rollout(torch.from_numpy(acts).cuda())]
+    assert want[0].max() >= 20 and (want[1] > 0).any() and (want[3] & (1 << 14)).any()
+    packed_acts = wire.pack_actions(acts)
+    out = env_b.alloc_rollout_out(T, codes=True)
+    env_b.rollout(torch.from_numpy(packed_acts).cuda(), out=out)
+    assert out[0] is None and torch.equal(env_b.state, env_a.state)
+    words = out[3].cpu()
+    got = wire.decode_codes(words.numpy(), env_b.code_reward_table(), env_b.env_layout_host)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    assert np.array_equal(got[2], want[2] != 0) and np.array_equal(got[3], want[3])
+    dense = env_b.expand_codes(words, events=True)
+    assert np.array_equal(dense["sparse"].numpy(), want[0]) and np.array_equal(dense["shaped"].numpy(), want[1])
+    assert np.array_equal(dense["done"].numpy(), want[2]) and np.array_equal(dense["events"].numpy(), want[3])
+    # the dish / soup taken from a counter logs the pickup event but grants nothing: the case the grant bits exist for
+    ev, sh = want[3], want[1]
+    assert ((ev & (1 << 14)) != 0)[sh == 0].any() and ((ev & (1 << 14)) != 0)[sh == 5].any()
+    env_b.reset()
+    env_a.reset()
+    want = [_np(x) for x in env_a.rollout(torch.from_numpy(acts).cuda())]
+    pipe = HostRolloutPipeline(env_b, T, chunk=40, codes=True)
+    assert pipe.h2d_bytes_per_step == n and pipe.d2h_bytes_per_step == 2 * n
+    h = pipe.run(torch.from_numpy(packed_acts).pin_memory())
+    torch.cuda.synchronize()
+    dense = env_b.expand_codes(h[3], events=True)
+    assert np.array_equal(dense["sparse"].numpy(), want[0]) and np.array_equal(dense["shaped"].numpy(), want[1])
+    assert np.array_equal(dense["done"].numpy(), want[2]) and np.array_equal(dense["events"].numpy(), want[3])
+    assert torch.equal(env_b.state, env_a.state)
+    # two passes submitted back to back without joining the current stream in between (two pinned output sets)
+    want2 = [_np(x) for x in env_a.rollout(torch.from_numpy(acts[::-1].copy()).cuda())]
+    want3 = [_np(x) for x in env_a.rollout(torch.from_numpy(acts).cuda())]
+    pipe = HostRolloutPipeline(env_b, T, chunk=40, codes=True, host_buffers=2)
+    rev = torch.from_numpy(wire.pack_actions(acts[::-1])).pin_memory()
+    fwd = torch.from_numpy(packed_acts).pin_memory()
+    (h2, e2), (h3, e3) = pipe.run(rev, wait=False), pipe.run(fwd, wait=False)
+    assert h2[3].data_ptr() != h3[3].data_ptr()
+    for h, e, w in ((h2, e2, want2), (h3, e3, want3)):
+        e.synchronize()
+        dense = env_b.expand_codes(h[3], events=True)
+        assert np.array_equal(dense["sparse"].numpy(), w[0]) and np.array_equal(dense["shaped"].numpy(), w[1])
+        assert np.array_equal(dense["done"].numpy(), w[2]) and np.array_equal(dense["events"].numpy(), w[3])
+    pipe.join()
+    assert torch.equal(env_b.state, env_a.state)
 
 
 @pytest.mark.parametrize("random_pos,thresh", [(True, 0.0), (False, 0.7), (True, 0.5)])

@@ -222,3 +222,32 @@ def test_event_code_table_covers_every_mask_the_engine_can_produce():
         seen |= set(np.unique(ev.astype(np.int64) & 0x1FFFFFFF).tolist())
     assert seen <= set(table.tolist()), sorted(seen - set(table.tolist()))
     assert len(seen) >= 26
+
+
+def test_host_expander_of_code_words_matches_the_numpy_decoder():
+    """ovc_expand_codes_host (host code of the library, no GPU involved) against wire.decode_codes on random valid
+    words, several layouts, threaded and not."""
+    import torch
+
+    from overcooked_ai_b200 import _native, wire
+
+    lib = _native.lib()
+    layouts = [L.compile_layout(n) for n in ("cramped_room", "counter_circuit", "asymmetric_advantages")]
+    tbl = wire.code_reward_table(layouts)
+    assert tbl[0, 0, 31] == 20 and tbl[1, 0].max() == 68 and tbl[0, 1, 15] == 3 and tbl[0, 1, 7] == 5 and tbl[0, 1, 5] == 0
+    rng = np.random.RandomState(0)
+    T, N = 37, 1501
+    w = (rng.randint(0, 32, (T, N)) | (rng.randint(0, 32, (T, N)) << 5) | (rng.randint(0, 2, (T, N)) << 10)
+         | ((rng.rand(T, N) < 0.05).astype(np.int64) << 11) | (rng.randint(0, 4, (T, N)) << 12)).astype(np.uint16).view(np.int16)
+    lay = rng.randint(0, 3, N).astype(np.int32)
+    want = wire.decode_codes(w, tbl, lay)
+    for threads in (1, 5):
+        sp, sh = np.zeros((T, N), np.int16), np.zeros((T, N, 2), np.int8)
+        dn, ev = np.zeros((T, N), np.uint8), np.zeros((T, N, 2), np.int32)
+        rc = lib.ovc_expand_codes_host(w.ctypes.data, T, N, lay.ctypes.data, tbl.ctypes.data, 3, sp.ctypes.data, sh.ctypes.data,
+                                       dn.ctypes.data, ev.ctypes.data, threads)
+        assert rc == 0
+        assert np.array_equal(sp, want[0]) and np.array_equal(sh, want[1]) and np.array_equal(dn != 0, want[2])
+        assert np.array_equal(ev, want[3])
+    assert lib.ovc_expand_codes_host(w.ctypes.data, T, N, (lay + 5).ctypes.data, tbl.ctypes.data, 3, 0, 0, 0, 0, 1) != 0
+    assert np.array_equal(wire.pack_actions(np.array([[5, 3], [0, 4]])), np.array([0x35, 0x40], np.uint8))
