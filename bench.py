@@ -384,7 +384,9 @@ def main():
         from the code words on the host cores inside the timed region (a consumer that wants arrays, not words)."""
         narrow = fmt != "int32"
         codes = fmt == "codes"
-        chunk = int(os.environ.get("OVC_E2E_CHUNK", "50"))
+        # measured over several boxes (tools/e2e_probe.py): with 2-byte words the copies are short, and fewer, larger
+        # chunks ride out the host's PCIe / memory noise best; the wider formats are plainly D2H bound at any size
+        chunk = int(os.environ.get("OVC_E2E_CHUNK", "200" if codes else "50"))
         pipe = HostRolloutPipeline(env, T, chunk=chunk, narrow=narrow, packed=fmt == "packed", codes=codes, host_buffers=2)
         if codes:
             from overcooked_ai_b200 import wire

@@ -70,19 +70,30 @@ public:
         static HostPool *p = new HostPool();  // never destroyed: its detached workers may outlive static destruction
         return *p;
     }
-    // runs job(k) for k in [0, n) on up to n workers (the caller takes k = 0) and returns when all are done
-    void run(int n, const std::function<void(int)> &job) {
+    // runs job(k) for k in [0, n_jobs) on n_threads threads (the caller is one of them); slices are claimed
+    // dynamically, so a core that is shared with somebody else's process only delays its current slice
+    void run(int n_jobs, int n_threads, const std::function<void(int)> &job) {
         std::unique_lock<std::mutex> call(call_mu_);  // one parallel region at a time
-        grow(n - 1);
+        grow(n_threads - 1);
         {
             std::lock_guard<std::mutex> g(mu_);
-            job_ = &job, n_jobs_ = n, next_ = 1, pending_ = n - 1;
+            job_ = &job, n_jobs_ = n_jobs, next_ = 0, pending_ = n_jobs, limit_ = n_threads - 1, active_ = 0;
         }
         cv_.notify_all();
-        job(0);
+        for (;;) {
+            int k;
+            {
+                std::lock_guard<std::mutex> g(mu_);
+                if (next_ >= n_jobs_) break;
+                k = next_++;
+            }
+            job(k);
+            std::lock_guard<std::mutex> g(mu_);
+            --pending_;
+        }
         std::unique_lock<std::mutex> g(mu_);
         done_cv_.wait(g, [&] { return pending_ == 0; });
-        job_ = nullptr;
+        job_ = nullptr, n_jobs_ = 0;
     }
 
 private:
@@ -98,14 +109,21 @@ private:
             const std::function<void(int)> *job;
             {
                 std::unique_lock<std::mutex> g(mu_);
-                cv_.wait(g, [&] { return next_ < n_jobs_; });  // an unclaimed slice of the current region
+                // an unclaimed slice of the current region, and room among the threads this region asked for
+                cv_.wait(g, [&] { return next_ < n_jobs_ && active_ < limit_; });
                 k = next_++;
                 job = job_;
+                active_++;
             }
-            (*job)(k);
-            {
+            for (;;) {
+                (*job)(k);
                 std::lock_guard<std::mutex> g(mu_);
                 if (--pending_ == 0) done_cv_.notify_all();
+                if (next_ >= n_jobs_) {
+                    active_--;
+                    break;
+                }
+                k = next_++;
             }
         }
     }
@@ -113,7 +131,7 @@ private:
     std::condition_variable cv_, done_cv_;
     std::vector<std::thread> workers_;
     const std::function<void(int)> *job_ = nullptr;
-    int n_jobs_ = 0, next_ = 0, pending_ = 0;
+    int n_jobs_ = 0, next_ = 0, pending_ = 0, limit_ = 0, active_ = 0;
 };
 
 static int expand_codes_host(const uint16_t *codes, int64_t n_steps, int64_t n_envs, const int32_t *env_layout,
@@ -137,8 +155,9 @@ static int expand_codes_host(const uint16_t *codes, int64_t n_steps, int64_t n_e
         expand_range(codes, 0, n, n_envs, env_layout, reward_tbl, sparse, shaped, done, events, mask);
         return OVC_OK;
     }
-    HostPool::get().run(n_threads, [&](int k) {
-        expand_range(codes, n * k / n_threads, n * (k + 1) / n_threads, n_envs, env_layout, reward_tbl, sparse, shaped, done,
+    const int n_slices = n_threads * 8;  // ~50 k words per slice at the bench's size
+    HostPool::get().run(n_slices, n_threads, [&](int k) {
+        expand_range(codes, n * k / n_slices, n * (k + 1) / n_slices, n_envs, env_layout, reward_tbl, sparse, shaped, done,
                      events, mask);
     });
     return OVC_OK;
