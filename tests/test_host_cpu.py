@@ -251,3 +251,38 @@ def test_host_expander_of_code_words_matches_the_numpy_decoder():
         assert np.array_equal(ev, want[3])
     assert lib.ovc_expand_codes_host(w.ctypes.data, T, N, (lay + 5).ctypes.data, tbl.ctypes.data, 3, 0, 0, 0, 0, 1) != 0
     assert np.array_equal(wire.pack_actions(np.array([[5, 3], [0, 4]])), np.array([0x35, 0x40], np.uint8))
+
+
+def test_host_expander_pool_survives_concurrent_and_repeated_regions():
+    """The persistent worker pool behind ovc_expand_codes_host: many regions with changing thread counts, issued
+    from two host threads at once, all produce the right arrays and none hangs."""
+    import threading
+
+    from overcooked_ai_b200 import _native, wire
+
+    lib = _native.lib()
+    tbl = wire.code_reward_table([L.compile_layout("cramped_room")])
+    rng = np.random.RandomState(1)
+    T, N = 16, 20011
+    w = (rng.randint(0, 32, (T, N)) | (rng.randint(0, 32, (T, N)) << 5) | (rng.randint(0, 4, (T, N)) << 12)).astype(np.uint16).view(np.int16)
+    want = wire.decode_codes(w, tbl)
+    errors = []
+
+    def worker(seed):
+        r = np.random.RandomState(seed)
+        sp, sh = np.zeros((T, N), np.int16), np.zeros((T, N, 2), np.int8)
+        for _ in range(60):
+            sp[:] = -1
+            thr = int(r.choice([1, 2, 3, 5, 8, 16]))
+            if lib.ovc_expand_codes_host(w.ctypes.data, T, N, 0, tbl.ctypes.data, 1, sp.ctypes.data, sh.ctypes.data, 0, 0, thr) != 0:
+                errors.append("rc")
+            if not (np.array_equal(sp, want[0]) and np.array_equal(sh, want[1])):
+                errors.append("mismatch with %d threads" % thr)
+
+    ts = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=120)
+    assert not any(t.is_alive() for t in ts), "expander pool deadlocked"
+    assert not errors, errors[:3]
