@@ -480,8 +480,8 @@ def main():
             "note": "achieved = env_steps_per_launch x %d B (SURVEY 8d) / avg launch duration; avg launch duration = CUDA-event time of the timed region / launches (includes launch gaps)" % bytes_per,
         }
         # secondary bound: warp-instruction issue.  Instructions per warp-transition come from the
-        # ncu captures under profiles/ (421 for K5, 445 for K1 on cramped_room); peak = SMs x 4 schedulers x SM clock.
-        wi = {16: (421, 445)}.get(S)
+        # ncu captures under profiles/ (418 for K5, 445 for K1 on cramped_room); peak = SMs x 4 schedulers x SM clock.
+        wi = {16: (418, 445)}.get(S)
         if wi and clocks and clocks.get("sm_mhz"):
             per_wt = wi[0] if fused else wi[1]
             issued = per_launch_env_steps / 32.0 * per_wt / avg_launch_s

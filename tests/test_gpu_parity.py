@@ -517,6 +517,8 @@ def test_variable_mdp_layout_redraw_vs_oracle_mirror(pool_size, random_pos, thre
     assert np.array_equal(_np(env.lossless_state_encoding(dtype=torch.int32)),
                           cpu.encode_lossless(env._tab_host, ref, W, H, horizon))
     assert np.array_equal(_np(env.featurize_state(2)).astype(np.float64), cpu.featurize(env._tab_host, lut_bytes(pool), ref, 2))
+    pt, cst, gpow = L.build_potential_tables(pool, 0.99)
+    assert np.array_equal(_np(env.potential(0.99)), cpu.potential(env._tab_host, pt, cst, gpow, ref))
     # masked reset: new layouts for exactly the masked environments
     mask = (rng.rand(n) < 0.5).astype(np.int32)
     env.reset(torch.from_numpy(mask).cuda())
