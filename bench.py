@@ -488,6 +488,13 @@ def main():
             peak_issue = 148 * 4 * clocks["sm_mhz"] * 1e6
             r["issue_bound"] = {"warp_instructions_per_warp_transition": per_wt, "source": "profiles/r1_final_kernels_ncu_full.md",
                                 "achieved_warp_inst_per_s": issued, "peak_warp_inst_per_s": peak_issue, "frac": issued / peak_issue}
+        # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full`
+        # captures of exactly this launch shape; any other shape has no capture and stays null
+        if S == 16 and n_envs == 65536 and args.workload == "config2":
+            cap = (213.935104e6 + 577.443584e6, "profiles/r1_final_k5_ncu_raw.csv") if fused and T == 400 else \
+                  (4.74e6, "profiles/r1_final_k1_ncu_raw.csv") if not fused else None
+            if cap:
+                r["traffic"], r["traffic_source"] = cap
         if fused:
             r["streamed_GBps"] = per_launch_env_steps * 32 / avg_launch_s / 1e9
             r["note"] += "; the fused kernel keeps the record on chip between transitions, so only actions + outputs (32 B per env-step, streamed_GBps) cross HBM: a frac near or above 1 is traffic avoided by fusion, not bandwidth"
