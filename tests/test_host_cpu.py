@@ -286,3 +286,42 @@ def test_host_expander_pool_survives_concurrent_and_repeated_regions():
         t.join(timeout=120)
     assert not any(t.is_alive() for t in ts), "expander pool deadlocked"
     assert not errors, errors[:3]
+
+
+def test_pipeline_descriptor_layout_matches_the_c_struct():
+    """ovc_pipeline_create validates its descriptor before it touches CUDA, so the argument checks double as a
+    field-offset check of the ctypes mirror (no GPU needed): each error below is reached only if the fields before
+    it were read where the C struct has them."""
+    import ctypes
+
+    from overcooked_ai_b200 import _native
+
+    lib = _native.lib()
+    assert ctypes.sizeof(_native.PipelineDesc) == 160 and _native.PipelineDesc.random_start.offset == 56
+    buf = (ctypes.c_char * 4096)()
+    base = ctypes.addressof(buf) & ~15 | 16  # any non-null, 16-byte aligned address: nothing is dereferenced
+
+    def create(**kw):
+        d = _native.PipelineDesc()
+        d.layouts, d.n_layouts, d.state_words, d.start_records, d.state = base, 1, 16, base, base
+        d.n_envs, d.horizon, d.flags, d.chunk = 128, 400, _native.F_OUT_CODES | _native.F_ACT_PACKED, 8
+        for b in range(2):
+            d.d_actions[b], d.d_events[b] = base, base
+        for k, v in kw.items():
+            if isinstance(v, tuple):
+                getattr(d, k)[v[0]] = v[1]
+            else:
+                setattr(d, k, v)
+        h = ctypes.c_void_p()
+        rc = lib.ovc_pipeline_create(ctypes.byref(d), ctypes.byref(h))
+        return rc, lib.ovc_last_error().decode(), h
+
+    for kw, msg in (({"chunk": 0}, "chunk must be >= 1"), ({"state_words": 24}, "state_words"), ({"n_layouts": 0}, "n_layouts"),
+                    ({"n_envs": -1}, "negative n_envs"), ({"state": base + 4}, "16-byte aligned"),
+                    ({"d_events": (1, None)}, "missing device staging buffer"), ({"d_actions": (0, None)}, "missing device staging buffer"),
+                    ({"flags": _native.F_OUT_PACKED}, "missing device staging buffer")):  # packed also needs sparse / shaped
+        rc, err, h = create(**kw)
+        assert rc != 0 and msg in err and not h.value, (kw, rc, err)
+    assert lib.ovc_pipeline_run(None, base, None, None, None, base, 1, None, 1, None) != 0
+    assert lib.ovc_pipeline_wait(None, 0) != 0 and lib.ovc_pipeline_join(None, None) != 0
+    lib.ovc_pipeline_destroy(None)
