@@ -159,6 +159,25 @@ def _resolve(conf, recipe, scalar_key, map_key, onion_key, tomato_key):
     return 20
 
 
+def _check_recipe_config(conf):
+    """The validity rules of Recipe.configure (overcooked_mdp.py:236-300): ValueError for a half-specified
+    ingredient pair, for two mechanisms setting the same quantity, and for per-recipe lists that do not line
+    up with the order list.  Like the reference, the rules look at which KEYS are present."""
+    for kind in ("time", "value"):
+        if ("tomato_" + kind in conf) != ("onion_" + kind in conf):
+            raise ValueError("Must specify both 'onion_%s' and 'tomato_%s'" % (kind, kind))
+    for ingredient_key, scalar_key, list_key in (("tomato_value", "delivery_reward", "recipe_values"),
+                                                 ("tomato_time", "cook_time", "recipe_times")):
+        for a, b in ((ingredient_key, scalar_key), (ingredient_key, list_key), (list_key, scalar_key)):
+            if a in conf and b in conf:
+                raise ValueError("%r is incompatible with %r" % (b, a))
+        if list_key in conf:
+            if not conf.get("all_orders"):
+                raise ValueError("Must specify 'all_orders' if %r is specified" % list_key)
+            if len(conf["all_orders"]) != len(conf[list_key]):
+                raise ValueError("Number of recipes in 'all_orders' must be the same as number in %r" % list_key)
+
+
 def _as_int(v, what):
     if isinstance(v, bool) or not (isinstance(v, (int, np.integer)) or (isinstance(v, float) and v.is_integer())):
         raise ValueError(
@@ -233,6 +252,7 @@ class CompiledLayout(object):
 
         # ---- recipe tables ----
         conf = self.recipe_config
+        _check_recipe_config(conf)
         all_set = set(_recipe_from_order(o) for o in self.start_all_orders)
         bonus_set = set(_recipe_from_order(o) for o in self.start_bonus_orders)
         self.cook_time = np.zeros(16, np.int64)

@@ -325,3 +325,25 @@ def test_pipeline_descriptor_layout_matches_the_c_struct():
     assert lib.ovc_pipeline_run(None, base, None, None, None, base, 1, None, 1, None) != 0
     assert lib.ovc_pipeline_wait(None, 0) != 0 and lib.ovc_pipeline_join(None, None) != 0
     lib.ovc_pipeline_destroy(None)
+
+
+def test_recipe_config_validity_rules():
+    """Recipe.configure's rules (overcooked_mdp.py:236-300) as restated in layout._check_recipe_config; the verdicts
+    below are the reference's (tests/test_oracle_live_reference.py checks them live where the reference is present)."""
+    orders = [{"ingredients": ["onion", "onion", "onion"]}]
+    bad = [
+        {"onion_value": 3}, {"tomato_time": 4}, {"onion_value": 3, "tomato_value": 2, "delivery_reward": 9},
+        {"onion_value": 3, "tomato_value": 2, "recipe_values": [5], "start_all_orders": orders},
+        {"recipe_values": [5], "delivery_reward": 9, "start_all_orders": orders},
+        {"onion_time": 3, "tomato_time": 2, "cook_time": 9},
+        {"onion_time": 3, "tomato_time": 2, "recipe_times": [5], "start_all_orders": orders},
+        {"recipe_times": [5], "cook_time": 9, "start_all_orders": orders},
+        {"recipe_values": [5]}, {"recipe_times": [5, 6], "start_all_orders": orders},
+    ]
+    for kw in bad:
+        with pytest.raises(ValueError):
+            L.compile_layout("cramped_room", **kw)
+    ok = L.compile_layout("cramped_room", recipe_values=[5], recipe_times=[7], start_all_orders=orders)
+    assert ok.deliver_value[12] == 5 and ok.cook_time[12] == 7
+    ok = L.compile_layout("cramped_room", onion_value=3, tomato_value=2, onion_time=4, tomato_time=5)
+    assert ok.base_value[12] == 9 and ok.cook_time[6] == 13  # 3 onions; 1 onion + 2 tomatoes

@@ -81,14 +81,18 @@ def _differential(ns, m, cl, name):
         holder = refboot.LitePlannerHolder(ns, m)
         lut = cl.feature_lut().view(np.uint8).reshape(1, -1)
         pt, cst, gpow = L.build_potential_tables([cl], 0.99)
-    seed = sum(map(ord, name))
+    # OVC_FUZZ_EPISODES / OVC_FUZZ_STEPS / OVC_FUZZ_SEED scale this into a fuzzing campaign (defaults: 6 x 60, seed 0)
+    import os
+
+    episodes, steps = int(os.environ.get("OVC_FUZZ_EPISODES", "6")), int(os.environ.get("OVC_FUZZ_STEPS", "60"))
+    seed = sum(map(ord, name)) + int(os.environ.get("OVC_FUZZ_SEED", "0"))
     np.random.seed(seed)
     rng = np.random.RandomState(seed)
     fn = m.get_random_start_state_fn(random_start_pos=True, rnd_obj_prob_thresh=0.6)
     n_obs = 0
-    for ep in range(6):
+    for ep in range(episodes):
         st = fn() if ep else m.get_standard_start_state()
-        for t in range(60):
+        for t in range(steps):
             a = rng.randint(0, 6, size=2)
             if rng.rand() < 0.4:
                 a[rng.randint(2)] = 5
@@ -109,4 +113,91 @@ def _differential(ns, m, cl, name):
             assert np.array_equal(rec[0], want), (name, ep, t, ja)
             assert sp[0] == sum(infos["sparse_reward_by_agent"]) and sh[0].tolist() == list(infos["shaped_reward_by_agent"])
             assert [int(ev[0, 0]) & 0x1FFFFFF, int(ev[0, 1]) & 0x1FFFFFF] == [_events_mask(ns, infos, 0), _events_mask(ns, infos, 1)]
-    assert n_obs == 36
+    assert n_obs == episodes * ((steps + 9) // 10)
+
+
+def _random_mdp_params(rng):
+    """A random, valid set of MDP parameter overrides (orders, bonus orders, recipe values / times by any of the
+    reference's three mechanisms, order bonus, shaping rewards, old dynamics)."""
+    onion, tomato = "onion", "tomato"
+    recipes = [[onion], [tomato], [onion, onion], [onion, tomato], [tomato, tomato], [onion] * 3, [onion, onion, tomato],
+               [onion, tomato, tomato], [tomato] * 3]
+    p = {}
+    old = rng.rand() < 0.25
+    pool = [r for r in recipes if len(r) == 3] if old else recipes
+    k = rng.randint(1, len(pool) + 1)
+    orders = [pool[i] for i in sorted(rng.choice(len(pool), k, replace=False))]
+    p["start_all_orders"] = [{"ingredients": list(r)} for r in orders]
+    p["start_bonus_orders"] = []  # always overridden: a layout's own bonus orders need not be among the new orders
+    if rng.rand() < 0.5:
+        nb = rng.randint(1, len(orders) + 1)
+        p["start_bonus_orders"] = [{"ingredients": list(orders[i])} for i in sorted(rng.choice(len(orders), nb, replace=False))]
+        p["order_bonus"] = int(rng.choice([2, 3, 5]))
+    mech = rng.randint(4)
+    if mech == 0:
+        p["recipe_values"] = [int(v) for v in rng.randint(1, 60, size=len(orders))]
+        p["recipe_times"] = [int(v) for v in rng.randint(1, 30, size=len(orders))]
+    elif mech == 1:
+        p["onion_value"], p["tomato_value"] = int(rng.randint(1, 25)), int(rng.randint(1, 25))
+        p["onion_time"], p["tomato_time"] = int(rng.randint(1, 12)), int(rng.randint(1, 12))
+    elif mech == 2:
+        p["delivery_reward"], p["cook_time"] = int(rng.randint(1, 50)), int(rng.randint(1, 25))
+    if rng.rand() < 0.5:
+        p["rew_shaping_params"] = {"PLACEMENT_IN_POT_REW": int(rng.randint(0, 9)), "DISH_PICKUP_REWARD": int(rng.randint(0, 9)),
+                                   "SOUP_PICKUP_REWARD": int(rng.randint(0, 9)), "DISH_DISP_DISTANCE_REW": 0,
+                                   "POT_DISTANCE_REW": 0, "SOUP_DISTANCE_REW": 0}
+    if old:
+        p["old_dynamics"] = True
+    return p
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_mdp_parameters_against_live_reference(seed):
+    """Parameter overrides of from_layout_name (overcooked_mdp.py:1090-1172: orders, bonus orders, the three ways to
+    set recipe values / times, order bonus, shaping rewards, old dynamics): same differential run as above."""
+    import copy
+
+    ns = refboot.boot()
+    rng = np.random.RandomState(1000 + seed)
+    name = ["cramped_room", "counter_circuit", "asymmetric_advantages", "cramped_room_tomato"][seed % 4]
+    if name not in ALL_LAYOUTS:
+        name = "cramped_room"
+    params = _random_mdp_params(rng)
+    try:
+        m = refboot.make_mdp(ns, name, **copy.deepcopy(params))
+    except ValueError:  # e.g. a scalar override on a layout that prices recipes per ingredient: same verdict here
+        with pytest.raises(ValueError):
+            L.compile_layout(name, **copy.deepcopy(params))
+        return
+    cl = L.compile_layout(name, **copy.deepcopy(params))
+    _differential(ns, m, cl, "%s-params-%d" % (name, seed))
+
+
+def test_recipe_config_conflicts_raise_like_the_reference():
+    """Recipe.configure's validity rules (overcooked_mdp.py:236-300) on every pair of mechanisms."""
+    ns = refboot.boot()
+    orders = [{"ingredients": ["onion", "onion", "onion"]}]
+    cases = [
+        {"onion_value": 3}, {"tomato_time": 4}, {"onion_value": 3, "tomato_value": 2, "delivery_reward": 9},
+        {"onion_value": 3, "tomato_value": 2, "recipe_values": [5], "start_all_orders": orders},
+        {"recipe_values": [5], "delivery_reward": 9, "start_all_orders": orders},
+        {"onion_time": 3, "tomato_time": 2, "cook_time": 9},
+        {"onion_time": 3, "tomato_time": 2, "recipe_times": [5], "start_all_orders": orders},
+        {"recipe_times": [5], "cook_time": 9, "start_all_orders": orders},
+        {"recipe_values": [5]}, {"recipe_times": [5, 6], "start_all_orders": orders},
+        {"recipe_values": [5], "recipe_times": [7], "start_all_orders": orders},  # valid
+        {"onion_value": 3, "tomato_value": 2, "onion_time": 4, "tomato_time": 5},  # valid
+    ]
+    for kw in cases:
+        import copy
+
+        try:
+            refboot.make_mdp(ns, "cramped_room", **copy.deepcopy(kw))
+            ok = True
+        except ValueError:
+            ok = False
+        if ok:
+            L.compile_layout("cramped_room", **copy.deepcopy(kw))
+        else:
+            with pytest.raises(ValueError):
+                L.compile_layout("cramped_room", **copy.deepcopy(kw))
