@@ -338,11 +338,12 @@ def test_recipe_config_validity_rules():
         {"onion_time": 3, "tomato_time": 2, "cook_time": 9},
         {"onion_time": 3, "tomato_time": 2, "recipe_times": [5], "start_all_orders": orders},
         {"recipe_times": [5], "cook_time": 9, "start_all_orders": orders},
-        {"recipe_values": [5]}, {"recipe_times": [5, 6], "start_all_orders": orders},
+        {"recipe_values": [5, 6]}, {"recipe_times": [5, 6], "start_all_orders": orders},
     ]
     for kw in bad:
         with pytest.raises(ValueError):
             L.compile_layout("cramped_room", **kw)
+    assert L.compile_layout("cramped_room", recipe_values=[5]).deliver_value[12] == 5  # the layout file's one order
     ok = L.compile_layout("cramped_room", recipe_values=[5], recipe_times=[7], start_all_orders=orders)
     assert ok.deliver_value[12] == 5 and ok.cook_time[12] == 7
     ok = L.compile_layout("cramped_room", onion_value=3, tomato_value=2, onion_time=4, tomato_time=5)
