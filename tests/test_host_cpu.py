@@ -347,4 +347,4 @@ def test_recipe_config_validity_rules():
     ok = L.compile_layout("cramped_room", recipe_values=[5], recipe_times=[7], start_all_orders=orders)
     assert ok.deliver_value[12] == 5 and ok.cook_time[12] == 7
     ok = L.compile_layout("cramped_room", onion_value=3, tomato_value=2, onion_time=4, tomato_time=5)
-    assert ok.base_value[12] == 9 and ok.cook_time[6] == 13  # 3 onions; 1 onion + 2 tomatoes
+    assert ok.base_value[12] == 9 and ok.cook_time[6] == 14  # 3 onions: 3 * 3; 1 onion + 2 tomatoes: 4 + 2 * 5
