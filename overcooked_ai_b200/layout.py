@@ -187,6 +187,31 @@ def _as_int(v, what):
     return int(v)
 
 
+def assert_valid_grid(grid):
+    """The grid rules of OvercookedGridworld._assert_valid_grid (overcooked_mdp.py:2064-2115), AssertionError like the
+    reference and checked in its order: not ragged; no free cell (or player) on the border; players numbered
+    1..n without gaps; known characters only; at least one dish dispenser, serving cell, pot and ingredient dispenser."""
+    width = len(grid[0])
+    assert all(len(row) == width for row in grid), "Ragged grid"
+    solid = "XOPDST"
+    for row in grid:
+        assert row[0] in solid, "Left border must not be free"
+        assert row[-1] in solid, "Right border must not be free"
+    for x in range(width):
+        assert grid[0][x] in solid, "Top border must not be free"
+        assert grid[-1][x] in solid, "Bottom border must not be free"
+    cells = [c for row in grid for c in row]
+    digits = sorted(int(c) for c in cells if c in "123456789")
+    assert len(digits) > 0, "No players (digits) in grid"
+    assert digits == list(range(1, len(digits) + 1)), "Some players were missing"
+    assert all(c in "XOPDST123456789 " for c in cells), "Invalid character in grid"
+    assert cells.count("1") == 1, "'1' must be present exactly once"
+    assert cells.count("D") >= 1, "'D' must be present at least once"
+    assert cells.count("S") >= 1, "'S' must be present at least once"
+    assert cells.count("P") >= 1, "'P' must be present at least once"
+    assert cells.count("O") >= 1 or cells.count("T") >= 1, "'O' or 'T' must be present at least once"
+
+
 class CompiledLayout(object):
     """One layout, compiled.  Attributes mirror what the reference's OvercookedGridworld keeps
     (terrain_mtx, start_player_positions, start_all_orders, ... overcooked_mdp.py:1090-1148)."""
@@ -196,7 +221,7 @@ class CompiledLayout(object):
         self.layout_name = layout_name
         grid = [list(row) for row in grid]
         self.height, self.width = len(grid), len(grid[0])
-        assert all(len(r) == self.width for r in grid), "Ragged grid"
+        assert_valid_grid(grid)
         if self.width > 16 or self.height > 16:
             raise ValueError("grid %dx%d exceeds the 16x16 pos-byte range" % (self.width, self.height))
         players = {}

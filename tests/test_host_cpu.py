@@ -348,3 +348,30 @@ def test_recipe_config_validity_rules():
     assert ok.deliver_value[12] == 5 and ok.cook_time[12] == 7
     ok = L.compile_layout("cramped_room", onion_value=3, tomato_value=2, onion_time=4, tomato_time=5)
     assert ok.base_value[12] == 9 and ok.cook_time[6] == 14  # 3 onions: 3 * 3; 1 onion + 2 tomatoes: 4 + 2 * 5
+
+
+def test_grid_validity_rules():
+    """OvercookedGridworld._assert_valid_grid (overcooked_mdp.py:2064-2115): AssertionError, the reference's messages."""
+    from overcooked_ai_b200.mdp import OvercookedGridworld
+
+    ok = ["XXPXX", "O  2O", "X1  X", "XDXSX"]
+    OvercookedGridworld.from_grid(ok)
+    cases = [
+        (["XXPXX", "O  2", "X1  X", "XDXSX"], "Ragged grid"),
+        (["XXPXX", "   2O", "X1  X", "XDXSX"], "Left border must not be free"),
+        (["XXPXX", "O  2 ", "X1  X", "XDXSX"], "Right border must not be free"),
+        (["XX XX", "O  2O", "X1  X", "XDXSX"], "Top border must not be free"),
+        (["XXPXX", "O  2O", "X1  X", "XD1SX"], "Bottom border must not be free"),
+        (["XXPXX", "O   O", "X   X", "XDXSX"], "No players (digits) in grid"),
+        (["XXPXX", "O  3O", "X1  X", "XDXSX"], "Some players were missing"),
+        (["XXPXX", "O ?2O", "X1  X", "XDXSX"], "Invalid character in grid"),
+        (["XXPXX", "O  2O", "X1  X", "XXXSX"], "'D' must be present at least once"),
+        (["XXPXX", "O  2O", "X1  X", "XDXXX"], "'S' must be present at least once"),
+        (["XXXXX", "O  2O", "X1  X", "XDXSX"], "'P' must be present at least once"),
+        (["XXPXX", "X  2X", "X1  X", "XDXSX"], "'O' or 'T' must be present at least once"),
+    ]
+    for grid, msg in cases:
+        with pytest.raises(AssertionError, match=msg.replace("(", r"\(").replace(")", r"\)")):
+            OvercookedGridworld.from_grid(grid)
+    with pytest.raises(ValueError):  # valid for the reference, outside this engine: the batched game is the 2-player game
+        OvercookedGridworld.from_grid(["XXPXX", "O   O", "X1  X", "XDXSX"])

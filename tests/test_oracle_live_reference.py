@@ -201,3 +201,29 @@ def test_recipe_config_conflicts_raise_like_the_reference():
         else:
             with pytest.raises(ValueError):
                 L.compile_layout("cramped_room", **copy.deepcopy(kw))
+
+
+def test_grid_validity_rules_against_live_reference():
+    """Same grids, same verdict and message as OvercookedGridworld.from_grid (overcooked_mdp.py:1175-1187, 2064-2115)."""
+    from overcooked_ai_b200.mdp import OvercookedGridworld
+
+    ns = refboot.boot()
+    grids = [
+        ["XXPXX", "O  2O", "X1  X", "XDXSX"], ["XXPXX", "O  2", "X1  X", "XDXSX"], ["XXPXX", "   2O", "X1  X", "XDXSX"],
+        ["XXPXX", "O  2 ", "X1  X", "XDXSX"], ["XX XX", "O  2O", "X1  X", "XDXSX"], ["XXPXX", "O  2O", "X1  X", "XD1SX"],
+        ["XXPXX", "O   O", "X   X", "XDXSX"], ["XXPXX", "O  3O", "X1  X", "XDXSX"], ["XXPXX", "O ?2O", "X1  X", "XDXSX"],
+        ["XXPXX", "O  2O", "X1  X", "XXXSX"], ["XXPXX", "O  2O", "X1  X", "XDXXX"], ["XXXXX", "O  2O", "X1  X", "XDXSX"],
+        ["XXPXX", "X  2X", "X1  X", "XDXSX"], ["XTPXX", "X  2X", "X1  X", "XDXSX"],
+    ]
+    for g in grids:
+        try:
+            ns.mdp.OvercookedGridworld.from_grid(g)
+            want = None
+        except AssertionError as e:
+            want = str(e)
+        try:
+            OvercookedGridworld.from_grid(g)
+            got = None
+        except AssertionError as e:
+            got = str(e)
+        assert got == want, (g, got, want)
