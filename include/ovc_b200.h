@@ -275,8 +275,10 @@ int ovc_step(const void *layouts, int n_layouts, const int32_t *start_records, i
 
 /*
  * T consecutive transitions in ONE launch (the record stays on chip between transitions).
- * actions int32[T][n_envs][2]; sparse/done int32[T][n_envs]; shaped/events int32[T][n_envs][2].
- * Semantically identical to T calls of ovc_step with the same flags.
+ * actions int32[T][n_envs][2]; sparse/done int32[T][n_envs]; shaped/events int32[T][n_envs][2] — or the narrower
+ * element types the OVC_F_ACT_* / OVC_F_OUT_* flags select (pointers are then reinterpreted; outputs a format does
+ * not produce may be NULL).  Semantically identical to T calls of ovc_step with the same flags.
+ * One pipeline object is driven by one host thread at a time.
  */
 int ovc_rollout(const void *layouts, int n_layouts, const int32_t *start_records, int32_t *state,
                 const int32_t *actions, int32_t *sparse, int32_t *shaped, int32_t *done,
