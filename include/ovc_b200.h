@@ -278,7 +278,6 @@ int ovc_step(const void *layouts, int n_layouts, const int32_t *start_records, i
  * actions int32[T][n_envs][2]; sparse/done int32[T][n_envs]; shaped/events int32[T][n_envs][2] — or the narrower
  * element types the OVC_F_ACT_* / OVC_F_OUT_* flags select (pointers are then reinterpreted; outputs a format does
  * not produce may be NULL).  Semantically identical to T calls of ovc_step with the same flags.
- * One pipeline object is driven by one host thread at a time.
  */
 int ovc_rollout(const void *layouts, int n_layouts, const int32_t *start_records, int32_t *state,
                 const int32_t *actions, int32_t *sparse, int32_t *shaped, int32_t *done,
@@ -294,6 +293,7 @@ int ovc_rollout(const void *layouts, int n_layouts, const int32_t *start_records
  * outputs device->host, the three stages on their own streams and overlapped across chunks AND across successive
  * calls.  Element formats follow `flags` exactly as in ovc_rollout (OVC_F_ACT_U8 / OVC_F_ACT_PACKED,
  * OVC_F_OUT_NARROW / OVC_F_OUT_PACKED / OVC_F_OUT_CODES); output pointers a format does not use may be NULL.
+ * One pipeline object is driven by one host thread at a time.
  */
 typedef struct ovc_pipeline ovc_pipeline_t;
 typedef struct ovc_pipeline_desc {
