@@ -194,3 +194,35 @@ def test_gym_wrapper_single_env():
         assert base.state.players[1 - gym.agent_idx].orientation == Direction.NORTH
     with pytest.raises(AssertionError):
         gym.step((7, 0))
+
+
+@pytest.mark.parametrize("seed", [0, 2, 7])
+def test_baseline_config_1_through_the_dropin_env(seed):
+    """BASELINE config 1: cramped_room, ONE environment, horizon 400, standard start, uniform random joint
+    actions from the documented counter-based stream — the reference's OvercookedEnv trace (fixture) against the
+    drop-in OvercookedEnv: every state, reward, done flag, and the episode info handed out with the last step."""
+    import json
+
+    from overcooked_ai_b200.actions import Action
+
+    tr = Trace(GOLD + "/trace_config1_cramped_room.npz")
+    want_info = json.loads(str(tr.data["episode_info"]))[seed]
+    mdp = OvercookedGridworld.from_layout_name("cramped_room")
+    env = OvercookedEnv.from_mdp(mdp, horizon=400, info_level=0)
+    assert np.array_equal(L.pack_state(mdp.compiled, env.state, 0, tr.S), tr.states[seed, 0])
+    for t in range(400):
+        ja = tuple(Action.INDEX_TO_ACTION[int(a)] for a in tr.actions[seed, t])
+        nxt, r, done, info = env.step(ja)
+        assert np.array_equal(L.pack_state(mdp.compiled, nxt, 0, tr.S), tr.states[seed, t + 1]), t
+        assert r == int(tr.sparse2[seed, t].sum()) and list(info["sparse_r_by_agent"]) == tr.sparse2[seed, t].tolist()
+        assert list(info["shaped_r_by_agent"]) == tr.shaped[seed, t].tolist()
+        assert done == (t == 399) and ("episode" in info) == done
+    ep = info["episode"]
+    assert ep["ep_length"] == want_info["ep_length"] == 400
+    assert int(ep["ep_sparse_r"]) == want_info["ep_sparse_r"] and int(ep["ep_shaped_r"]) == want_info["ep_shaped_r"]
+    assert [int(v) for v in ep["ep_sparse_r_by_agent"]] == want_info["ep_sparse_r_by_agent"]
+    assert [int(v) for v in ep["ep_shaped_r_by_agent"]] == want_info["ep_shaped_r_by_agent"]
+    for name, lists in want_info["game_stats"].items():
+        assert [list(map(int, l)) for l in ep["ep_game_stats"][name]] == lists, name
+    with pytest.raises(AssertionError):  # overcooked_env.py:255
+        env.step(ja)

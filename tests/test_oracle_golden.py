@@ -211,3 +211,38 @@ def test_random_start_states_are_valid_and_follow_the_reference_distribution():
     state2 = np.zeros((8, S), np.int32)
     cpu.reset_random(tab, starts, state2, cpu.random_start(5, 0.0, False))
     assert np.array_equal(state2[:, :3], np.repeat(starts[:, :3], 8, 0))
+
+
+def _philox4x32_10(key, c0, c1, c2, c3):
+    k0, k1 = key & 0xFFFFFFFF, (key >> 32) & 0xFFFFFFFF
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c0, 0xCD9E8D57 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & 0xFFFFFFFF, p1 & 0xFFFFFFFF, ((p0 >> 32) ^ c3 ^ k1) & 0xFFFFFFFF, p0 & 0xFFFFFFFF
+        k0, k1 = (k0 + 0x9E3779B9) & 0xFFFFFFFF, (k1 + 0xBB67AE85) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def test_baseline_config_1_trace_and_episode_info():
+    """BASELINE config 1: the fixture's actions are the documented counter-based stream (Philox4x32-10, key = seed,
+    counter (env id, t), word = agent, scaled by multiply-high), and the oracle's outputs over the 400 transitions
+    add up to the episode info the reference's OvercookedEnv reports (overcooked_env.py:363-401)."""
+    tr = Trace(GOLD + "/trace_config1_cramped_room.npz")
+    infos = json.loads(str(tr.data["episode_info"]))
+    assert tr.E == 8 and tr.T == 400 and (tr.states[:, 0] == tr.starts[0]).all() and (tr.states[:, -1, 0] == 400).all()
+    for seed in range(8):
+        for t in (0, 1, 57, 399):
+            v = _philox4x32_10(seed, 0, t, 0, 0)
+            assert tr.actions[seed, t].tolist() == [(v[0] * 6) >> 32, (v[1] * 6) >> 32]
+    st = np.ascontiguousarray(tr.states[:, 0])
+    acts = np.ascontiguousarray(tr.actions.transpose(1, 0, 2))
+    sparse, shaped, done, events = cpu.rollout(tr.tables, tr.starts, st, acts, horizon=400, flags=0)
+    assert np.array_equal(st, tr.states[:, -1]) and done[-1].all() and not done[:-1].any()
+    val = tr.layout.deliver_value
+    for seed, info in enumerate(infos):
+        ev = events[:, seed]
+        by_agent = (val[(ev >> 25) & 15] * ((ev >> 15) & 1)).sum(0)
+        assert by_agent.tolist() == info["ep_sparse_r_by_agent"] and int(sparse[:, seed].sum()) == info["ep_sparse_r"]
+        assert shaped[:, seed].sum(0).tolist() == info["ep_shaped_r_by_agent"] and info["ep_length"] == 400
+        for i, name in enumerate(L.EVENT_TYPES):
+            for agent in range(2):
+                assert np.nonzero((ev[:, agent] >> i) & 1)[0].tolist() == info["game_stats"][name][agent], (seed, name)

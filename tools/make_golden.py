@@ -173,6 +173,80 @@ def gen_traces(ns, name, layout, params, episodes, steps, seed):
         name, episodes, steps, S, int(np.stack(all_sparse).sum()), cover))
 
 
+def philox4x32_10(key, c0, c1, c2, c3):
+    """Philox4x32-10 (the generator of include/ovc_b200.h's random start states), plain Python integers."""
+    k0, k1 = key & 0xFFFFFFFF, (key >> 32) & 0xFFFFFFFF
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c0, 0xCD9E8D57 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & 0xFFFFFFFF, p1 & 0xFFFFFFFF, ((p0 >> 32) ^ c3 ^ k1) & 0xFFFFFFFF, p0 & 0xFFFFFFFF
+        k0, k1 = (k0 + 0x9E3779B9) & 0xFFFFFFFF, (k1 + 0xBB67AE85) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def config1_actions(seed, T=400, env_id=0):
+    """BASELINE config 1 / SURVEY 8d: a[t, agent] uniform in 0..5 from a counter-based generator keyed by the seed,
+    counter (env id, t): word `agent` of the block, scaled by multiply-high."""
+    a = np.zeros((T, 2), np.int32)
+    for t in range(T):
+        v = philox4x32_10(seed, env_id, t, 0, 0)
+        a[t] = [(v[0] * 6) >> 32, (v[1] * 6) >> 32]
+    return a
+
+
+def gen_config1(ns):
+    """BASELINE config 1: cramped_room, ONE environment, horizon 400, standard start state, uniform random joint actions
+    (seeds 0..7), stepped through the reference's OvercookedEnv: every state / reward / event flag, and the episode
+    info the env hands out with the last transition."""
+    m = refboot.make_mdp(ns, "cramped_room")
+    refboot.use_mdp(ns, m)
+    cl = L.compile_layout("cramped_room")
+    S, T = cl.state_words, 400
+    holder = refboot.LitePlannerHolder(ns, m)
+    states, actions, sparse, shaped, events, infos_out = [], [], [], [], [], []
+    obs_states, obs_lossless, obs_feat = [], [], {0: [], 1: [], 2: [], 3: []}
+    sample = {}
+    for seed in range(8):
+        env = refboot.make_env(ns, m, horizon=T)
+        env._mp = object()
+        acts = config1_actions(seed, T)
+        st_arr = np.zeros((T + 1, S), np.int32)
+        sp, sh, ev = np.zeros((T, 2), np.int32), np.zeros((T, 2), np.int32), np.zeros((T, 2), np.int32)
+        st_arr[0] = pack_ref(cl, env.state, S)
+        for t in range(T):
+            ja = tuple(ns.actions.Action.INDEX_TO_ACTION[int(a)] for a in acts[t])
+            prev = env.state
+            _, mdp_infos = m.get_state_transition(prev, ja)  # for the event flags (the env keeps only their timesteps)
+            nxt, r, done, info = env.step(ja)
+            st_arr[t + 1] = pack_ref(cl, nxt, S)
+            sp[t], sh[t] = info["sparse_r_by_agent"], info["shaped_r_by_agent"]
+            ev[t] = [events_mask(ns, mdp_infos, 0), events_mask(ns, mdp_infos, 1)]
+            assert r == sum(info["sparse_r_by_agent"]) and done == (t == T - 1)
+            if seed < 3 and t in (0, 150, 399):
+                sample["%d:%d" % (seed, t)] = jsonable(prev.to_dict())
+            if t % 25 == 0:
+                obs_states.append(st_arr[t])
+                obs_lossless.append(np.stack(m.lossless_state_encoding(prev, horizon=T)).astype(np.int16))
+                for npots in obs_feat:
+                    obs_feat[npots].append(np.stack(m.featurize_state(prev, holder, num_pots=npots)))
+        ep = info["episode"]
+        infos_out.append({
+            "ep_sparse_r": int(ep["ep_sparse_r"]), "ep_shaped_r": int(ep["ep_shaped_r"]),
+            "ep_sparse_r_by_agent": [int(v) for v in ep["ep_sparse_r_by_agent"]],
+            "ep_shaped_r_by_agent": [int(v) for v in ep["ep_shaped_r_by_agent"]], "ep_length": int(ep["ep_length"]),
+            "game_stats": {k: [[int(x) for x in lst] for lst in v] for k, v in ep["ep_game_stats"].items()
+                           if k in ns.mdp.EVENT_TYPES},
+        })
+        states.append(st_arr), actions.append(acts), sparse.append(sp), shaped.append(sh), events.append(ev)
+    out = dict(layout="cramped_room", params=json.dumps({}), horizon=T, states=np.stack(states), actions=np.stack(actions),
+               sparse=np.stack(sparse), shaped=np.stack(shaped), events=np.stack(events), to_dict_sample=json.dumps(sample),
+               obs_states=np.stack(obs_states), obs_lossless=np.stack(obs_lossless), episode_info=json.dumps(infos_out))
+    for npots, v in obs_feat.items():
+        out["obs_feat_%d" % npots] = np.stack(v).astype(np.int16)
+    np.savez_compressed(os.path.join(GOLD, "trace_config1_cramped_room.npz"), **out)
+    print("trace_config1_cramped_room: 8 seeds x %d steps, shaped sums %s, sparse sums %s" % (
+        T, [i["ep_shaped_r"] for i in infos_out], [i["ep_sparse_r"] for i in infos_out]))
+
+
 def gen_greedy_cramped_room(ns):
     """The reference's featurisation goldens (testing/overcooked_test.py:1005-1093): 5 seeded
     GreedyHumanModel self-play games on cramped_room; expected.pickle / expected_{0,1,2}.pickle."""
@@ -396,6 +470,8 @@ def main():
         gen_human_2020(ns)
     if not only or "potential" in only:
         gen_potential(ns)
+    if not only or "config1" in only:
+        gen_config1(ns)
     if not only or "layoutgen" in only:
         gen_layoutgen(ns)
     print("done in %.1fs" % (time.time() - t0))
