@@ -11,6 +11,9 @@ for API compatibility and parity testing; one launch + sync per call cannot beat
 Error behaviour follows the reference: ``ValueError`` for an illegal action (:1394-1398),
 ``AssertionError`` for an invalid state (_check_valid_state :1910-1949).
 """
+import itertools
+from collections import defaultdict
+
 import numpy as np
 import torch
 
@@ -18,7 +21,7 @@ from overcooked_ai_b200 import layout as L
 from overcooked_ai_b200.actions import Action
 from overcooked_ai_b200.batched import BatchedOvercookedEnv
 from overcooked_ai_b200.layout import EVENT_TYPES
-from overcooked_ai_b200.state import OvercookedState
+from overcooked_ai_b200.state import ObjectState, OvercookedState, SoupState
 
 
 class OvercookedGridworld(object):
@@ -85,6 +88,73 @@ class OvercookedGridworld(object):
 
     def get_standard_start_state(self):
         return self.compiled.get_standard_start_state()
+
+    def get_valid_joint_player_positions(self):
+        """All ordered tuples of distinct floor cells, in itertools.product order (:1736-1747)."""
+        cells = self.get_valid_player_positions()
+        return [j for j in itertools.product(cells, repeat=self.num_players) if len(set(j)) == len(j)]
+
+    def get_pot_states(self, state):
+        """{'empty' | '<k>_items' | 'cooking' | 'ready': [pot positions]} (:1809-1838)."""
+        out = defaultdict(list)
+        for pos in self.get_pot_locations():
+            if not state.has_object(pos):
+                out["empty"].append(pos)
+                continue
+            soup = state.get_object(pos)
+            assert soup.name == "soup", "soup at %s is not a soup but a %s" % (pos, soup.name)
+            tick, ct = soup._cooking_tick, self.compiled.soup_cook_time(soup) if soup._cooking_tick >= 0 else None
+            if tick >= 0 and tick >= ct:
+                out["ready"].append(pos)
+            elif tick >= 0:
+                out["cooking"].append(pos)
+            else:
+                out["%d_items" % len(soup.ingredients)].append(pos)
+        return out
+
+    def get_actions(self, state):
+        """Every action is legal for every player in every (valid) state (:1273-1288)."""
+        L.pack_state(self.compiled, state, 0, self.compiled.state_words)  # _check_valid_state: AssertionError if invalid
+        return [list(Action.ALL_ACTIONS) for _ in state.players]
+
+    def get_random_start_state_fn(self, random_start_pos=False, rnd_obj_prob_thresh=0.0):
+        """The host form of the reference's randomised start states (:1307-1369), for the drop-in
+        ``OvercookedEnv(start_state_fn=...)``: numpy's GLOBAL generator is called exactly as the reference calls it
+        (one ``choice`` for the joint position; per empty pot ``rand``, then ``randint`` x2 and ``rand`` if it fills;
+        per player ``rand``, then ``choice(p=[.2, .6, .2])`` and ``randint`` x2 if it holds something), so a seeded run
+        starts from the reference's states.  (The batched engine draws on the device instead: ovc_random_start_t.)"""
+        cook_time = self.compiled.cook_time
+
+        def start_state_fn():
+            if random_start_pos:
+                valid_positions = self.get_valid_joint_player_positions()
+                start_pos = valid_positions[np.random.choice(len(valid_positions))]
+            else:
+                start_pos = self.start_player_positions
+            start_state = OvercookedState.from_player_positions(
+                start_pos, bonus_orders=self.start_bonus_orders, all_orders=self.start_all_orders)
+            if rnd_obj_prob_thresh == 0:
+                return start_state
+            for pot_loc in self.get_pot_states(start_state)["empty"]:
+                if np.random.rand() < rnd_obj_prob_thresh:
+                    n = int(np.random.randint(low=1, high=4))
+                    m = int(np.random.randint(low=0, high=4 - n))
+                    cooking_tick = 0 if np.random.rand() < rnd_obj_prob_thresh else -1
+                    start_state.objects[pot_loc] = SoupState.get_soup(
+                        pot_loc, num_onions=n, num_tomatoes=m, cooking_tick=cooking_tick, cook_time=int(cook_time[n * 4 + m]))
+            for player in start_state.players:
+                if np.random.rand() < rnd_obj_prob_thresh:
+                    obj = np.random.choice(["dish", "onion", "soup"], p=[0.2, 0.6, 0.2])
+                    n = int(np.random.randint(low=1, high=4))
+                    m = int(np.random.randint(low=0, high=4 - n))
+                    if obj == "soup":
+                        player.set_object(SoupState.get_soup(player.position, num_onions=n, num_tomatoes=m, finished=True,
+                                                             cook_time=int(cook_time[n * 4 + m])))
+                    else:
+                        player.set_object(ObjectState(str(obj), player.position))
+            return start_state
+
+        return start_state_fn
 
     def soup_cook_time(self, soup):
         return self.compiled.soup_cook_time(soup)

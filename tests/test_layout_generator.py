@@ -143,3 +143,30 @@ def test_layout_redraw_mirror_is_uniform_deterministic_and_per_episode():
     for _ in range(3):
         cpu.reset_random(tab, starts, chk, rs)
     assert np.array_equal(st[:, 3] & ~0xFF00, chk[:, 3])  # bits 8-15 count dishes dropped on counters since
+
+
+def test_host_random_start_states_reproduce_the_reference_under_a_numpy_seed():
+    """The drop-in mdp's get_random_start_state_fn (overcooked_mdp.py:1307-1369) against draws of the reference stored by
+    tools/make_golden.py: joint positions, pot soups (idle / cooking), held dishes / onions / finished soups."""
+    from overcooked_ai_b200.mdp import OvercookedGridworld
+
+    with open(os.path.join(os.path.dirname(GOLD), "random_start_host.json")) as fh:
+        gold = json.load(fh)
+    mdps = {}
+    kinds = set()
+    for key, want in gold.items():
+        name, pos, thr, seed = key.split("|")
+        m = mdps.setdefault(name, OvercookedGridworld.from_layout_name(name))
+        np.random.seed(int(seed))
+        fn = m.get_random_start_state_fn(random_start_pos=bool(int(pos)), rnd_obj_prob_thresh=float(thr))
+        for w in want:
+            st = fn()
+            got = json.loads(json.dumps(st.to_dict()))
+            got["objects"].sort(key=lambda o: o["position"]), w["objects"].sort(key=lambda o: o["position"])
+            assert got == w, key
+            L.pack_state(m.compiled, st, 0, m.compiled.state_words)  # and the engine can hold it
+            kinds |= {p["held_object"]["name"] for p in got["players"] if p["held_object"]} | {"pot:%s" % o["is_cooking"] for o in got["objects"]}
+    assert {"dish", "onion", "soup", "pot:True", "pot:False"} <= kinds
+    env = OvercookedEnv.from_mdp(mdps["cramped_room"], start_state_fn=mdps["cramped_room"].get_random_start_state_fn(True, 0.8), horizon=400)
+    first = env.state
+    assert any(env.reset() or env.state != first for _ in range(5))  # overcooked_test.py:1288-1309

@@ -227,3 +227,30 @@ def test_grid_validity_rules_against_live_reference():
         except AssertionError as e:
             got = str(e)
         assert got == want, (g, got, want)
+
+
+@pytest.mark.parametrize("name", ["cramped_room", "counter_circuit", "asymmetric_advantages", "forced_coordination_tomato"])
+def test_host_random_start_states_against_live_reference(name):
+    """get_random_start_state_fn (overcooked_mdp.py:1307-1369) of the drop-in mdp: same numpy seed, same states."""
+    from overcooked_ai_b200.mdp import OvercookedGridworld
+
+    if name not in ALL_LAYOUTS:
+        pytest.skip("layout not bundled")
+    ns = refboot.boot()
+    m = refboot.make_mdp(ns, name)
+    mine = OvercookedGridworld.from_layout_name(name)
+    assert mine.get_valid_joint_player_positions() == m.get_valid_joint_player_positions()
+    for pos, thr in ((True, 0.0), (False, 0.7), (True, 0.5), (True, 1.0)):
+        for seed in range(6):
+            refboot.use_mdp(ns, m)
+            np.random.seed(seed)
+            f = m.get_random_start_state_fn(random_start_pos=pos, rnd_obj_prob_thresh=thr)
+            want = [json.loads(json.dumps(f().to_dict())) for _ in range(4)]
+            np.random.seed(seed)
+            g = mine.get_random_start_state_fn(random_start_pos=pos, rnd_obj_prob_thresh=thr)
+            got = [json.loads(json.dumps(g().to_dict())) for _ in range(4)]
+            for a, b in zip(got, want):
+                a["objects"].sort(key=lambda o: o["position"]), b["objects"].sort(key=lambda o: o["position"])
+                assert a == b, (name, pos, thr, seed)
+            st = g()
+            assert dict(mine.get_pot_states(st)) == dict(m.get_pot_states(ns.mdp.OvercookedState.from_dict(json.loads(json.dumps(st.to_dict())))))

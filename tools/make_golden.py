@@ -430,6 +430,22 @@ LAYOUTGEN_CASES = [
 ]
 
 
+def gen_random_start_host(ns):
+    """get_random_start_state_fn of the reference under np.random.seed(k): to_dict() of four consecutive draws."""
+    out = {}
+    for name in ("cramped_room", "counter_circuit"):
+        m = refboot.make_mdp(ns, name)
+        for pos, thr in ((True, 0.0), (False, 0.7), (True, 0.5)):
+            for seed in range(4):
+                refboot.use_mdp(ns, m)
+                np.random.seed(seed)
+                f = m.get_random_start_state_fn(random_start_pos=pos, rnd_obj_prob_thresh=thr)
+                out["%s|%d|%s|%d" % (name, int(pos), thr, seed)] = [jsonable(f().to_dict()) for _ in range(4)]
+    with open(os.path.join(GOLD, "random_start_host.json"), "w") as fh:
+        json.dump(out, fh, sort_keys=True)
+    print("random_start_host: %d seeded draws" % (4 * len(out)))
+
+
 def gen_layoutgen(ns):
     """LayoutGenerator outputs of the reference under np.random.seed(k): terrain rows + start cells."""
     import copy
@@ -472,6 +488,8 @@ def main():
         gen_potential(ns)
     if not only or "config1" in only:
         gen_config1(ns)
+    if not only or "randstart" in only:
+        gen_random_start_host(ns)
     if not only or "layoutgen" in only:
         gen_layoutgen(ns)
     print("done in %.1fs" % (time.time() - t0))
