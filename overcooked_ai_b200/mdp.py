@@ -119,42 +119,45 @@ class OvercookedGridworld(object):
 
     def get_random_start_state_fn(self, random_start_pos=False, rnd_obj_prob_thresh=0.0):
         """The host form of the reference's randomised start states (:1307-1369), for the drop-in
-        ``OvercookedEnv(start_state_fn=...)``: numpy's GLOBAL generator is called exactly as the reference calls it
-        (one ``choice`` for the joint position; per empty pot ``rand``, then ``randint`` x2 and ``rand`` if it fills;
-        per player ``rand``, then ``choice(p=[.2, .6, .2])`` and ``randint`` x2 if it holds something), so a seeded run
-        starts from the reference's states.  (The batched engine draws on the device instead: ovc_random_start_t.)"""
-        cook_time = self.compiled.cook_time
+        ``OvercookedEnv(start_state_fn=...)``.  numpy's GLOBAL generator is consumed exactly as the reference consumes
+        it — one ``choice`` for the joint position; per pot ``rand``, and if that fills it ``randint`` x2 + ``rand``;
+        per player ``rand``, and if that hands it something ``choice(p=[.2, .6, .2])`` + ``randint`` x2 (drawn whatever
+        the object is) — so a seeded run starts from the reference's states.  (The batched engine draws on the
+        device instead: ovc_random_start_t.)"""
+        layout, thr = self.compiled, rnd_obj_prob_thresh
 
-        def start_state_fn():
+        def draw_counts():
+            onions = int(np.random.randint(low=1, high=4))
+            return onions, int(np.random.randint(low=0, high=4 - onions))
+
+        def cook_time_of(onions, tomatoes):
+            return int(layout.cook_time[onions * 4 + tomatoes])
+
+        def make():
+            cells = self.start_player_positions
             if random_start_pos:
-                valid_positions = self.get_valid_joint_player_positions()
-                start_pos = valid_positions[np.random.choice(len(valid_positions))]
-            else:
-                start_pos = self.start_player_positions
-            start_state = OvercookedState.from_player_positions(
-                start_pos, bonus_orders=self.start_bonus_orders, all_orders=self.start_all_orders)
-            if rnd_obj_prob_thresh == 0:
-                return start_state
-            for pot_loc in self.get_pot_states(start_state)["empty"]:
-                if np.random.rand() < rnd_obj_prob_thresh:
-                    n = int(np.random.randint(low=1, high=4))
-                    m = int(np.random.randint(low=0, high=4 - n))
-                    cooking_tick = 0 if np.random.rand() < rnd_obj_prob_thresh else -1
-                    start_state.objects[pot_loc] = SoupState.get_soup(
-                        pot_loc, num_onions=n, num_tomatoes=m, cooking_tick=cooking_tick, cook_time=int(cook_time[n * 4 + m]))
-            for player in start_state.players:
-                if np.random.rand() < rnd_obj_prob_thresh:
-                    obj = np.random.choice(["dish", "onion", "soup"], p=[0.2, 0.6, 0.2])
-                    n = int(np.random.randint(low=1, high=4))
-                    m = int(np.random.randint(low=0, high=4 - n))
-                    if obj == "soup":
-                        player.set_object(SoupState.get_soup(player.position, num_onions=n, num_tomatoes=m, finished=True,
-                                                             cook_time=int(cook_time[n * 4 + m])))
-                    else:
-                        player.set_object(ObjectState(str(obj), player.position))
-            return start_state
+                joint = self.get_valid_joint_player_positions()
+                cells = joint[np.random.choice(len(joint))]
+            state = OvercookedState.from_player_positions(cells, bonus_orders=self.start_bonus_orders,
+                                                          all_orders=self.start_all_orders)
+            if thr == 0:
+                return state
+            for pot in self.get_pot_locations():  # a fresh state has no soups: every pot is "empty" (:1331)
+                if np.random.rand() < thr:
+                    o, t = draw_counts()
+                    tick = 0 if np.random.rand() < thr else -1  # cooking from tick 0, or idle
+                    state.add_object(SoupState.get_soup(pot, num_onions=o, num_tomatoes=t, cooking_tick=tick,
+                                                        cook_time=cook_time_of(o, t)))
+            for player in state.players:
+                if np.random.rand() < thr:
+                    kind = str(np.random.choice(["dish", "onion", "soup"], p=[0.2, 0.6, 0.2]))
+                    o, t = draw_counts()
+                    held = ObjectState(kind, player.position) if kind != "soup" else SoupState.get_soup(
+                        player.position, num_onions=o, num_tomatoes=t, finished=True, cook_time=cook_time_of(o, t))
+                    player.set_object(held)
+            return state
 
-        return start_state_fn
+        return make
 
     def soup_cook_time(self, soup):
         return self.compiled.soup_cook_time(soup)
