@@ -17,12 +17,15 @@ MAX_HORIZON = 1e10
 
 
 class OvercookedEnv(object):
-    def __init__(self, mdp_generator_fn, start_state_fn=None, horizon=MAX_HORIZON, info_level=0, num_mdp=1,
-                 initial_info={}, **kwargs):
+    def __init__(self, mdp_generator_fn, start_state_fn=None, horizon=MAX_HORIZON, mlam_params=None, info_level=0,
+                 num_mdp=1, initial_info={}, **kwargs):
         assert callable(mdp_generator_fn), (
             "OvercookedEnv takes in a OvercookedGridworld generator function. "
             "If trying to instantiate directly from a OvercookedGridworld instance, use the OvercookedEnv.from_mdp method"
         )
+        # mlam_params: the reference's planner parameters (default NO_COUNTERS_PARAMS, overcooked_env.py:92-100).  The
+        # planners themselves are outside this engine; featurize_state bakes exactly those defaults into its table.
+        self.mlam_params = mlam_params
         self.num_mdp = num_mdp
         self.variable_mdp = num_mdp > 1
         self.mdp_generator_fn = mdp_generator_fn
@@ -32,17 +35,17 @@ class OvercookedEnv(object):
         self.reset(outside_info=initial_info)
 
     @staticmethod
-    def from_mdp(mdp, start_state_fn=None, horizon=MAX_HORIZON, info_level=1, num_mdp=None, **kwargs):
+    def from_mdp(mdp, start_state_fn=None, horizon=MAX_HORIZON, mlam_params=None, info_level=1, num_mdp=None, **kwargs):
         assert isinstance(mdp, OvercookedGridworld)
         if num_mdp is not None:
             assert num_mdp == 1
         return OvercookedEnv(lambda _ignored: mdp, start_state_fn=start_state_fn, horizon=horizon,
-                             info_level=info_level, num_mdp=1)
+                             mlam_params=mlam_params, info_level=info_level, num_mdp=1)
 
     @property
     def env_params(self):
-        return {"start_state_fn": self.start_state_fn, "horizon": self.horizon, "info_level": self.info_level,
-                "num_mdp": self.num_mdp}
+        return {"start_state_fn": self.start_state_fn, "horizon": self.horizon, "mlam_params": self.mlam_params,
+                "info_level": self.info_level, "num_mdp": self.num_mdp}
 
     def step(self, joint_action, joint_agent_action_info=None, display_phi=False):
         assert not self.is_done()
@@ -61,6 +64,10 @@ class OvercookedEnv(object):
         return self.mdp.lossless_state_encoding(state, self.horizon)
 
     def featurize_state_mdp(self, state, num_pots=2):
+        p = self.mlam_params
+        if p is not None and (p.get("counter_goals") or p.get("counter_drop") or p.get("counter_pickup")):
+            raise NotImplementedError("featurize_state is built for the env's default planner parameters "
+                                      "(NO_COUNTERS_PARAMS: counters are never motion goals)")
         return self.mdp.featurize_state(state, None, num_pots=num_pots)
 
     def potential(self, mlam=None, state=None, gamma=0.99):

@@ -47,11 +47,13 @@ class OvercookedGridworld(object):
 
     # ---- construction ----------------------------------------------------------------------------
     @staticmethod
-    def from_layout_name(layout_name, device="cuda", **params_to_overwrite):
+    def from_layout_name(layout_name, **params_to_overwrite):
+        """:1151-1172.  ``device=...`` (not a layout parameter) selects the CUDA device of the N = 1 engine."""
+        device = params_to_overwrite.pop("device", "cuda")
         return OvercookedGridworld(L.compile_layout(layout_name, **params_to_overwrite), device=device)
 
     @staticmethod
-    def from_grid(layout_grid, base_layout_params={}, params_to_overwrite={}, device="cuda"):
+    def from_grid(layout_grid, base_layout_params={}, params_to_overwrite={}, debug=False, device="cuda"):
         params = dict(base_layout_params)
         params.update(params_to_overwrite)
         name = params.pop("layout_name", "|".join("".join(r) for r in layout_grid))

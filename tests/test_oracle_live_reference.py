@@ -254,3 +254,31 @@ def test_host_random_start_states_against_live_reference(name):
                 assert a == b, (name, pos, thr, seed)
             st = g()
             assert dict(mine.get_pot_states(st)) == dict(m.get_pot_states(ns.mdp.OvercookedState.from_dict(json.loads(json.dumps(st.to_dict())))))
+
+
+def test_call_signatures_of_the_boundary_match_the_reference():
+    """the drop-in classes keep the reference's parameter names, order and kinds on every entry point of
+    the path (extra trailing parameters — ``device``, ``**kwargs`` — are allowed), and its simple default values."""
+    import inspect
+
+    from overcooked_ai_b200 import env as E
+    from overcooked_ai_b200 import mdp as M
+
+    ns = refboot.boot()
+    env_names = ["__init__", "from_mdp", "step", "reset", "is_done", "potential", "lossless_state_encoding_mdp",
+                 "featurize_state_mdp", "execute_plan"]
+    mdp_names = ["from_layout_name", "from_grid", "get_state_transition", "lossless_state_encoding", "featurize_state",
+                 "potential_function", "get_random_start_state_fn", "get_standard_start_state", "get_pot_states", "get_actions",
+                 "get_valid_joint_player_positions", "get_valid_player_positions", "get_pot_locations",
+                 "get_counter_locations", "get_serving_locations", "get_dish_dispenser_locations",
+                 "get_onion_dispenser_locations", "get_tomato_dispenser_locations", "get_terrain_type_at_pos", "is_terminal"]
+    pairs = [(getattr(ns.env.OvercookedEnv, n), getattr(E.OvercookedEnv, n)) for n in env_names]
+    pairs += [(getattr(ns.env.Overcooked, n), getattr(E.Overcooked, n)) for n in ("step", "reset")]
+    pairs += [(getattr(ns.mdp.OvercookedGridworld, n), getattr(M.OvercookedGridworld, n)) for n in mdp_names]
+    for ref_fn, my_fn in pairs:
+        ref_p = list(inspect.signature(ref_fn).parameters.values())
+        my_p = list(inspect.signature(my_fn).parameters.values())
+        assert [(p.name, p.kind) for p in my_p[:len(ref_p)]] == [(p.name, p.kind) for p in ref_p], ref_fn.__qualname__
+        for a, b in zip(ref_p, my_p):
+            if isinstance(a.default, (int, float, bool, str, type(None))) and a.default is not inspect.Parameter.empty:
+                assert a.default == b.default, (ref_fn.__qualname__, a.name, a.default, b.default)
