@@ -28,7 +28,9 @@
  *   word 3        bits 0-7   layout id (index into the layout table)
  *                 bits 8-15  number of loose dishes on counters (derived cache, kept by every
  *                            kernel; pack() computes it)
- *                 bits 16-31 episode counter of the random-start generator (0 unless random starts are used)
+ *                 bits 16-31 episode counter of the random-start generator (0 unless random starts are used);
+ *                            it is part of the Philox counter and wraps after 65 536 episodes of an environment, after
+ *                            which that environment's start-state sequence repeats (change the seed to move on)
  *   word 4+k      object on object-capable cell k, 22-bit object code (0 = empty).
  *                 Cells are ordered: the layout's pots (terrain row-major order, = the order of
  *                 get_pot_locations(), :1799) first, then its counters 'X' (row-major).
@@ -182,7 +184,8 @@ typedef struct ovc_cost_lut_entry {
  * uses Philox4x32-10 keyed by `seed`, counter (env index, episode counter, draw block), mirrored bit for
  * bit by the CPU oracle.  Draw plan per reset: block 0 = {joint position, p0 holds?, p0 object, p0 n},
  * block 1 = {p0 m, p1 holds?, p1 object, p1 n}, block 2 = {p1 m, -, -, -}, block 3+k = pot k {filled?, n, m,
- * cooking?}.  "u < p" is `draw < threshold` with threshold = p * 2^32; randint(lo, hi) is lo + mulhi(draw, hi-lo);
+ * cooking?}.  "u < p" is `draw < threshold` with threshold = p * 2^32, saturated at 0xFFFFFFFF which means ALWAYS
+ * (p = 1.0); randint(lo, hi) is lo + mulhi(draw, hi-lo);
  * the object is a dish / onion / soup with probability 0.2 / 0.6 / 0.2 (:1351-1353), a held soup is finished,
  * a pot soup has n in 1..3 onions then m in 0..3-n tomatoes and is cooking (tick 0) or idle.
  * Variable MDP (OvercookedEnv.reset(regen_mdp=True) with a generator over num_mdp > 1 layouts, overcooked_env.py:

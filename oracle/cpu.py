@@ -19,7 +19,7 @@ def build(force=False):
     hdr = os.path.join(_HERE, "..", "include", "ovc_b200.h")
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
         subprocess.check_call(
-            ["gcc", "-O2", "-fPIC", "-pthread", "-std=c11", "-shared", "-o", so, src], cwd=_HERE
+            ["gcc", "-O2", "-fPIC", "-pthread", "-std=gnu11", "-shared", "-o", so, src], cwd=_HERE
         )
     return so
 

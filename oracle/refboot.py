@@ -1,8 +1,10 @@
-"""Import the UNMODIFIED reference implementation from /root/reference (build container only).
+"""Import the UNMODIFIED reference implementation: /root/reference in the build container, or the file-by-file copy
+under oracle/_ref/ (oracle/make_ref.py; git-ignored, shipped to the GPU box) where that tree does not exist.
 
-TEST INFRASTRUCTURE.  Used by tools/make_golden.py to generate the fixtures under tests/golden/
-and by the ``reference``-marked tests that compare against the live reference when it is present.
-The GPU box has no /root/reference: nothing on the ``-m gpu`` / smoke / bench path imports this.
+TEST / MEASUREMENT INFRASTRUCTURE.  Used by tools/make_golden.py to generate the fixtures under tests/golden/,
+by the ``reference``-marked tests that compare against the live reference, and by oracle/ref_python_bench.py
+(bench.py's `cpu_baseline.reference_python`: the reference's own Python step timed on the box's host cores).
+Nothing on the ``-m gpu`` / smoke path imports this.
 
 Follows SURVEY.md appendix E: stub the four optional modules the reference imports at module
 scope (gymnasium, pygame, IPython, ipywidgets), never let the planners write pickles into the
@@ -12,7 +14,20 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("OVC_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    """/root/reference in the build container; on the GPU box the file-by-file copy oracle/make_ref.py shipped."""
+    env = os.environ.get("OVC_REFERENCE")
+    if env:
+        return env
+    if os.path.isdir(os.path.join("/root/reference", "src", "overcooked_ai_py")):
+        return "/root/reference"
+    return os.path.join(_HERE, "_ref")
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available():

@@ -103,12 +103,11 @@ class BatchedOvercookedEnv(object):
         self._rs = None
         self.random_layout = bool(random_layout)
         if random_start_pos or rnd_obj_prob_thresh > 0 or random_layout:
-            thr = min(int(float(rnd_obj_prob_thresh) * 4294967296.0), 0xFFFFFFFF)
+            thr = min(int(float(rnd_obj_prob_thresh) * 4294967296.0), 0xFFFFFFFF)  # 0xFFFFFFFF = always (ovc_rng.cuh)
             self._rs = _native.RandomStart(int(seed) & 0xFFFFFFFFFFFFFFFF, thr, int(bool(random_start_pos)),
                                            int(self.random_layout), 0)
         self._lut = None
         self._segments = None
-        self._p_tables, self._p_starts, self._p_state = self.tables.data_ptr(), self.start_records.data_ptr(), self.state.data_ptr()
         with torch.cuda.device(self.device):
             self.reset()
 
@@ -155,7 +154,7 @@ class BatchedOvercookedEnv(object):
                 assert o.dtype == torch.int32 and o.is_cuda and o.is_contiguous() and o.numel() == n * self.n_envs, \
                     "step(out=...) takes int32 CUDA tensors (sparse[N], shaped[N,2], done[N], events[N,2])"
         _native.check(self._lib.ovc_step(
-            self._p_tables, self.n_layouts, self._p_starts, self._p_state,
+            self.tables.data_ptr(), self.n_layouts, self.start_records.data_ptr(), self.state.data_ptr(),
             actions.data_ptr(), sparse.data_ptr(), shaped.data_ptr(), done.data_ptr(),
             events.data_ptr(), self.n_envs, self.state_words, self.horizon, self._flags(), self._rs_ptr(), self._stream()))
         return sparse, shaped, done, events

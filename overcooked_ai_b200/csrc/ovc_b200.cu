@@ -130,6 +130,7 @@ struct GlobalRec {
 #ifndef OVC_TILE16
 #define OVC_TILE16 128
 #endif
+
 template <int S>
 struct Cfg {
     static constexpr int TILE = S <= 16 ? OVC_TILE16 : S <= 32 ? 128 : 64;  // environments (= threads) per CTA
@@ -310,6 +311,12 @@ step_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
     }
 }
 
+}  // namespace ovc
+
+#include "ovc_rollout.cuh"
+
+namespace ovc {
+
 __global__ void reset_kernel(const int32_t *__restrict__ start_records, int n_layouts, int32_t *__restrict__ state,
                              const int32_t *__restrict__ env_layout, const int32_t *__restrict__ mask,
                              long long n_envs, int S) {
@@ -366,13 +373,13 @@ static encode_tiled_fn get_encode_fn() {
 }
 
 template <int S>
-static int make_tmap(CUtensorMap *m, int32_t *state, long long n_envs) {
+static int make_tmap(CUtensorMap *m, int32_t *state, long long n_envs, int box_rows = Cfg<S>::BOX_ROWS) {
     using C = Cfg<S>;
     encode_tiled_fn enc = get_encode_fn();
     if (!enc) return fail(OVC_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[2] = {(cuuint64_t)C::ROW_WORDS, (cuuint64_t)(n_envs * C::ROWS_PER_ENV)};
     cuuint64_t strides[1] = {(cuuint64_t)C::ROW_WORDS * 4};
-    cuuint32_t box[2] = {(cuuint32_t)C::ROW_WORDS, (cuuint32_t)C::BOX_ROWS};
+    cuuint32_t box[2] = {(cuuint32_t)C::ROW_WORDS, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, state, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      S == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -400,9 +407,80 @@ static cudaError_t launch_one(const CUtensorMap &tmap, const StepArgs &a, unsign
                 : cudaLaunchKernelEx(&cfg, step_kernel<S, IO, false, false>, tmap, a);
 }
 
+// ---- K5: the fused rollout kernel (ovc_rollout.cuh) ----
+template <int S, int TILE>
+static int launch_rollout(const StepArgs &a, cudaStream_t st) {
+    using C = RollCfg<S, TILE>;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    int rc = make_tmap<S>(&tmap, a.state, a.n_envs, C::BOX_ROWS);
+    if (rc) return rc;
+    const size_t smem = C::smem_bytes(a.n_layouts);
+    const bool wide = !(a.flags & (OVC_F_ACT_U8 | OVC_F_ACT_PACKED | OVC_F_OUT_NARROW | OVC_F_OUT_PACKED | OVC_F_OUT_CODES));
+    void (*kern)(const CUtensorMap, const StepArgs) =
+        a.has_rs ? (wide ? rollout_kernel<S, TILE, true, true> : rollout_kernel<S, TILE, true, false>)
+                 : (wide ? rollout_kernel<S, TILE, false, true> : rollout_kernel<S, TILE, false, false>);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "rollout kernel shared-memory attribute");
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)((a.n_envs + TILE - 1) / TILE)), cfg.blockDim = dim3(TILE), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (a.flags & OVC_F_PDL) ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap, a);
+    if (e != cudaSuccess) return cuda_fail(e, "rollout kernel launch");
+    return OVC_OK;
+}
+
+// environments per CTA of the rollout kernel (measured, profiles/r2_k5_tile_sweep.md): one warp per CTA spreads a small
+// batch most evenly over the 148 SMs (65 536 envs = 13.8 warps per SM); bigger batches amortise the per-CTA table
+// derivation better with 2-4 warps per CTA, and a many-layout table set (4.5 KB of shared memory per layout and CTA)
+// wants the largest tile.  OVC_K5_TILE overrides (tuning hook).
+static int rollout_tile(int S, long long n_envs, int n_layouts) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char *e = getenv("OVC_K5_TILE");
+        forced = e ? atoi(e) : 0;
+    }
+    if (S > 32) return 64;
+    if (forced == 32 || forced == 64 || forced == 128) return forced;
+    if (n_layouts >= 3) return 128;
+    if (S == 16 && n_envs <= 148LL * 16 * 32) return 32;
+    return 64;
+}
+
+// true: handled by the rollout kernel; false: the caller falls back to step_kernel with n_steps > 1
+static bool use_rollout_kernel(const StepArgs &a, int io) {
+    static int off = -1;
+    if (off < 0) {
+        const char *e = getenv("OVC_K5_LEGACY");  // measure / test the pre-round-2 fused path
+        off = e && atoi(e) ? 1 : 0;
+    }
+    return !off && a.n_steps > 1 && a.n_steps <= ROLLOUT_MAX_STEPS && io == 1 && a.n_layouts <= MAX_SMEM_LAYOUTS;
+}
+
+template <int S>
+static int launch_rollout_any(const StepArgs &a, cudaStream_t st) {
+    if constexpr (S > 32) {
+        return launch_rollout<S, 64>(a, st);
+    } else {
+        switch (rollout_tile(S, a.n_envs, a.n_layouts)) {
+        case 32: return launch_rollout<S, 32>(a, st);
+        case 64: return launch_rollout<S, 64>(a, st);
+        default: return launch_rollout<S, 128>(a, st);
+        }
+    }
+}
+
 template <int S>
 static int launch_step(const StepArgs &a, int io, cudaStream_t st) {
     using C = Cfg<S>;
+    if (use_rollout_kernel(a, io)) return launch_rollout_any<S>(a, st);
     const unsigned grid = (unsigned)((a.n_envs + C::TILE - 1) / C::TILE);
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);

@@ -2,6 +2,7 @@
 // OVC_F_OUT_CODES transfer words into the dense reward / done / event arrays a host consumer indexes.
 // The result of a rollout crosses PCIe as codes; this runs on the host cores at memory speed.
 #pragma once
+#include <sched.h>
 #include <stdint.h>
 #include <unistd.h>
 
@@ -145,9 +146,13 @@ static int expand_codes_host(const uint16_t *codes, int64_t n_steps, int64_t n_e
     int32_t mask[32];
     build_code_masks(mask);
     const int64_t n = n_steps * n_envs;
-    if (n_threads <= 0) {
-        const long c = sysconf(_SC_NPROCESSORS_ONLN);
-        n_threads = c > 0 ? (int)c : 1;
+    if (n_threads <= 0) {  // every CPU of the process's affinity mask (a fractional-node lease sees the whole machine online)
+        cpu_set_t set;
+        n_threads = sched_getaffinity(0, sizeof set, &set) == 0 ? CPU_COUNT(&set) : 0;
+        if (n_threads <= 0) {
+            const long c = sysconf(_SC_NPROCESSORS_ONLN);
+            n_threads = c > 0 ? (int)c : 1;
+        }
     }
     if (n_threads > 256) n_threads = 256;
     if (n < (int64_t)n_threads * 4096) n_threads = (int)(n / 4096) + 1;
@@ -290,7 +295,8 @@ static int pipeline_run(ovc_pipeline_t *p, const void *h_actions, void *h_sparse
 
 static int pipeline_wait(ovc_pipeline_t *p, int64_t ticket) {
     if (ticket < 0 || ticket >= p->n_pass) return fail(OVC_E_BADARG, "unknown pass ticket", (long long)ticket);
-    if (p->n_pass - ticket > ovc_pipeline::RING) return OVC_OK;  // that pass was overwritten in the ring: long finished or superseded
+    // the ring slot may by now hold the event of a LATER pass: it was recorded later on the same copy stream, so
+    // waiting for it implies the asked-for pass has landed too
     OVC_CK(cudaEventSynchronize(p->ev_pass[ticket % ovc_pipeline::RING]), "pipeline wait");
     return OVC_OK;
 }

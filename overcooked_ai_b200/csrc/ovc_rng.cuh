@@ -29,6 +29,9 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint64_t key, uint32_t
 
 __host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t x, uint32_t n) { return (uint32_t)(((uint64_t)x * n) >> 32); }
 
+// "u < p" on 32-bit draws: draw < threshold, with the saturated threshold 0xFFFFFFFF (p = 1.0) meaning always
+__host__ __device__ __forceinline__ bool draw_below(uint32_t draw, uint32_t thr) { return draw < thr || thr == 0xFFFFFFFFu; }
+
 // soup code with n onions followed by m tomatoes and the given tick+1 field
 __host__ __device__ __forceinline__ uint32_t soup_code(int n, int m, uint32_t tick_plus_1) {
     return (uint32_t)OVC_O_SOUP | ((uint32_t)(n + m) << 3) | ((((1u << m) - 1u) << n) << 5) | (tick_plus_1 << 8);
@@ -37,7 +40,7 @@ __host__ __device__ __forceinline__ uint32_t soup_code(int n, int m, uint32_t ti
 // The object a player starts with (:1346-1366) or 0: draws = {holds?, which, n, m}
 __host__ __device__ __forceinline__ uint32_t random_held(const int32_t *cook_time, uint32_t thr, uint32_t d_has, uint32_t d_obj,
                                                          uint32_t d_n, uint32_t d_m) {
-    if (!(d_has < thr)) return 0;
+    if (!draw_below(d_has, thr)) return 0;
     if (d_obj < 858993459u) return OVC_O_DISH;    // p = 0.2
     if (d_obj < 3435973836u) return OVC_O_ONION;  // p = 0.6
     const int n = 1 + (int)mulhi32(d_n, 3), m = (int)mulhi32(d_m, (uint32_t)(4 - n));
@@ -81,9 +84,9 @@ __host__ __device__ __forceinline__ void random_start_record(Store &&store, int 
         uint32_t code = 0;
         if (thr && k < n_pots) {  // :1331-1344
             const Philox4 Pk = philox4x32_10(rs.seed, e_lo, e_hi, episode, 3 + (uint32_t)k);
-            if (Pk.v[0] < thr) {
+            if (draw_below(Pk.v[0], thr)) {
                 const int n = 1 + (int)mulhi32(Pk.v[1], 3), m = (int)mulhi32(Pk.v[2], (uint32_t)(4 - n));
-                code = soup_code(n, m, Pk.v[3] < thr ? 1u : 0u);
+                code = soup_code(n, m, draw_below(Pk.v[3], thr) ? 1u : 0u);
             }
         }
         store(4 + k, (int32_t)code);

@@ -133,6 +133,8 @@ class BatchedOvercookedMultiAgent(object):
             self._phi = torch.where(done != 0, self.env.potential(self.gamma), phi_next)
         else:
             rewards = {a: sp + self.reward_shaping_factor * shaped[:, i].to(torch.float32) for i, a in enumerate(self.AGENTS)}
+            if not self.env.auto_reset:
+                self.env.reset(done)  # finished envs start their next episode now (with auto_reset the kernel already did)
         d = done != 0
         dones = {self.AGENTS[0]: d, self.AGENTS[1]: d, "__all__": d}
         info = {"sparse_r": sparse, "shaped_r_by_agent": shaped, "events": events}

@@ -44,6 +44,27 @@ def test_golden_transitions(path, io):
     assert np.array_equal(by_agent.reshape(tr.sparse2.shape), tr.sparse2)
 
 
+@pytest.mark.parametrize("chunk", [2, 7, 0], ids=["chunks_of_2", "chunks_of_7", "whole"])
+@pytest.mark.parametrize("path", TRACE_FILES, ids=TRACE_IDS)
+def test_golden_trajectories_fused(path, chunk):
+    """Every fixture trajectory through the fused rollout kernel K5, cut into launches of `chunk` transitions (0: one
+    launch): rewards / events of every transition and the record after every launch.  Short launches put every
+    cooking soup through the kernel's on-chip <-> record conversion at every possible tick."""
+    tr = Trace(path)
+    env = _env_for_trace(tr, tr.E, _native.IO_DEFAULT)
+    env.state.copy_(torch.from_numpy(np.ascontiguousarray(tr.states[:, 0])))
+    acts = torch.from_numpy(np.ascontiguousarray(tr.actions.transpose(1, 0, 2))).cuda()  # [T,E,2]
+    step = chunk if chunk else tr.T
+    for t0 in range(0, tr.T, step):
+        t1 = min(tr.T, t0 + step)
+        sp, sh, dn, ev = [_np(x) for x in env.rollout(acts[t0:t1].contiguous())]
+        assert np.array_equal(_np(env.state), tr.states[:, t1]), "record after transitions %d..%d" % (t0, t1)
+        assert np.array_equal(sp.T, tr.sparse[:, t0:t1])
+        assert np.array_equal(sh.transpose(1, 0, 2), tr.shaped[:, t0:t1])
+        assert np.array_equal(ev.transpose(1, 0, 2) & EVENT_MASK, tr.events[:, t0:t1])
+        assert not dn.any()
+
+
 def test_greedy_games_stepwise_and_fused():
     """5 GreedyHumanModel games on cramped_room (9 deliveries each): per-step launches, then the same
     games again through the fused T-step rollout kernel."""
