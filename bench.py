@@ -593,12 +593,13 @@ def main():
 
     # ---- e2e: the same workload through the public host-buffer API ----
     def run_e2e(fmt, expand=False):
-        """One HostRolloutPipeline format.  expand: rebuild the dense sparse / shaped / done arrays from the code words
-        on this rank's host cores inside the timed region (the payload a host consumer indexes)."""
+        """One HostRolloutPipeline format.  expand: rebuild the dense sparse / shaped / done arrays on this rank's host
+        cores inside the timed region (the payload a host consumer indexes)."""
         narrow = fmt != "int32"
-        codes = fmt == "codes"
-        chunk = int(os.environ.get("OVC_E2E_CHUNK", "200" if codes else "50"))
-        pipe = HostRolloutPipeline(env, T, chunk=chunk, narrow=narrow, packed=fmt == "packed", codes=codes, host_buffers=2)
+        codes = fmt in ("codes", "stream")
+        stream = fmt == "stream"
+        chunk = int(os.environ.get("OVC_E2E_CHUNK", "100" if stream else "200" if codes else "50"))
+        pipe = HostRolloutPipeline(env, T, chunk=chunk, narrow=narrow, packed=fmt == "packed", codes=codes, stream=stream, host_buffers=2)
         if codes:
             from overcooked_ai_b200 import wire
             h_actions = torch.from_numpy(wire.pack_actions(actions.cpu().numpy())).pin_memory()
@@ -611,20 +612,29 @@ def main():
             h_actions.copy_(actions)
         env.reset()
         n_thr = max(1, host["bound_cpus"])
+        overflow = [0]
+
+        def finish(p_):
+            """Pass p_ = (host tensors, ticket, dense-backup set) has been submitted: wait for it, expand it."""
+            p_[1].synchronize()
+            if expand:
+                if stream:
+                    pipe.expand(p_[0], codes_set=p_[2], out=dense, n_threads=n_thr)
+                    overflow[0] += pipe.last_overflow
+                else:
+                    env.expand_codes(p_[0][3], out=dense, n_threads=n_thr)
 
         def passes_e2e(k):
             """k passes back to back, as a collection loop runs them: pass i+1 is submitted before pass i has
             drained (two pinned output sets), and with `expand` the host rebuilds pass i's arrays meanwhile."""
             prev = None
             for _ in range(k):
-                cur_ = pipe.run(h_actions, wait=False)
-                if expand and prev is not None:
-                    prev[1].synchronize()
-                    env.expand_codes(prev[0][3], out=dense, n_threads=n_thr)
+                h_, tk_ = pipe.run(h_actions, wait=False)
+                cur_ = (h_, tk_, getattr(pipe, "_last_set", 0))
+                if prev is not None:
+                    finish(prev)
                 prev = cur_
-            prev[1].synchronize()
-            if expand:
-                env.expand_codes(prev[0][3], out=dense, n_threads=n_thr)
+            finish(prev)
             pipe.join()
             return prev[0]
 
@@ -632,33 +642,48 @@ def main():
         torch.cuda.synchronize(dev)
         D.barrier()
         k_e2e = max(3, min(args.steps, 8))
+        overflow[0] = 0
         t0 = time.perf_counter()
         h_out = passes_e2e(k_e2e)
         torch.cuda.synchronize(dev)
         e2e_ms = (time.perf_counter() - t0) * 1e3
         D.barrier()
         _, e2e_max_ms, _ = D.reduce_counters(0, e2e_ms, 0, device=dev)
-        sparse_host = dense["sparse"] if (codes and expand) else env.expand_codes(h_out[3], shaped=False, done=False)["sparse"] if codes else h_out[0]
-        what = {"codes": "both agents' event codes + done + reward-grant bits in ONE int16 per env-step (lossless: rewards are table lookups of "
-                         "the codes)%s" % (", expanded to dense int16 sparse / int8x2 shaped / uint8 done arrays by %d host threads inside the timed region" % n_thr if expand else ""),
+        if codes and expand:
+            sparse_host = dense["sparse"]
+        elif stream:
+            sparse_host = pipe.expand(h_out, shaped=False, done=False)["sparse"]
+        elif codes:
+            sparse_host = env.expand_codes(h_out[3], shaped=False, done=False)["sparse"]
+        else:
+            sparse_host = h_out[0]
+        exp_txt = ", expanded to dense int16 sparse / int8x2 shaped / uint8 done arrays by %d host threads inside the timed region" % n_thr if expand else ""
+        what = {"stream": "a sparse event stream: per transition one warp-vote lane mask per 32 environments + the non-zero code words, %d value "
+                          "slots per group and chunk (lossless; an overflowing group falls back to the dense words kept on the device)%s" % (pipe.stream_cap, exp_txt),
+                "codes": "both agents' event codes + done + reward-grant bits in ONE int16 per env-step (lossless: rewards are table lookups of "
+                         "the codes)%s" % exp_txt,
                 "packed": "sparse int16 + shaped int8x2 + both agents' event codes and done in one int16 (lossless, wire.decode_event_codes)",
                 "narrow": "sparse int16 / shaped int8 / done uint8 / events int32", "int32": "sparse/shaped/done/events int32"}[fmt]
         pipe.close()
-        return {"value": float(n_envs) * T * k_e2e * world / (e2e_max_ms * 1e-3), "unit": "env-steps/s",
-                "h2d_bytes_per_step": pipe.h2d_bytes_per_step * T, "d2h_bytes_per_step": pipe.d2h_bytes_per_step * T,
-                "steps": k_e2e, "ms_per_step": e2e_max_ms / k_e2e,
-                "api": "overcooked_ai_b200.batched.HostRolloutPipeline(%s).run: pinned host actions (%s) in, %s out, "
-                       "%d-transition chunks, H2D / fused rollout kernel / D2H on three streams, successive passes submitted back to back "
-                       "(two pinned output sets; every pass's copies, its expansion and its completion are inside the timed region)"
-                       % (fmt, "one uint8 per joint action" if codes else "uint8" if narrow else "int32", what, chunk),
-                "host_threads": n_thr if expand else 0, "checksum_sparse": int(sparse_host.sum(dtype=torch.int64).item())}
+        r = {"value": float(n_envs) * T * k_e2e * world / (e2e_max_ms * 1e-3), "unit": "env-steps/s",
+             "h2d_bytes_per_step": pipe.h2d_bytes_per_step * T, "d2h_bytes_per_step": pipe.d2h_bytes_per_step * T,
+             "steps": k_e2e, "ms_per_step": e2e_max_ms / k_e2e,
+             "api": "overcooked_ai_b200.batched.HostRolloutPipeline(%s).run: pinned host actions (%s) in, %s out, "
+                    "%d-transition chunks, H2D / fused rollout kernel / D2H on three streams, successive passes submitted back to back "
+                    "(two pinned output sets; every pass's copies, its expansion and its completion are inside the timed region)"
+                    % (fmt, "one uint8 per joint action" if codes else "uint8" if narrow else "int32", what, chunk),
+             "host_threads": n_thr if expand else 0, "checksum_sparse": int(sparse_host.sum(dtype=torch.int64).item())}
+        if stream:
+            r["stream_overflows"] = overflow[0]
+        return r
 
     e2e = None
     if not args.no_e2e:
         if env.narrow_ok():
-            e2e = run_e2e("codes", expand=True)             # headline: dense reward / done arrays in host memory
-            e2e["code_words_only"] = run_e2e("codes")       # what crosses PCIe, not expanded (1 B in, 2 B out per env-step)
-            e2e["int32_formats"] = run_e2e("int32")         # the reference arm's own 32-bit formats (8 B in, 24 B out)
+            e2e = run_e2e("stream", expand=True)             # headline: dense reward / done arrays in host memory
+            e2e["event_stream_only"] = run_e2e("stream")     # what crosses PCIe, left as the sparse stream
+            e2e["code_words_expanded"] = run_e2e("codes", expand=True)  # round 1's format: one dense int16 word per env-step
+            e2e["int32_formats"] = run_e2e("int32")          # the reference arm's own 32-bit formats (8 B in, 24 B out)
         else:
             e2e = run_e2e("int32")
         e2e["host_placement"] = host

@@ -54,7 +54,7 @@
 extern "C" {
 #endif
 
-#define OVC_ABI_VERSION 3
+#define OVC_ABI_VERSION 4
 
 /* ---- action indices: Action.INDEX_TO_ACTION, actions.py:47-57 ---- */
 #define OVC_A_NORTH 0
@@ -242,6 +242,22 @@ typedef struct ovc_random_start {
  *   OVC_F_ACT_PACKED  `actions` is uint8[..]: agent 0's action index in bits 0-3, agent 1's in bits 4-7. */
 #define OVC_F_OUT_CODES 32
 #define OVC_F_ACT_PACKED 64
+/*   OVC_F_OUT_STREAM  (ovc_rollout and the pipeline) the result as a SPARSE EVENT STREAM — what a rollout produces is mostly
+ *                     zeros, so only the non-zero OVC_F_OUT_CODES words travel.  With G = ceil(n_envs / 32) groups of 32
+ *                     consecutive environments (one warp each):
+ *                       `events`  uint32[n_steps][G]  lane masks: bit l of [t][g] set = environment 32 g + l produced a
+ *                                 non-zero code word in transition t (one __ballot_sync per warp and transition);
+ *                       `sparse`  uint16[G][cap]      the group's non-zero words in (transition, lane) order; cap (words per
+ *                                 group and launch) travels in flags bits 16-31 (OVC_F_STREAM_CAP_SHIFT).  Words beyond
+ *                                 cap are dropped; the masks still count them, so the reader sees the overflow;
+ *                       `done`    uint16[n_steps][n_envs] or NULL: the dense code words as well (device-side backup that
+ *                                 makes an overflow recoverable; never copied to the host by the pipeline);
+ *                       `shaped`  unused (may be NULL).
+ *                     Lossless for every group whose word count stays within cap.  Combines with OVC_F_ACT_U8 / _PACKED.
+ *                     ovc_expand_stream_host rebuilds dense arrays on the host. */
+#define OVC_F_OUT_STREAM 128
+#define OVC_F_STREAM_CAP_SHIFT 16
+#define OVC_F_STREAM_CAP_MAX 0xFFFF
 /* bits 8-11 select the record I/O strategy of the step kernel (0 = library default):
  *   1 = 2-D tensor-map TMA tile with hardware swizzle, 2 = 1-D bulk TMA (linear tile),
  *   3 = direct vectorised global loads/stores (no staging).  All produce identical results. */
@@ -313,9 +329,13 @@ typedef struct ovc_pipeline_desc {
     ovc_random_start_t random_start;
     void *d_actions[2];           /* device staging: chunk * n_envs joint actions each */
     void *d_sparse[2];            /* device staging of the outputs, chunk * n_envs env-steps each */
-    void *d_shaped[2];
-    void *d_done[2];
+    void *d_shaped[2];            /*   (OVC_F_OUT_STREAM: d_events = lane masks uint32[chunk][G], d_sparse = values */
+    void *d_done[2];              /*    uint16[G][stream_cap], d_shaped / d_done unused) */
     void *d_events[2];
+    int32_t stream_cap;           /* OVC_F_OUT_STREAM: value words per group and CHUNK, 1..OVC_F_STREAM_CAP_MAX */
+    int32_t reserved;
+    void *d_codes_full[2];        /* OVC_F_OUT_STREAM, optional: dense code words uint16[n_steps][n_envs] of a whole pass, kept
+                                     on the device (pass k writes set k & 1) so that the caller can recover an overflow */
 } ovc_pipeline_desc_t;
 
 int ovc_pipeline_create(const ovc_pipeline_desc_t *desc, ovc_pipeline_t **out);
@@ -323,6 +343,8 @@ int ovc_pipeline_create(const ovc_pipeline_desc_t *desc, ovc_pipeline_t **out);
  * The pipeline first waits for the work already enqueued on `stream` (the caller's stream).  `join` != 0: `stream`
  * then waits for the pass, so later work on it sees the results (stream-ordered call); join == 0: successive passes
  * overlap, *ticket (nullable) identifies this pass for ovc_pipeline_wait. */
+/* OVC_F_OUT_STREAM: h_events = lane masks uint32[n_steps][G], h_sparse = values uint16[n_chunks][G][stream_cap]
+ * (n_chunks = ceil(n_steps / chunk); every chunk starts its groups' value slices afresh), h_shaped / h_done unused. */
 int ovc_pipeline_run(ovc_pipeline_t *p, const void *h_actions, void *h_sparse, void *h_shaped, void *h_done,
                      void *h_events, int n_steps, void *stream, int join, int64_t *ticket);
 int ovc_pipeline_wait(ovc_pipeline_t *p, int64_t ticket); /* blocks the HOST until that pass's last copy has landed */
@@ -341,6 +363,19 @@ void ovc_pipeline_destroy(ovc_pipeline_t *p);
 int ovc_expand_codes_host(const uint16_t *codes, int64_t n_steps, int64_t n_envs, const int32_t *env_layout,
                           const int32_t *reward_tbl, int n_layouts, int16_t *sparse, int8_t *shaped, uint8_t *done,
                           int32_t *events, int n_threads);
+
+/*
+ * HOST function (no GPU work): dense arrays from an OVC_F_OUT_STREAM result, multi-threaded (threads own ranges of
+ * groups; zero fill + scatter of the non-zeros, so the cost is that of writing the arrays once).
+ *   masks    uint32[n_steps][G]                    values  uint16[n_chunks][G][cap], n_chunks = ceil(n_steps / chunk)
+ *   chunk    transitions per launch that produced the stream (n_steps for one ovc_rollout call)
+ *   outputs / env_layout / reward_tbl / n_threads as ovc_expand_codes_host
+ *   overflow (nullable) receives the number of (chunk, group) slices whose word count exceeded cap: their excess
+ *            words read as zero and the caller must fall back to the dense code words of those chunks
+ */
+int ovc_expand_stream_host(const uint32_t *masks, const uint16_t *values, int64_t n_steps, int64_t chunk, int64_t cap,
+                           int64_t n_envs, const int32_t *env_layout, const int32_t *reward_tbl, int n_layouts,
+                           int16_t *sparse, int8_t *shaped, uint8_t *done, int32_t *events, int n_threads, int64_t *overflow);
 
 /*
  * OvercookedEnv.reset (overcooked_env.py:288-319) for the envs whose mask[i] != 0 (all if mask

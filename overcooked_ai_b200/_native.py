@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libovc_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 F_AUTO_RESET = 1
 F_PDL = 2
 F_ACT_U8 = 4
@@ -18,6 +18,9 @@ F_OUT_NARROW = 8
 F_OUT_PACKED = 16
 F_OUT_CODES = 32
 F_ACT_PACKED = 64
+F_OUT_STREAM = 128
+F_STREAM_CAP_SHIFT = 16
+STREAM_CAP_MAX = 0xFFFF
 F_IO_SHIFT = 8
 IO_DEFAULT, IO_TMA_TENSOR, IO_TMA_BULK, IO_DIRECT = 0, 1, 2, 3
 DT_F32, DT_U8, DT_I32, DT_BF16 = 0, 1, 2, 3
@@ -37,7 +40,8 @@ class PipelineDesc(ctypes.Structure):
                 ("horizon", ctypes.c_int32), ("flags", ctypes.c_int32), ("chunk", ctypes.c_int32),
                 ("has_random_start", ctypes.c_int32), ("random_start", RandomStart),
                 ("d_actions", ctypes.c_void_p * 2), ("d_sparse", ctypes.c_void_p * 2), ("d_shaped", ctypes.c_void_p * 2),
-                ("d_done", ctypes.c_void_p * 2), ("d_events", ctypes.c_void_p * 2)]
+                ("d_done", ctypes.c_void_p * 2), ("d_events", ctypes.c_void_p * 2),
+                ("stream_cap", ctypes.c_int32), ("reserved", ctypes.c_int32), ("d_codes_full", ctypes.c_void_p * 2)]
 
 
 _lib = None
@@ -71,6 +75,7 @@ def lib():
     L.ovc_potential.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, i64, i32, vp]
     L.ovc_potential_table_size.restype = ctypes.c_size_t
     L.ovc_expand_codes_host.argtypes = [vp, i64, i64, vp, vp, i32, vp, vp, vp, vp, i32]
+    L.ovc_expand_stream_host.argtypes = [vp, vp, i64, i64, i64, i64, vp, vp, i32, vp, vp, vp, vp, i32, ctypes.POINTER(i64)]
     L.ovc_pipeline_create.argtypes = [ctypes.POINTER(PipelineDesc), ctypes.POINTER(vp)]
     L.ovc_pipeline_run.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, i32, ctypes.POINTER(i64)]
     L.ovc_pipeline_wait.argtypes = [vp, i64]
@@ -78,7 +83,7 @@ def lib():
     L.ovc_pipeline_destroy.argtypes = [vp]
     L.ovc_pipeline_destroy.restype = None
     for f in (L.ovc_step, L.ovc_rollout, L.ovc_reset, L.ovc_encode_lossless, L.ovc_featurize, L.ovc_potential,
-              L.ovc_expand_codes_host, L.ovc_pipeline_create, L.ovc_pipeline_run, L.ovc_pipeline_wait, L.ovc_pipeline_join):
+              L.ovc_expand_codes_host, L.ovc_expand_stream_host, L.ovc_pipeline_create, L.ovc_pipeline_run, L.ovc_pipeline_wait, L.ovc_pipeline_join):
         f.restype = i32
     if L.ovc_abi_version() != ABI_VERSION:
         raise NativeLibraryError("ABI version mismatch: library %d, binding %d" % (L.ovc_abi_version(), ABI_VERSION))
@@ -89,7 +94,7 @@ def lib():
 EXPORTED_SYMBOLS = (
     "ovc_abi_version", "ovc_layout_table_size", "ovc_feat_lut_entry_size", "ovc_last_error",
     "ovc_step", "ovc_rollout", "ovc_reset", "ovc_encode_lossless", "ovc_featurize", "ovc_potential",
-    "ovc_potential_table_size", "ovc_expand_codes_host",
+    "ovc_potential_table_size", "ovc_expand_codes_host", "ovc_expand_stream_host",
     "ovc_pipeline_create", "ovc_pipeline_run", "ovc_pipeline_wait", "ovc_pipeline_join", "ovc_pipeline_destroy",
 )
 

@@ -165,6 +165,79 @@ class BatchedOvercookedEnv(object):
             int(l.reward_shaping_params[k]) for k in ("PLACEMENT_IN_POT_REW", "DISH_PICKUP_REWARD", "SOUP_PICKUP_REWARD")) <= 127
             for l in self.layouts)
 
+    def n_groups(self):
+        """Groups of 32 consecutive environments (one warp each) — the unit of the sparse event stream."""
+        return (self.n_envs + 31) // 32
+
+    def alloc_stream_out(self, T, cap, n_chunks=1, pin=False, dense_backup=False):
+        """Buffers of the sparse event stream (OVC_F_OUT_STREAM): (masks uint32 as int32 [T, G], values int16 [n_chunks, G, cap],
+        dense code words int16 [T, N] or None)."""
+        G = self.n_groups()
+        mk = (lambda sh, dt: torch.zeros(sh, dtype=dt, pin_memory=True)) if pin else (lambda sh, dt: torch.zeros(sh, dtype=dt, device=self.device))
+        return (mk((T, G), torch.int32), mk((n_chunks, G, cap), torch.int16), mk((T, self.n_envs), torch.int16) if dense_backup else None)
+
+    def rollout_stream(self, actions, cap, out=None, dense_backup=False):
+        """T transitions in one launch with the result as a sparse event stream (include/ovc_b200.h OVC_F_OUT_STREAM):
+        per transition and group of 32 environments one lane mask of the non-zero code words, plus each group's
+        non-zero words compacted in (transition, lane) order, at most ``cap`` per group (the masks count the rest).
+        actions: int32 / uint8 [T, N, 2] or one-byte joint actions uint8 [T, N].  Returns (masks, values, dense or None);
+        expand with ``expand_stream``."""
+        assert actions.dtype in (torch.int32, torch.uint8) and actions.is_cuda and actions.is_contiguous() and actions.dim() in (2, 3)
+        T = actions.shape[0]
+        assert actions.shape[1] == self.n_envs and 1 <= cap <= _native.STREAM_CAP_MAX
+        if out is None:
+            out = self.alloc_stream_out(T, cap, dense_backup=dense_backup)
+        masks, values, dense = out
+        assert masks.dtype == torch.int32 and tuple(masks.shape) == (T, self.n_groups()) and masks.is_cuda and masks.is_contiguous()
+        assert values.dtype == torch.int16 and values.numel() == self.n_groups() * cap and values.is_cuda and values.is_contiguous()
+        flags = self._flags() | _native.F_OUT_STREAM | (int(cap) << _native.F_STREAM_CAP_SHIFT)
+        if actions.dim() == 2:
+            assert actions.dtype == torch.uint8
+            flags |= _native.F_ACT_PACKED
+        elif actions.dtype == torch.uint8:
+            flags |= _native.F_ACT_U8
+        if flags >= 2**31:  # the C int carries the capacity in its upper half
+            flags -= 2**32
+        _native.check(self._lib.ovc_rollout(
+            self.tables.data_ptr(), self.n_layouts, self.start_records.data_ptr(), self.state.data_ptr(),
+            actions.data_ptr(), values.data_ptr(), 0, 0 if dense is None else dense.data_ptr(), masks.data_ptr(),
+            self.n_envs, T, self.state_words, self.horizon, flags, self._rs_ptr(), self._stream()))
+        return out
+
+    def expand_stream(self, masks, values, chunk=None, sparse=True, shaped=True, done=True, events=False, n_threads=0, out=None):
+        """Dense host arrays from a HOST sparse event stream (ovc_expand_stream_host): masks int32 [T, G], values int16
+        [n_chunks, G, cap] with ``chunk`` transitions per launch (default: all T in one).  Returns (dict of arrays as
+        expand_codes, number of (chunk, group) slices that overflowed their capacity)."""
+        assert masks.dtype == torch.int32 and not masks.is_cuda and masks.is_contiguous() and masks.dim() == 2
+        assert values.dtype == torch.int16 and not values.is_cuda and values.is_contiguous() and values.dim() == 3
+        T, G = masks.shape
+        assert G == self.n_groups() and values.shape[1] == G
+        chunk = T if chunk is None else int(chunk)
+        assert values.shape[0] == -(-T // chunk)
+        N, cap = self.n_envs, values.shape[2]
+        tbl = self.code_reward_table()
+        lay = self.env_layout_host
+        if self.random_layout:
+            assert (tbl == tbl[:1]).all(), "random_layout with different reward tables: the codes alone do not name the layout"
+            lay = None
+        if out is None:
+            out = {}
+            if sparse:
+                out["sparse"] = torch.empty((T, N), dtype=torch.int16)
+            if shaped:
+                out["shaped"] = torch.empty((T, N, 2), dtype=torch.int8)
+            if done:
+                out["done"] = torch.empty((T, N), dtype=torch.uint8)
+            if events:
+                out["events"] = torch.empty((T, N, 2), dtype=torch.int32)
+        ptr = lambda k: out[k].data_ptr() if k in out else 0
+        tbl = np.ascontiguousarray(tbl, dtype=np.int32)
+        over = ctypes.c_int64(0)
+        _native.check(self._lib.ovc_expand_stream_host(
+            masks.data_ptr(), values.data_ptr(), T, chunk, cap, N, 0 if lay is None else lay.ctypes.data, tbl.ctypes.data,
+            self.n_layouts, ptr("sparse"), ptr("shaped"), ptr("done"), ptr("events"), int(n_threads), ctypes.byref(over)))
+        return out, int(over.value)
+
     def alloc_rollout_out(self, T, narrow=False, pin=False, packed=False, codes=False):
         """Output tensors for rollout(): (sparse[T,N], shaped[T,N,2], done[T,N], events[T,N,2]); int32, or with
         ``narrow`` int16 / int8 / uint8 / int32 (13 bytes per env-step), or with ``packed`` (6 bytes per env-step)
@@ -406,7 +479,8 @@ class HostRolloutPipeline(object):
     stream has been synchronised (``torch.cuda.current_stream().synchronize()``), not when ``run`` returns.
     """
 
-    def __init__(self, env, n_steps, chunk=50, narrow=False, packed=False, codes=False, host_buffers=1):
+    def __init__(self, env, n_steps, chunk=50, narrow=False, packed=False, codes=False, host_buffers=1, stream=False,
+                 stream_fill=0.25, packed_actions=True):
         """narrow=True: uint8 actions in, int16 sparse / int8 shaped / uint8 done / int32 events out — the same
         values in 2 + 13 instead of 8 + 24 bytes per env-step.  packed=True: uint8 actions in, int16 sparse / int8
         shaped / int16 event codes (+done) out — 2 + 6 bytes per env-step, lossless (wire.decode_event_codes).
@@ -414,26 +488,49 @@ class HostRolloutPipeline(object):
         event codes + done + reward-grant bits out — 1 + 2 bytes per env-step, lossless (env.expand_codes).
         host_buffers: number of pinned output sets, used round robin by successive run() calls (2 lets a consumer
         read pass i while pass i+1 is in flight, see run(wait=False))."""
+        """stream=True: the result as a sparse event stream (OVC_F_OUT_STREAM): per transition one lane mask per 32
+        environments + the non-zero code words, ``stream_fill`` x 32 x chunk value slots per group and chunk (0.125 + 2 x
+        stream_fill bytes per env-step device->host instead of 2); run() returns (masks, values) host tensors and
+        ``expand(result)`` rebuilds dense arrays, falling back to the dense code words kept on the device for any chunk
+        whose group overflowed.  packed_actions=False (with codes / stream): uint8 [T, N, 2] actions instead of one byte
+        per joint action."""
+        codes = codes or stream
         narrow = narrow or packed or codes
         self.env, self.T, self.chunk, self.narrow, self.packed = env, int(n_steps), int(chunk), bool(narrow), bool(packed)
-        self.codes = bool(codes)
+        self.codes, self.stream = bool(codes), bool(stream)
+        self.packed_actions = bool(packed_actions) and self.codes
         if narrow:
             assert env.narrow_ok(), "rewards of these layouts do not fit the narrow formats"
         N, dev = env.n_envs, env.device
         self._lib = env._lib
         self.act_dtype = torch.uint8 if narrow else torch.int32
-        self.act_shape = (N,) if codes else (N, 2)
+        self.act_shape = (N,) if self.packed_actions else (N, 2)
+        self.n_chunks = -(-self.T // self.chunk)
+        self.stream_cap = max(1, min(_native.STREAM_CAP_MAX, int(round(self.chunk * 32 * float(stream_fill))))) if stream else 0
         with torch.cuda.device(dev):
             self.d_act = [torch.empty((self.chunk,) + self.act_shape, dtype=self.act_dtype, device=dev) for _ in range(2)]
-            self.d_out = [env.alloc_rollout_out(self.chunk, narrow=narrow, packed=packed, codes=codes) for _ in range(2)]
-            self.h_outs = [env.alloc_rollout_out(self.T, narrow=narrow, pin=True, packed=packed, codes=codes)
-                           for _ in range(max(1, int(host_buffers)))]
+            if stream:
+                G = env.n_groups()
+                self.d_out = [(torch.empty((G, self.stream_cap), dtype=torch.int16, device=dev), None, None,
+                               torch.empty((self.chunk, G), dtype=torch.int32, device=dev)) for _ in range(2)]
+                # dense code words of a whole pass stay on the device (two sets: pass k uses set k & 1): overflow backup
+                self.d_codes_full = [torch.empty((self.T, N), dtype=torch.int16, device=dev) for _ in range(2)]
+                self.h_outs = [(torch.zeros((self.n_chunks, G, self.stream_cap), dtype=torch.int16, pin_memory=True), None, None,
+                                torch.zeros((self.T, G), dtype=torch.int32, pin_memory=True)) for _ in range(max(1, int(host_buffers)))]
+            else:
+                self.d_out = [env.alloc_rollout_out(self.chunk, narrow=narrow, packed=packed, codes=codes) for _ in range(2)]
+                self.h_outs = [env.alloc_rollout_out(self.T, narrow=narrow, pin=True, packed=packed, codes=codes)
+                               for _ in range(max(1, int(host_buffers)))]
         self.h_out = self.h_outs[0]
         self._runs = 0
-        self.h2d_bytes_per_step = N * (1 if codes else 2) * self.d_act[0].element_size()
-        self.d2h_bytes_per_step = sum(N * (2 if o.dim() == 3 else 1) * o.element_size() for o in self.h_out if o is not None)
-        flags = env._flags() | (_native.F_ACT_PACKED if codes else _native.F_ACT_U8 if narrow else 0)
-        flags |= _native.F_OUT_CODES if codes else _native.F_OUT_PACKED if packed else _native.F_OUT_NARROW if narrow else 0
+        self.h2d_bytes_per_step = N * (1 if self.packed_actions else 2) * self.d_act[0].element_size()
+        if stream:
+            self.d2h_bytes_per_step = (self.h_out[3].numel() * 4 + self.h_out[0].numel() * 2) / float(self.T)
+        else:
+            self.d2h_bytes_per_step = sum(N * (2 if o.dim() == 3 else 1) * o.element_size() for o in self.h_out if o is not None)
+        flags = env._flags() | (_native.F_ACT_PACKED if self.packed_actions else _native.F_ACT_U8 if narrow else 0)
+        flags |= (_native.F_OUT_STREAM if stream else _native.F_OUT_CODES if codes else _native.F_OUT_PACKED if packed
+                  else _native.F_OUT_NARROW if narrow else 0)
         d = _native.PipelineDesc()
         d.layouts, d.n_layouts, d.state_words = env.tables.data_ptr(), env.n_layouts, env.state_words
         d.start_records, d.state, d.n_envs = env.start_records.data_ptr(), env.state.data_ptr(), N
@@ -445,6 +542,8 @@ class HostRolloutPipeline(object):
         for b in range(2):
             d.d_actions[b] = self.d_act[b].data_ptr()
             d.d_sparse[b], d.d_shaped[b], d.d_done[b], d.d_events[b] = (ptr(t) for t in self.d_out[b])
+            d.d_codes_full[b] = self.d_codes_full[b].data_ptr() if stream else 0
+        d.stream_cap = self.stream_cap
         h = ctypes.c_void_p()
         with torch.cuda.device(dev):
             _native.check(self._lib.ovc_pipeline_create(ctypes.byref(d), ctypes.byref(h)))
@@ -459,6 +558,7 @@ class HostRolloutPipeline(object):
         assert actions_host.dtype == self.act_dtype and actions_host.is_pinned() and actions_host.is_contiguous()
         assert tuple(actions_host.shape) == (self.T,) + self.act_shape
         h_out = self.h_outs[self._runs % len(self.h_outs)]
+        self._last_set = self._runs & 1  # which dense-backup set this pass writes (the native side counts the same way)
         self._runs += 1
         ptr = lambda t: 0 if t is None else t.data_ptr()
         ticket = ctypes.c_int64(-1)
@@ -469,6 +569,20 @@ class HostRolloutPipeline(object):
         if wait:
             return h_out
         return h_out, PassTicket(self, ticket.value)
+
+    def expand(self, h_out, codes_set=None, out=None, n_threads=0, **which):
+        """stream=True: dense host arrays (dict, as env.expand_codes) from one pass's (values, -, -, masks) host tensors,
+        AFTER the pass has landed.  ``codes_set``: the dense-backup set that pass wrote (``self._last_set`` right after
+        its run()); if a group overflowed its value slots the dense words are fetched from that set and expanded instead
+        (correct as long as no later pass has reused the set: passes k and k + 2 share one)."""
+        assert self.stream
+        dense, over = self.env.expand_stream(h_out[3], h_out[0], chunk=self.chunk, out=out, n_threads=n_threads, **which)
+        self.last_overflow = over
+        if over:
+            cs = self._last_set if codes_set is None else codes_set
+            words = self.d_codes_full[cs].cpu()  # synchronising copy: the rare slow path
+            dense = self.env.expand_codes(words, out=dense, n_threads=n_threads)
+        return dense
 
     def join(self):
         """Make the current stream wait for everything the pipeline has in flight."""

@@ -416,10 +416,11 @@ static int launch_rollout(const StepArgs &a, cudaStream_t st) {
     int rc = make_tmap<S>(&tmap, a.state, a.n_envs, C::BOX_ROWS);
     if (rc) return rc;
     const size_t smem = C::smem_bytes(a.n_layouts);
-    const bool wide = !(a.flags & (OVC_F_ACT_U8 | OVC_F_ACT_PACKED | OVC_F_OUT_NARROW | OVC_F_OUT_PACKED | OVC_F_OUT_CODES));
+    const bool wide = !(a.flags & (OVC_F_ACT_U8 | OVC_F_ACT_PACKED | OVC_F_OUT_NARROW | OVC_F_OUT_PACKED | OVC_F_OUT_CODES | OVC_F_OUT_STREAM));
+    const bool stream = a.flags & OVC_F_OUT_STREAM;
     void (*kern)(const CUtensorMap, const StepArgs) =
-        a.has_rs ? (wide ? rollout_kernel<S, TILE, true, true> : rollout_kernel<S, TILE, true, false>)
-                 : (wide ? rollout_kernel<S, TILE, false, true> : rollout_kernel<S, TILE, false, false>);
+        a.has_rs ? (wide ? rollout_kernel<S, TILE, true, FMT_WIDE> : stream ? rollout_kernel<S, TILE, true, FMT_STREAM> : rollout_kernel<S, TILE, true, FMT_HOST>)
+                 : (wide ? rollout_kernel<S, TILE, false, FMT_WIDE> : stream ? rollout_kernel<S, TILE, false, FMT_STREAM> : rollout_kernel<S, TILE, false, FMT_HOST>);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "rollout kernel shared-memory attribute");
@@ -461,7 +462,8 @@ static bool use_rollout_kernel(const StepArgs &a, int io) {
         const char *e = getenv("OVC_K5_LEGACY");  // measure / test the pre-round-2 fused path
         off = e && atoi(e) ? 1 : 0;
     }
-    return !off && a.n_steps > 1 && a.n_steps <= ROLLOUT_MAX_STEPS && io == 1 && a.n_layouts <= MAX_SMEM_LAYOUTS;
+    const bool stream = a.flags & OVC_F_OUT_STREAM;  // only the rollout kernel produces the sparse stream (step_impl checked it can)
+    return (!off || stream) && (a.n_steps > 1 || stream) && a.n_steps <= ROLLOUT_MAX_STEPS && io == 1 && a.n_layouts <= MAX_SMEM_LAYOUTS;
 }
 
 template <int S>
@@ -517,12 +519,20 @@ static int step_impl(const void *layouts, int n_layouts, const int32_t *start_re
     int rc = check_common(layouts, n_layouts, state, n_envs, S);
     if (rc) return rc;
     const bool codes = flags & OVC_F_OUT_CODES;
-    if (!actions || !events || !start_records || (!codes && (!sparse || !shaped)) ||
-        (!done && !(flags & (OVC_F_OUT_PACKED | OVC_F_OUT_CODES))))
+    const bool is_stream = flags & OVC_F_OUT_STREAM;
+    if (is_stream && (flags & (OVC_F_OUT_CODES | OVC_F_OUT_PACKED | OVC_F_OUT_NARROW)))
+        return fail(OVC_E_BADARG, "OVC_F_OUT_STREAM excludes the other output formats");
+    if (!actions || !events || !start_records || (!codes && !sparse) || (!codes && !is_stream && !shaped) ||
+        (!done && !(flags & (OVC_F_OUT_PACKED | OVC_F_OUT_CODES | OVC_F_OUT_STREAM))))
         return fail(OVC_E_BADARG, "null pointer argument");
     if (codes) sparse = nullptr, shaped = nullptr, done = nullptr;
-    const bool small_out = flags & (OVC_F_OUT_NARROW | OVC_F_OUT_PACKED | OVC_F_OUT_CODES);
-    const bool small_ev = flags & (OVC_F_OUT_PACKED | OVC_F_OUT_CODES);
+    if (is_stream) {
+        shaped = nullptr;
+        if ((((unsigned)flags >> OVC_F_STREAM_CAP_SHIFT) & 0xFFFFu) == 0) return fail(OVC_E_BADARG, "OVC_F_OUT_STREAM needs a capacity in flags bits 16-31");
+        if (((uintptr_t)events & 3) || ((uintptr_t)sparse & 1) || ((uintptr_t)done & 1)) return fail(OVC_E_BADARG, "stream buffers are misaligned");
+    }
+    const bool small_out = flags & (OVC_F_OUT_NARROW | OVC_F_OUT_PACKED | OVC_F_OUT_CODES | OVC_F_OUT_STREAM);
+    const bool small_ev = flags & (OVC_F_OUT_PACKED | OVC_F_OUT_CODES | OVC_F_OUT_STREAM);
     const bool small_act = flags & (OVC_F_ACT_U8 | OVC_F_ACT_PACKED);
     if (((small_act ? 0 : (uintptr_t)actions) | (small_out ? 0 : (uintptr_t)shaped) | (small_ev ? 0 : (uintptr_t)events)) & 7)
         return fail(OVC_E_BADARG, "actions / shaped / events must be 8-byte aligned");
@@ -535,6 +545,8 @@ static int step_impl(const void *layouts, int n_layouts, const int32_t *start_re
     if (io == 0) io = 1;
     if (io < 1 || io > 3) return fail(OVC_E_BADARG, "unknown record I/O strategy", (long long)(io));
     if (io == 1 && (n_envs * (S / (S == 16 ? 16 : 32))) > 0x7FFFFFFFLL) io = 2;  // tensor coordinates are int32
+    if (is_stream && (io != 1 || n_layouts > MAX_SMEM_LAYOUTS || n_steps > ROLLOUT_MAX_STEPS))
+        return fail(OVC_E_UNSUPPORTED, "OVC_F_OUT_STREAM needs the rollout kernel: default record I/O, at most 8 layouts");
     StepArgs a{(const ovc_layout_t *)layouts, start_records, state, actions, sparse, shaped, done, events,
                n_envs, n_layouts, n_steps, horizon, flags, rs != nullptr, rs ? *rs : ovc_random_start_t{0, 0, 0}};
     cudaStream_t st = (cudaStream_t)stream;
@@ -640,6 +652,13 @@ int ovc_pipeline_join(ovc_pipeline_t *p, void *stream) {
     return ovc::pipeline_join(p, (cudaStream_t)stream);
 }
 void ovc_pipeline_destroy(ovc_pipeline_t *p) { ovc::pipeline_destroy(p); }
+
+int ovc_expand_stream_host(const uint32_t *masks, const uint16_t *values, int64_t n_steps, int64_t chunk, int64_t cap,
+                           int64_t n_envs, const int32_t *env_layout, const int32_t *reward_tbl, int n_layouts, int16_t *sparse,
+                           int8_t *shaped, uint8_t *done, int32_t *events, int n_threads, int64_t *overflow) {
+    return ovc::expand_stream_host(masks, values, n_steps, chunk, cap, n_envs, env_layout, reward_tbl, n_layouts, sparse, shaped,
+                                   done, events, n_threads, overflow);
+}
 
 int ovc_expand_codes_host(const uint16_t *codes, int64_t n_steps, int64_t n_envs, const int32_t *env_layout,
                           const int32_t *reward_tbl, int n_layouts, int16_t *sparse, int8_t *shaped, uint8_t *done,

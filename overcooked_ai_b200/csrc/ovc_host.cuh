@@ -135,6 +135,16 @@ private:
     int n_jobs_ = 0, next_ = 0, pending_ = 0, limit_ = 0, active_ = 0;
 };
 
+static int default_host_threads() {  // every CPU of the process's affinity mask (a fractional-node lease sees the whole machine online)
+    cpu_set_t set;
+    int n = sched_getaffinity(0, sizeof set, &set) == 0 ? CPU_COUNT(&set) : 0;
+    if (n <= 0) {
+        const long c = sysconf(_SC_NPROCESSORS_ONLN);
+        n = c > 0 ? (int)c : 1;
+    }
+    return n;
+}
+
 static int expand_codes_host(const uint16_t *codes, int64_t n_steps, int64_t n_envs, const int32_t *env_layout,
                              const int32_t *reward_tbl, int n_layouts, int16_t *sparse, int8_t *shaped, uint8_t *done,
                              int32_t *events, int n_threads) {
@@ -146,14 +156,7 @@ static int expand_codes_host(const uint16_t *codes, int64_t n_steps, int64_t n_e
     int32_t mask[32];
     build_code_masks(mask);
     const int64_t n = n_steps * n_envs;
-    if (n_threads <= 0) {  // every CPU of the process's affinity mask (a fractional-node lease sees the whole machine online)
-        cpu_set_t set;
-        n_threads = sched_getaffinity(0, sizeof set, &set) == 0 ? CPU_COUNT(&set) : 0;
-        if (n_threads <= 0) {
-            const long c = sysconf(_SC_NPROCESSORS_ONLN);
-            n_threads = c > 0 ? (int)c : 1;
-        }
-    }
+    if (n_threads <= 0) n_threads = default_host_threads();
     if (n_threads > 256) n_threads = 256;
     if (n < (int64_t)n_threads * 4096) n_threads = (int)(n / 4096) + 1;
     if (n_threads == 1) {
@@ -168,17 +171,102 @@ static int expand_codes_host(const uint16_t *codes, int64_t n_steps, int64_t n_e
     return OVC_OK;
 }
 
+// OVC_F_OUT_STREAM -> dense arrays.  A thread owns a range of groups [g0, g1) = environments [32 g0, 32 g1): per
+// transition it zero-fills its segment of every output row and scatters the few non-zero words its masks name,
+// reading each group's value slice sequentially (the cursor restarts at every chunk).
+static void expand_stream_range(const uint32_t *masks, const uint16_t *values, int64_t n_steps, int64_t chunk, int64_t cap,
+                                int64_t n_envs, int64_t G, int64_t g0, int64_t g1, const int32_t *env_layout,
+                                const int32_t *reward_tbl, int16_t *sparse, int8_t *shaped, uint8_t *done, int32_t *events,
+                                const int32_t *mask, int64_t *overflow) {
+    const int64_t e0 = g0 * 32, e1 = g1 * 32 < n_envs ? g1 * 32 : n_envs;
+    if (e1 <= e0) return;
+    std::vector<uint32_t> cur((size_t)(g1 - g0));
+    int64_t over = 0;
+    for (int64_t t = 0; t < n_steps; t++) {
+        const int64_t c = t / chunk;
+        if (t % chunk == 0) {
+            for (auto &x : cur) over += x > (uint64_t)cap, x = 0;
+        }
+        const int64_t row = t * n_envs;
+        if (sparse) memset(sparse + row + e0, 0, (size_t)(e1 - e0) * sizeof(int16_t));
+        if (shaped) memset(shaped + 2 * (row + e0), 0, (size_t)(e1 - e0) * 2);
+        if (done) memset(done + row + e0, 0, (size_t)(e1 - e0));
+        if (events) memset(events + 2 * (row + e0), 0, (size_t)(e1 - e0) * 2 * sizeof(int32_t));
+        const uint32_t *mrow = masks + t * G;
+        for (int64_t g = g0; g < g1; g++) {
+            uint32_t m = mrow[g];
+            if (!m) continue;
+            const uint16_t *vals = values + ((size_t)c * (size_t)G + (size_t)g) * (size_t)cap;
+            uint32_t &k = cur[(size_t)(g - g0)];
+            while (m) {
+                const int l = __builtin_ctz(m);
+                m &= m - 1;
+                const uint32_t kk = k++;
+                if (kk >= (uint64_t)cap) continue;  // dropped by the kernel: counted at the chunk boundary
+                const unsigned w = vals[kk];
+                const int64_t e = g * 32 + l, i = row + e;
+                const unsigned c0 = w & 31u, c1 = (w >> 5) & 31u;
+                const int32_t *tb = reward_tbl + (env_layout ? (size_t)env_layout[e] * 64 : 0);
+                if (sparse) sparse[i] = (int16_t)(tb[c0] + tb[c1]);
+                if (shaped) {
+                    shaped[2 * i] = (int8_t)((w >> 12) & 1u ? tb[32 + c0] : 0);
+                    shaped[2 * i + 1] = (int8_t)((w >> 13) & 1u ? tb[32 + c1] : 0);
+                }
+                if (done) done[i] = (uint8_t)((w >> 10) & 1u);
+                if (events) {
+                    const bool stepped = (w >> 11) & 1u;
+                    events[2 * i] = stepped ? (int32_t)OVC_EVF_STEPPED_DONE : mask[c0];
+                    events[2 * i + 1] = stepped ? (int32_t)OVC_EVF_STEPPED_DONE : mask[c1];
+                }
+            }
+        }
+    }
+    for (auto &x : cur) over += x > (uint64_t)cap;
+    if (over) __atomic_fetch_add(overflow, over, __ATOMIC_RELAXED);
+}
+
+static int expand_stream_host(const uint32_t *masks, const uint16_t *values, int64_t n_steps, int64_t chunk, int64_t cap,
+                              int64_t n_envs, const int32_t *env_layout, const int32_t *reward_tbl, int n_layouts, int16_t *sparse,
+                              int8_t *shaped, uint8_t *done, int32_t *events, int n_threads, int64_t *overflow) {
+    if (!masks || !values || !reward_tbl) return fail(OVC_E_BADARG, "null pointer argument");
+    if (n_steps < 0 || n_envs < 0 || n_layouts < 1 || chunk < 1 || cap < 1) return fail(OVC_E_BADARG, "bad sizes");
+    if (env_layout)
+        for (int64_t e = 0; e < n_envs; e++)
+            if (env_layout[e] < 0 || env_layout[e] >= n_layouts) return fail(OVC_E_BADARG, "layout id out of range", (long long)e);
+    int32_t mask[32];
+    build_code_masks(mask);
+    const int64_t G = (n_envs + 31) / 32;
+    int64_t over = 0;
+    if (n_threads <= 0) n_threads = default_host_threads();
+    if (n_threads > 256) n_threads = 256;
+    if (G < (int64_t)n_threads * 4) n_threads = (int)(G / 4) + 1;
+    if (n_threads == 1) {
+        expand_stream_range(masks, values, n_steps, chunk, cap, n_envs, G, 0, G, env_layout, reward_tbl, sparse, shaped, done, events, mask, &over);
+    } else {
+        const int n_slices = n_threads * 4;
+        HostPool::get().run(n_slices, n_threads, [&](int k) {
+            expand_stream_range(masks, values, n_steps, chunk, cap, n_envs, G, G * k / n_slices, G * (k + 1) / n_slices, env_layout, reward_tbl,
+                                sparse, shaped, done, events, mask, &over);
+        });
+    }
+    if (overflow) *overflow = over;
+    return OVC_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host-buffer rollout pipeline (ovc_pipeline_*): H2D / rollout kernel / D2H on three streams
 // ------------------------------------------------------------------------------------------------
 struct OutFmt {
     int act, sparse, shaped, done, events;  // bytes per env-step of each array (0 = not produced)
+    bool stream;                            // OVC_F_OUT_STREAM: sizes come from the group count and the capacity instead
 };
 
 static OutFmt formats_of(int flags) {
     OutFmt f;
     f.act = (flags & OVC_F_ACT_PACKED) ? 1 : (flags & OVC_F_ACT_U8) ? 2 : 8;
-    if (flags & OVC_F_OUT_CODES) f.sparse = 0, f.shaped = 0, f.done = 0, f.events = 2;
+    f.stream = flags & OVC_F_OUT_STREAM;
+    if (f.stream) f.sparse = 0, f.shaped = 0, f.done = 0, f.events = 0;
+    else if (flags & OVC_F_OUT_CODES) f.sparse = 0, f.shaped = 0, f.done = 0, f.events = 2;
     else if (flags & OVC_F_OUT_PACKED) f.sparse = 2, f.shaped = 2, f.done = 0, f.events = 2;
     else if (flags & OVC_F_OUT_NARROW) f.sparse = 2, f.shaped = 2, f.done = 1, f.events = 8;
     else f.sparse = 4, f.shaped = 8, f.done = 4, f.events = 8;
@@ -214,9 +302,11 @@ static int pipeline_create(const ovc_pipeline_desc_t *desc, ovc_pipeline_t **out
     if (rc) return rc;
     const OutFmt f = formats_of(desc->flags);
     for (int b = 0; b < 2; b++)
-        if (!desc->d_actions[b] || !desc->d_events[b] || (f.sparse && !desc->d_sparse[b]) || (f.shaped && !desc->d_shaped[b]) ||
+        if (!desc->d_actions[b] || !desc->d_events[b] || ((f.sparse || f.stream) && !desc->d_sparse[b]) || (f.shaped && !desc->d_shaped[b]) ||
             (f.done && !desc->d_done[b]))
             return fail(OVC_E_BADARG, "missing device staging buffer");
+    if (f.stream && (desc->stream_cap < 1 || desc->stream_cap > OVC_F_STREAM_CAP_MAX))
+        return fail(OVC_E_BADARG, "stream_cap must be 1..65535", (long long)desc->stream_cap);
     ovc_pipeline_t *p = new ovc_pipeline_t();
     p->d = *desc;
     p->fmt = f;
@@ -250,11 +340,12 @@ static int pipeline_join(ovc_pipeline_t *p, cudaStream_t caller) {
 static int pipeline_run(ovc_pipeline_t *p, const void *h_actions, void *h_sparse, void *h_shaped, void *h_done, void *h_events,
                         int n_steps, cudaStream_t caller, int join, int64_t *ticket) {
     const OutFmt &f = p->fmt;
-    if (!h_actions || !h_events || (f.sparse && !h_sparse) || (f.shaped && !h_shaped) || (f.done && !h_done))
+    if (!h_actions || !h_events || ((f.sparse || f.stream) && !h_sparse) || (f.shaped && !h_shaped) || (f.done && !h_done))
         return fail(OVC_E_BADARG, "null host buffer");
     if (n_steps < 1) return fail(OVC_E_BADARG, "n_steps must be >= 1");
     const ovc_pipeline_desc_t &d = p->d;
-    const size_t N = (size_t)d.n_envs;
+    const size_t N = (size_t)d.n_envs, G = (N + 31) / 32;
+    void *const codes_full = f.stream ? d.d_codes_full[p->n_pass & 1] : nullptr;
     OVC_CK(cudaEventRecord(p->ev_start, caller), "pipeline start record");
     OVC_CK(cudaStreamWaitEvent(p->s_h2d, p->ev_start, 0), "pipeline start wait");
     OVC_CK(cudaStreamWaitEvent(p->s_comp, p->ev_start, 0), "pipeline start wait");
@@ -271,7 +362,14 @@ static int pipeline_run(ovc_pipeline_t *p, const void *h_actions, void *h_sparse
         // stage 2: the fused rollout kernel, once the outputs of two chunks ago have left the staging buffers
         OVC_CK(cudaStreamWaitEvent(p->s_comp, p->ev_in[b], 0), "pipeline wait");
         if (p->d2h_rec[b]) OVC_CK(cudaStreamWaitEvent(p->s_comp, p->ev_d2h[b], 0), "pipeline wait");
-        int rc = step_impl(d.layouts, d.n_layouts, d.start_records, d.state, (const int32_t *)d.d_actions[b], (int32_t *)d.d_sparse[b],
+        int rc;
+        if (f.stream)  // masks + compacted values of this chunk; the dense words (if kept) go to their rows of the pass buffer
+            rc = step_impl(d.layouts, d.n_layouts, d.start_records, d.state, (const int32_t *)d.d_actions[b], (int32_t *)d.d_sparse[b], nullptr,
+                           codes_full ? (int32_t *)((char *)codes_full + off * 2) : nullptr, (int32_t *)d.d_events[b], d.n_envs, tc,
+                           d.state_words, d.horizon, (int)((unsigned)d.flags | ((unsigned)d.stream_cap << OVC_F_STREAM_CAP_SHIFT)),
+                           d.has_random_start ? &d.random_start : nullptr, p->s_comp);
+        else
+            rc = step_impl(d.layouts, d.n_layouts, d.start_records, d.state, (const int32_t *)d.d_actions[b], (int32_t *)d.d_sparse[b],
                            (int32_t *)d.d_shaped[b], (int32_t *)d.d_done[b], (int32_t *)d.d_events[b], d.n_envs, tc, d.state_words,
                            d.horizon, d.flags, d.has_random_start ? &d.random_start : nullptr, p->s_comp);
         if (rc) return rc;
@@ -282,7 +380,12 @@ static int pipeline_run(ovc_pipeline_t *p, const void *h_actions, void *h_sparse
         if (f.sparse) OVC_CK(cudaMemcpyAsync((char *)h_sparse + off * f.sparse, d.d_sparse[b], cnt * f.sparse, cudaMemcpyDeviceToHost, p->s_d2h), "pipeline D2H copy");
         if (f.shaped) OVC_CK(cudaMemcpyAsync((char *)h_shaped + off * f.shaped, d.d_shaped[b], cnt * f.shaped, cudaMemcpyDeviceToHost, p->s_d2h), "pipeline D2H copy");
         if (f.done) OVC_CK(cudaMemcpyAsync((char *)h_done + off * f.done, d.d_done[b], cnt * f.done, cudaMemcpyDeviceToHost, p->s_d2h), "pipeline D2H copy");
-        OVC_CK(cudaMemcpyAsync((char *)h_events + off * f.events, d.d_events[b], cnt * f.events, cudaMemcpyDeviceToHost, p->s_d2h), "pipeline D2H copy");
+        if (f.stream) {
+            const size_t c = (size_t)(t0 / d.chunk), vbytes = G * (size_t)d.stream_cap * 2;
+            OVC_CK(cudaMemcpyAsync((char *)h_events + (size_t)t0 * G * 4, d.d_events[b], (size_t)tc * G * 4, cudaMemcpyDeviceToHost, p->s_d2h), "pipeline D2H copy");
+            OVC_CK(cudaMemcpyAsync((char *)h_sparse + c * vbytes, d.d_sparse[b], vbytes, cudaMemcpyDeviceToHost, p->s_d2h), "pipeline D2H copy");
+        } else
+            OVC_CK(cudaMemcpyAsync((char *)h_events + off * f.events, d.d_events[b], cnt * f.events, cudaMemcpyDeviceToHost, p->s_d2h), "pipeline D2H copy");
         OVC_CK(cudaEventRecord(p->ev_d2h[b], p->s_d2h), "pipeline record");
         p->d2h_rec[b] = true;
     }

@@ -19,8 +19,8 @@
 //     event masks of the int32 format are one shared-memory table lookup of that code, and the 2-byte host-transfer
 //     word is the two codes side by side.
 //
-// One thread owns one environment; a warp's 32 environments run the (single-emission) interact body as a loop of up
-// to two trips exactly as in ovc_step.cuh.  Results are bit-identical to step_kernel (tests replay every fixture
+// One thread owns one environment; the interact body is emitted twice (first interacting player of an environment,
+// then player 1 where both interact: most warps skip the second).  Results are bit-identical to step_kernel (tests replay every fixture
 // through both).  Included by ovc_b200.cu after the PTX helpers and StepArgs.
 #pragma once
 
@@ -249,16 +249,26 @@ __device__ __forceinline__ unsigned interact_v2(const R &r, uint32_t L, uint32_t
     return code;
 }
 
+// Kernel instantiations by transfer format: the device-resident int32 formats carry none of the format tests
+// (3 % of a transition when they sat in every instantiation), the sparse event stream carries the warp votes.
+constexpr int FMT_WIDE = 0, FMT_HOST = 1, FMT_STREAM = 2;
+
 // Running output / action pointers of one thread: advanced by one transition (n_envs elements) per step, so the
 // loop carries 64-bit adds instead of 64-bit multiplies.  Element sizes follow the transfer format (ovc_b200.cu).
-template <bool WIDE>
+template <int FMT>
 struct RollIO {
+    static constexpr bool WIDE = FMT == FMT_WIDE;
     const char *act;
     char *sparse, *shaped, *done, *events;
     long long s_act, s_sparse, s_shaped, s_done, s_events;  // bytes per transition (uniform)
     int flags;
-    __device__ __forceinline__ RollIO(const StepArgs &a, long long env) {
+    // FMT_STREAM: `events` walks the lane-mask rows uint32[n_steps][n_groups], `sparse` is the group's slice of the
+    // value array uint16[n_groups][cap], `done` (nullable) the dense code words uint16[n_steps][n_envs]
+    unsigned live_mask, cnt, cap, lane_lt;
+    bool leader;
+    __device__ __forceinline__ RollIO(const StepArgs &a, long long env, unsigned live) {
         flags = a.flags;
+        live_mask = live, cnt = 0, cap = 0, lane_lt = 0, leader = false;
         int b_act = 8, b_sparse = 4, b_shaped = 8, b_done = 4, b_events = 8;
         if (!WIDE) {
             b_act = (flags & OVC_F_ACT_PACKED) ? 1 : (flags & OVC_F_ACT_U8) ? 2 : 8;
@@ -267,6 +277,17 @@ struct RollIO {
             else if (flags & OVC_F_OUT_NARROW) b_sparse = 2, b_shaped = 2, b_done = 1, b_events = 8;
         }
         act = reinterpret_cast<const char *>(a.actions) + env * b_act, s_act = a.n_envs * b_act;
+        if (FMT == FMT_STREAM) {
+            const long long n_groups = (a.n_envs + 31) >> 5, g = env >> 5;
+            cap = ((unsigned)flags >> OVC_F_STREAM_CAP_SHIFT) & 0xFFFFu;
+            const unsigned lane = (unsigned)env & 31u;
+            lane_lt = (1u << lane) - 1u, leader = lane == 0;
+            events = reinterpret_cast<char *>(a.events) + g * 4, s_events = n_groups * 4;
+            sparse = reinterpret_cast<char *>(a.sparse) + g * (long long)cap * 2, s_sparse = 0;
+            done = a.done ? reinterpret_cast<char *>(a.done) + env * 2 : nullptr, s_done = a.n_envs * 2;
+            shaped = nullptr, s_shaped = 0;
+            return;
+        }
         sparse = reinterpret_cast<char *>(a.sparse) + env * b_sparse, s_sparse = a.n_envs * b_sparse;
         shaped = reinterpret_cast<char *>(a.shaped) + env * b_shaped, s_shaped = a.n_envs * b_shaped;
         done = reinterpret_cast<char *>(a.done) + env * b_done, s_done = a.n_envs * b_done;
@@ -284,8 +305,26 @@ struct RollIO {
         return *reinterpret_cast<const int2 *>(act);
     }
     __device__ __forceinline__ void next_action() { act += s_act; }
-    // writes this transition's outputs and advances to the next transition
+    // Writes this transition's outputs and advances to the next transition.  Called at ONE program point by every
+    // live thread of the warp, once per transition (FMT_STREAM votes across the warp here).
     __device__ __forceinline__ void write(const RollOut &o, int done_v, bool stepped, uint32_t mask) {
+        if (FMT == FMT_STREAM) {
+            // What a rollout produces is mostly zeros.  Per warp (32 consecutive environments) and transition: ONE
+            // 32-bit lane mask of the non-zero code words (__ballot_sync), and the non-zero words compacted behind the
+            // group's earlier ones (rank among the voters = popcount of the lower lanes).
+            const unsigned w = o.c0 | (o.c1 << 5) | ((unsigned)done_v << 10) | (stepped ? 1u << 11 : 0u) |
+                               (o.sh0 != 0 ? 1u << 12 : 0u) | (o.sh1 != 0 ? 1u << 13 : 0u);
+            const unsigned m = __ballot_sync(live_mask, w != 0);
+            if (leader) *reinterpret_cast<unsigned *>(events) = m;
+            if (w != 0) {
+                const unsigned pos = cnt + __popc(m & lane_lt);
+                if (pos < cap) reinterpret_cast<unsigned short *>(sparse)[pos] = (unsigned short)w;  // beyond cap: dropped, the masks tell
+            }
+            cnt += __popc(m);
+            events += s_events;
+            if (done) *reinterpret_cast<unsigned short *>(done) = (unsigned short)w, done += s_done;
+            return;
+        }
         if (!WIDE && (flags & (OVC_F_OUT_CODES | OVC_F_OUT_PACKED))) {
             unsigned w = o.c0 | (o.c1 << 5) | ((unsigned)done_v << 10) | (stepped ? 1u << 11 : 0u);
             if (flags & OVC_F_OUT_CODES) {
@@ -329,10 +368,11 @@ struct RollCfg {
     static size_t smem_bytes(int n_layouts) { return (size_t)TILE_BYTES + (size_t)n_layouts * (sizeof(ovc_layout_t) + sizeof(Derived)) + 128 + 16; }
 };
 
-template <int S, int TILE, bool RS, bool WIDE>
+template <int S, int TILE, bool RS, int FMT>
 __global__ void __launch_bounds__(TILE)
 rollout_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
     using C = RollCfg<S, TILE>;
+    constexpr bool WIDE = FMT == FMT_WIDE;
     const int tid = threadIdx.x;
     const long long env0 = (long long)blockIdx.x * TILE;
     const long long env = env0 + tid;
@@ -407,6 +447,7 @@ rollout_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
     }
     __syncthreads();
 
+    const unsigned live_mask = __ballot_sync(0xFFFFFFFFu, live);  // the warp's live lanes (a partial last tile)
     if (live) {
         const TileRec<S, C::SWZ> r(smem_u32(tile), tid);
         const uint32_t tbl_s = smem_u32(tbl), der_s = smem_u32(der), mask_s = smem_u32(mask);
@@ -433,7 +474,7 @@ rollout_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
         };
         load_regs(0u);
 
-        RollIO<WIDE> io(a, env);
+        RollIO<FMT> io(a, env, live_mask);
         for (int s = 0; s < T; s++) {
             int2 nxt = act;
             io.next_action();
@@ -441,53 +482,54 @@ rollout_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
             const int a0 = act.x, a1 = act.y;
             act = nxt;
             RollOut o{0, 0, 0, 0u, 0u};
-            if (a.horizon > 0 && t >= a.horizon) {  // stepping a finished env: untouched + flagged (overcooked_env.py:255)
-                io.write(o, 1, true, mask_s);
-                continue;
-            }
-            // ---- resolve_interacts :1446-1577: player 0 then player 1 on the live record.  Two emissions of the body:
-            //      the first serves, per environment, the first interacting player (player 0 if it interacts, else
-            //      player 1), the second serves player 1 where BOTH interact (1 environment in 36 under a uniform
-            //      policy), so most warps skip it ----
-            const bool i0 = a0 == OVC_A_INTERACT, i1 = a1 == OVC_A_INTERACT;
-            bool pot_dirty = false;
-            if (i0 || i1) {
-                const bool second = !i0;  // the acting player is player 1
-                unsigned pa = second ? p1 : p0;
-                const unsigned pb = second ? p0 : p1;
-                int sh = 0;
-                const unsigned c = interact_v2(r, L, D, pa, (pb >> 10) & 7u, misc, ps, old_dyn, (unsigned)t + toff, o.sparse, sh, pot_dirty);
-                if (second) p1 = pa, o.sh1 = sh, o.c1 = c;
-                else p0 = pa, o.sh0 = sh, o.c0 = c;
-            }
-            if (i0 && i1) o.c1 = interact_v2(r, L, D, p1, (p0 >> 10) & 7u, misc, ps, old_dyn, (unsigned)t + toff, o.sparse, o.sh1, pot_dirty);
-            // ---- resolve_movement :1644-1727; a blocked or collided player still turns (quirk Q8) ----
-            {
-                const unsigned o0 = p0 & 0xFFu, o1 = p1 & 0xFFu;
-                unsigned n0 = lds_tbl8(D + OVC_DOFF(move) + ((((unsigned)a0 & 7u) << 8) | o0));
-                unsigned n1 = lds_tbl8(D + OVC_DOFF(move) + ((((unsigned)a1 & 7u) << 8) | o1));
-                const bool collide = n0 == n1 || (n0 == o1 && n1 == o0);  // :1673-1683
-                if (collide) n0 = o0, n1 = o1;
-                if ((unsigned)a0 < 4u) p0 = (p0 & ~0x3FFu) | ((unsigned)a0 << 8) | n0;
-                if ((unsigned)a1 < 4u) p1 = (p1 & ~0x3FFu) | ((unsigned)a1 << 8) | n1;
-            }
-            // ---- step_environment_effects :1691-1703: cooking soups carry their ready clock, nothing to advance.
-            //      Old dynamics: an idle soup with 3 ingredients starts by itself (:1696-1701), tick 0 -> 1 in this
-            //      transition, i.e. the same clock as a soup started by an interact of this transition ----
-            if (old_dyn) {
+            // stepping a finished env leaves it untouched and flags it (overcooked_env.py:255)
+            const bool stepped = a.horizon > 0 && t >= a.horizon;
+            int done = 1;
+            if (!stepped) {
+                // ---- resolve_interacts :1446-1577: player 0 then player 1 on the live record.  Two emissions of the body:
+                //      the first serves, per environment, the first interacting player (player 0 if it interacts, else
+                //      player 1), the second serves player 1 where BOTH interact (1 environment in 36 under a uniform
+                //      policy), so most warps skip it ----
+                const bool i0 = a0 == OVC_A_INTERACT, i1 = a1 == OVC_A_INTERACT;
+                bool pot_dirty = false;
+                if (i0 || i1) {
+                    const bool second = !i0;  // the acting player is player 1
+                    unsigned pa = second ? p1 : p0;
+                    const unsigned pb = second ? p0 : p1;
+                    int sh = 0;
+                    const unsigned c = interact_v2(r, L, D, pa, (pb >> 10) & 7u, misc, ps, old_dyn, (unsigned)t + toff, o.sparse, sh, pot_dirty);
+                    if (second) p1 = pa, o.sh1 = sh, o.c1 = c;
+                    else p0 = pa, o.sh0 = sh, o.c0 = c;
+                }
+                if (i0 && i1) o.c1 = interact_v2(r, L, D, p1, (p0 >> 10) & 7u, misc, ps, old_dyn, (unsigned)t + toff, o.sparse, o.sh1, pot_dirty);
+                // ---- resolve_movement :1644-1727; a blocked or collided player still turns (quirk Q8) ----
+                {
+                    const unsigned o0 = p0 & 0xFFu, o1 = p1 & 0xFFu;
+                    unsigned n0 = lds_tbl8(D + OVC_DOFF(move) + ((((unsigned)a0 & 7u) << 8) | o0));
+                    unsigned n1 = lds_tbl8(D + OVC_DOFF(move) + ((((unsigned)a1 & 7u) << 8) | o1));
+                    const bool collide = n0 == n1 || (n0 == o1 && n1 == o0);  // :1673-1683
+                    if (collide) n0 = o0, n1 = o1;
+                    if ((unsigned)a0 < 4u) p0 = (p0 & ~0x3FFu) | ((unsigned)a0 << 8) | n0;
+                    if ((unsigned)a1 < 4u) p1 = (p1 & ~0x3FFu) | ((unsigned)a1 << 8) | n1;
+                }
+                // ---- step_environment_effects :1691-1703: cooking soups carry their ready clock, nothing to advance.
+                //      Old dynamics: an idle soup with 3 ingredients starts by itself (:1696-1701), tick 0 -> 1 in this
+                //      transition, i.e. the same clock as a soup started by an interact of this transition ----
+                if (old_dyn) {
 #pragma unroll 1
-                for (int k = 0; k < n_pots; k++) {
-                    const unsigned w = r.ldw(4 + k);
-                    if ((w & ~0xE0u) == (OVC_O_SOUP | (3u << 3))) {
-                        r.stw(4 + k, w | (((unsigned)t + toff + lds_tbl32(D + OVC_DOFF(cook5) + 4u * ((w >> 3) & 31u)) + 1u) << 8));
-                        pot_dirty = true;
+                    for (int k = 0; k < n_pots; k++) {
+                        const unsigned w = r.ldw(4 + k);
+                        if ((w & ~0xE0u) == (OVC_O_SOUP | (3u << 3))) {
+                            r.stw(4 + k, w | (((unsigned)t + toff + lds_tbl32(D + OVC_DOFF(cook5) + 4u * ((w >> 3) & 31u)) + 1u) << 8));
+                            pot_dirty = true;
+                        }
                     }
                 }
+                if (pot_dirty) ps = pot_summary(r, n_pots);  // next transition's snapshot
+                done = a.horizon > 0 && t + 1 >= a.horizon;  // is_done overcooked_env.py:321-325
             }
-            if (pot_dirty) ps = pot_summary(r, n_pots);  // next transition's snapshot
-            const int tn = t + 1;
-            const int done = a.horizon > 0 && tn >= a.horizon;  // is_done overcooked_env.py:321-325
-            io.write(o, done, false, mask_s);
+            io.write(o, done, stepped, mask_s);
+            if (stepped) continue;
             if (done && (a.flags & OVC_F_AUTO_RESET)) {
                 const unsigned lid0 = misc & 0xFFu;
                 if (RS && a.has_rs) {
@@ -504,7 +546,7 @@ rollout_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
                 }
                 load_regs((unsigned)t + toff + 1u);
             } else {
-                t = tn;
+                t = t + 1;
             }
         }
         // ---- registers and pot clocks back into the tile in the external format ----

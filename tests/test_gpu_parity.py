@@ -455,6 +455,80 @@ def test_code_words_and_one_byte_actions_carry_the_whole_result():
     assert torch.equal(env_b.state, env_a.state)
 
 
+def test_sparse_event_stream_carries_the_whole_result():
+    """OVC_F_OUT_STREAM: one warp vote (lane mask) per 32 environments and transition + the compacted non-zero code
+    words.  Expanded on the host it must give back sparse / shaped / done / events of the int32 formats — through
+    rollout_stream() (partial last group, random-start auto-resets, mixed layouts, stepped-after-done words) and through
+    the host pipeline; a capacity that is too small is counted, and the dense backup recovers the pass."""
+    from overcooked_ai_b200 import wire
+
+    n, T = 6007, 96  # 6007 = 187 full groups + one of 23 environments
+    names = ["cramped_room", "counter_circuit", "asymmetric_advantages"]
+    rng = np.random.RandomState(4)
+    acts = _random_actions(rng, T, n, 0.45)
+    kw = dict(horizon=40, auto_reset=True, rnd_obj_prob_thresh=0.6, seed=9)
+    env_a, env_b = BatchedOvercookedEnv(names, n, **kw), BatchedOvercookedEnv(names, n, **kw)
+    want = [_np(x) for x in env_a.rollout(torch.from_numpy(acts).cuda())]
+    masks, values, dense_words = env_b.rollout_stream(torch.from_numpy(wire.pack_actions(acts)).cuda(), cap=T * 32, dense_backup=True)
+    assert torch.equal(env_b.state, env_a.state)
+    codes = env_a.alloc_rollout_out(T, codes=True)
+    env_a.reset(), env_b.reset()
+    env_a.rollout(torch.from_numpy(wire.pack_actions(acts)).cuda(), out=codes)
+    env_b.rollout(torch.from_numpy(acts).cuda())
+    assert torch.equal(dense_words, codes[3]), "the dense backup is the OVC_F_OUT_CODES word"
+    nz = _np(codes[3]) != 0
+    m = _np(masks).view(np.uint32)
+    bits = ((m[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(T, -1)[:, :n].astype(bool)
+    assert np.array_equal(bits, nz) and 0.02 < nz.mean() < 0.5, "lane masks = non-zero words"
+    got, over = env_b.expand_stream(masks.cpu(), values.cpu(), events=True)
+    assert over == 0
+    for k, w in zip(("sparse", "shaped", "done", "events"), want):
+        assert np.array_equal(got[k].numpy(), w), k
+    # too small a capacity: nothing is written out of bounds, the overflow is counted
+    per_group = bits.reshape(T, -1)[:, : (n // 32) * 32].reshape(T, n // 32, 32).sum((0, 2))
+    cap = int(per_group.max()) - 1
+    env_b.reset(), env_a.reset()
+    guard = torch.full((env_b.n_groups() * cap + 64,), 0x5A5A, dtype=torch.int16, device="cuda")
+    out = (torch.zeros((T, env_b.n_groups()), dtype=torch.int32, device="cuda"), guard[: env_b.n_groups() * cap].view(1, env_b.n_groups(), cap), None)
+    env_b.rollout_stream(torch.from_numpy(acts).cuda(), cap=cap, out=out)
+    assert (guard[env_b.n_groups() * cap:] == 0x5A5A).all()
+    _, over = env_b.expand_stream(out[0].cpu(), out[1].cpu().contiguous())
+    assert over == int((per_group > cap).sum()) >= 1
+    # ---- the host pipeline: chunks, two overlapping passes, and an overflow recovered from the device-side backup ----
+    env_a.reset(), env_b.reset()
+    want = [_np(x) for x in env_a.rollout(torch.from_numpy(acts).cuda())]
+    want2 = [_np(x) for x in env_a.rollout(torch.from_numpy(acts[::-1].copy()).cuda())]
+    pipe = HostRolloutPipeline(env_b, T, chunk=40, stream=True, stream_fill=0.5, host_buffers=2)
+    assert pipe.stream_cap == 640 and pipe.h2d_bytes_per_step == n
+    fwd, rev = torch.from_numpy(wire.pack_actions(acts)).pin_memory(), torch.from_numpy(wire.pack_actions(acts[::-1])).pin_memory()
+    (h1, e1), s1 = pipe.run(fwd, wait=False), pipe._last_set
+    (h2, e2), s2 = pipe.run(rev, wait=False), pipe._last_set
+    assert s1 != s2
+    for h, e, st, w in ((h1, e1, s1, want), (h2, e2, s2, want2)):
+        e.synchronize()
+        dense = pipe.expand(h, codes_set=st, events=True)
+        assert pipe.last_overflow == 0
+        for k, x in zip(("sparse", "shaped", "done", "events"), w):
+            assert np.array_equal(dense[k].numpy(), x), k
+    pipe.join()
+    torch.cuda.synchronize()
+    assert torch.equal(env_b.state, env_a.state)
+    pipe.close()
+    env_a.reset(), env_b.reset()
+    pipe = HostRolloutPipeline(env_b, T, chunk=40, stream=True, stream_fill=0.02, packed_actions=False)  # 26 slots per group and chunk
+    h = pipe.run(torch.from_numpy(acts.astype(np.uint8)).pin_memory())
+    torch.cuda.synchronize()
+    dense = pipe.expand(h, events=True)
+    assert pipe.last_overflow > 0, "the capacity was chosen to overflow"
+    for k, x in zip(("sparse", "shaped", "done", "events"), want):
+        assert np.array_equal(dense[k].numpy(), x), k
+    pipe.close()
+    # not available where the rollout kernel is not: the per-step record I/O experiments and > 8 layouts
+    env_c = BatchedOvercookedEnv("cramped_room", 64, io=_native.IO_DIRECT)
+    with pytest.raises(RuntimeError, match="OVC_F_OUT_STREAM"):
+        env_c.rollout_stream(torch.zeros((4, 64, 2), dtype=torch.int32, device="cuda"), cap=16)
+
+
 @pytest.mark.parametrize("random_pos,thresh", [(True, 0.0), (False, 0.7), (True, 0.5)])
 def test_random_start_states_vs_oracle_mirror(random_pos, thresh):
     """get_random_start_state_fn on the device (reset + auto-reset inside step / rollout): bit-exact against the
@@ -640,3 +714,22 @@ def test_packed_event_codes_cover_every_event_pattern():
     env.rollout(acts, out=out)
     ev, dn = wire.decode_event_codes(_np(out[3]))
     assert dn[2:].all() and not dn[:2].any() and (ev[3:] == L.EVF_STEPPED_DONE).all()
+
+
+def test_two_ranks_mixed_batch_on_gpus():
+    """SURVEY 8(e) on hardware: 2 NCCL ranks (one per GPU), a config-3-shaped mixed batch sharded with
+    dist.shard_segments, each rank's shard against the oracle, the reduced counters against the whole batch.  Needs two
+    visible GPUs (the 1-GPU lease skips it)."""
+    import os
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    port = 29600 + os.getpid() % 2000
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(root, "tests", "_dist_gpu_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, PYTHONPATH=root, OMP_NUM_THREADS="1"))
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert "DIST_GPU_OK" in out.stdout

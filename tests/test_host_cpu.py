@@ -26,7 +26,7 @@ def test_native_library_loads_and_exports_every_declared_symbol():
     lib = _native.lib()
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.ovc_abi_version() == _native.ABI_VERSION == 3
+    assert lib.ovc_abi_version() == _native.ABI_VERSION == 4
     assert lib.ovc_layout_table_size() == L.LAYOUT_DTYPE.itemsize == 1024
     assert lib.ovc_feat_lut_entry_size() == L.FEAT_LUT_DTYPE.itemsize == 12
 
@@ -253,6 +253,77 @@ def test_host_expander_of_code_words_matches_the_numpy_decoder():
     assert np.array_equal(wire.pack_actions(np.array([[5, 3], [0, 4]])), np.array([0x35, 0x40], np.uint8))
 
 
+def test_host_expander_of_the_sparse_event_stream():
+    """ovc_expand_stream_host (host code of the library, no GPU involved): lane masks + compacted non-zero words built
+    here with numpy from random code words, chunked as the pipeline chunks them; the expansion must equal the expansion
+    of the dense words, count overflowing (chunk, group) slices, and read dropped words as zero."""
+    from overcooked_ai_b200 import _native, wire
+
+    lib = _native.lib()
+    layouts = [L.compile_layout(n) for n in ("cramped_room", "counter_circuit")]
+    tbl = wire.code_reward_table(layouts)
+    rng = np.random.RandomState(3)
+    T, N, chunk = 23, 1000, 8  # N not a multiple of 32: the last group is partial
+    G, n_chunks = (N + 31) // 32, -(-T // chunk)
+    w = (rng.randint(0, 32, (T, N)) | (rng.randint(0, 32, (T, N)) << 5) | (rng.randint(0, 2, (T, N)) << 10)
+         | (rng.randint(0, 4, (T, N)) << 12)).astype(np.uint16)
+    w[rng.rand(T, N) < 0.85] = 0
+    lay = rng.randint(0, 2, N).astype(np.int32)
+
+    def build(cap):
+        masks, vals = np.zeros((T, G), np.uint32), np.zeros((n_chunks, G, cap), np.uint16)
+        over = 0
+        for c in range(n_chunks):
+            for g in range(G):
+                k = 0
+                for t in range(c * chunk, min(T, (c + 1) * chunk)):
+                    for l in range(32):
+                        e = g * 32 + l
+                        if e < N and w[t, e]:
+                            masks[t, g] |= np.uint32(1) << np.uint32(l)
+                            if k < cap:
+                                vals[c, g, k] = w[t, e]
+                            k += 1
+                over += k > cap
+        return masks, vals, over
+
+    def expand(words):
+        sp, sh = np.full((T, N), -1, np.int16), np.full((T, N, 2), -1, np.int8)
+        dn, ev = np.full((T, N), 7, np.uint8), np.full((T, N, 2), -1, np.int32)
+        assert lib.ovc_expand_codes_host(words.ctypes.data, T, N, lay.ctypes.data, tbl.ctypes.data, 2, sp.ctypes.data, sh.ctypes.data,
+                                         dn.ctypes.data, ev.ctypes.data, 1) == 0
+        return sp, sh, dn, ev
+
+    want = expand(w)
+    for cap, threads in ((chunk * 32, 1), (chunk * 32, 4), (40, 3)):
+        masks, vals, n_over = build(cap)
+        sp, sh = np.full((T, N), -1, np.int16), np.full((T, N, 2), -1, np.int8)
+        dn, ev = np.full((T, N), 7, np.uint8), np.full((T, N, 2), -1, np.int32)
+        over = ctypes.c_int64(-1)
+        rc = lib.ovc_expand_stream_host(masks.ctypes.data, vals.ctypes.data, T, chunk, cap, N, lay.ctypes.data, tbl.ctypes.data, 2,
+                                        sp.ctypes.data, sh.ctypes.data, dn.ctypes.data, ev.ctypes.data, threads, ctypes.byref(over))
+        assert rc == 0 and over.value == n_over
+        if n_over == 0:
+            for got, wnt in zip((sp, sh, dn, ev), want):
+                assert np.array_equal(got, wnt)
+        else:  # dropped words read as zero: rebuild the dense words the stream still holds and compare with their expansion
+            assert n_over > 0
+            kept = w.copy()
+            for c in range(n_chunks):
+                for g in range(G):
+                    k = 0
+                    for t in range(c * chunk, min(T, (c + 1) * chunk)):
+                        for l in range(32):
+                            e = g * 32 + l
+                            if e < N and w[t, e]:
+                                if k >= cap:
+                                    kept[t, e] = 0
+                                k += 1
+            for got, wnt in zip((sp, sh, dn, ev), expand(kept)):
+                assert np.array_equal(got, wnt)
+    assert lib.ovc_expand_stream_host(None, None, T, chunk, 8, N, 0, tbl.ctypes.data, 1, 0, 0, 0, 0, 1, None) != 0
+
+
 def test_host_expander_pool_survives_concurrent_and_repeated_regions():
     """The persistent worker pool behind ovc_expand_codes_host: many regions with changing thread counts, issued
     from two host threads at once, all produce the right arrays and none hangs."""
@@ -297,7 +368,8 @@ def test_pipeline_descriptor_layout_matches_the_c_struct():
     from overcooked_ai_b200 import _native
 
     lib = _native.lib()
-    assert ctypes.sizeof(_native.PipelineDesc) == 160 and _native.PipelineDesc.random_start.offset == 56
+    assert ctypes.sizeof(_native.PipelineDesc) == 184 and _native.PipelineDesc.random_start.offset == 56
+    assert _native.PipelineDesc.stream_cap.offset == 160 and _native.PipelineDesc.d_codes_full.offset == 168
     buf = (ctypes.c_char * 4096)()
     base = ctypes.addressof(buf) & ~15 | 16  # any non-null, 16-byte aligned address: nothing is dereferenced
 
@@ -319,9 +391,21 @@ def test_pipeline_descriptor_layout_matches_the_c_struct():
     for kw, msg in (({"chunk": 0}, "chunk must be >= 1"), ({"state_words": 24}, "state_words"), ({"n_layouts": 0}, "n_layouts"),
                     ({"n_envs": -1}, "negative n_envs"), ({"state": base + 4}, "16-byte aligned"),
                     ({"d_events": (1, None)}, "missing device staging buffer"), ({"d_actions": (0, None)}, "missing device staging buffer"),
-                    ({"flags": _native.F_OUT_PACKED}, "missing device staging buffer")):  # packed also needs sparse / shaped
+                    ({"flags": _native.F_OUT_PACKED}, "missing device staging buffer"),  # packed also needs sparse / shaped
+                    ({"flags": _native.F_OUT_STREAM | _native.F_ACT_PACKED}, "missing device staging buffer"),  # stream needs the value slots
+                    ({"flags": _native.F_OUT_STREAM | _native.F_ACT_PACKED, "d_sparse": (0, base)}, "missing device staging buffer"),
+                    ):
         rc, err, h = create(**kw)
         assert rc != 0 and msg in err and not h.value, (kw, rc, err)
+    d = _native.PipelineDesc()  # stream format: the capacity field is read where the C struct has it
+    d.layouts, d.n_layouts, d.state_words, d.start_records, d.state = base, 1, 16, base, base
+    d.n_envs, d.horizon, d.flags, d.chunk = 128, 400, _native.F_OUT_STREAM | _native.F_ACT_PACKED, 8
+    for b in range(2):
+        d.d_actions[b], d.d_events[b], d.d_sparse[b] = base, base, base
+    for cap in (0, 70000):
+        d.stream_cap = cap
+        h = ctypes.c_void_p()
+        assert lib.ovc_pipeline_create(ctypes.byref(d), ctypes.byref(h)) != 0 and "stream_cap" in lib.ovc_last_error().decode()
     assert lib.ovc_pipeline_run(None, base, None, None, None, base, 1, None, 1, None) != 0
     assert lib.ovc_pipeline_wait(None, 0) != 0 and lib.ovc_pipeline_join(None, None) != 0
     lib.ovc_pipeline_destroy(None)
