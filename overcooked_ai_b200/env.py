@@ -48,17 +48,23 @@ class OvercookedEnv(object):
                 "info_level": self.info_level, "num_mdp": self.num_mdp}
 
     def step(self, joint_action, joint_agent_action_info=None, display_phi=False):
+        """(next_state, summed sparse reward, done, env_info) — overcooked_env.py:244-274."""
         assert not self.is_done()
-        if joint_agent_action_info is None:
-            joint_agent_action_info = [{}, {}]
-        next_state, mdp_infos = self.mdp.get_state_transition(self.state, joint_action, display_phi)
-        self._update_game_stats(mdp_infos)
-        self.state = next_state
+        agent_infos = [{}, {}] if joint_agent_action_info is None else joint_agent_action_info
+        t = self.state.timestep  # events are logged with the pre-transition timestep: 0 .. horizon - 1
+        self.state, infos = self.mdp.get_state_transition(self.state, joint_action, display_phi)
+        sparse, shaped = infos["sparse_reward_by_agent"], infos["shaped_reward_by_agent"]
+        self._returns += np.array([sparse, shaped])
+        self._event_log.extend((t, agent, name) for name, flags in infos["event_infos"].items() for agent, hit in enumerate(flags) if hit)
         done = self.is_done()
-        env_info = self._prepare_info_dict(joint_agent_action_info, mdp_infos)
+        env_info = {
+            "agent_infos": [agent_infos[i] for i in range(self.mdp.num_players)],
+            "sparse_r_by_agent": sparse, "shaped_r_by_agent": shaped,
+            "phi_s": infos.get("phi_s"), "phi_s_prime": infos.get("phi_s_prime"),
+        }
         if done:
-            self._add_episode_info(env_info)
-        return (next_state, sum(mdp_infos["sparse_reward_by_agent"]), done, env_info)
+            env_info["episode"] = self._episode_summary()
+        return (self.state, sum(sparse), done, env_info)
 
     def lossless_state_encoding_mdp(self, state):
         return self.mdp.lossless_state_encoding(state, self.horizon)
@@ -75,61 +81,46 @@ class OvercookedEnv(object):
         return self.mdp.potential_function(state if state else self.state, gamma=gamma)
 
     def reset(self, regen_mdp=True, outside_info={}):
+        """overcooked_env.py:288-319: new MDP (unless told not to), start state, empty episode statistics."""
         if regen_mdp:
             self.mdp = self.mdp_generator_fn(outside_info)
-        if self.start_state_fn is None:
-            self.state = self.mdp.get_standard_start_state()
-        else:
-            self.state = self.start_state_fn()
-        events_dict = {k: [[] for _ in range(self.mdp.num_players)] for k in EVENT_TYPES}
-        rewards_dict = {
-            "cumulative_sparse_rewards_by_agent": np.array([0] * self.mdp.num_players),
-            "cumulative_shaped_rewards_by_agent": np.array([0] * self.mdp.num_players),
-        }
-        self.game_stats = {**events_dict, **rewards_dict}
+        self.state = self.mdp.get_standard_start_state() if self.start_state_fn is None else self.start_state_fn()
+        # episode statistics live in the engine's terms — a log of (timestep, agent, event) and a [sparse|shaped, agent]
+        # return array; `game_stats` renders them in the reference's shape on demand
+        self._event_log = []
+        self._returns = np.zeros((2, self.mdp.num_players), dtype=np.int64)
+
+    @property
+    def game_stats(self):
+        """The reference's dict (:308-319, 382-401): per event name a list per agent of the timesteps it fired at, plus
+        the two cumulative reward arrays."""
+        stats = {name: [[] for _ in range(self.mdp.num_players)] for name in EVENT_TYPES}
+        for t, agent, name in self._event_log:
+            stats[name][agent].append(t)
+        stats["cumulative_sparse_rewards_by_agent"] = self._returns[0].copy()
+        stats["cumulative_shaped_rewards_by_agent"] = self._returns[1].copy()
+        return stats
 
     def is_done(self):
         return self.state.timestep >= self.horizon or self.mdp.is_terminal(self.state)
 
-    def _prepare_info_dict(self, joint_agent_action_info, mdp_infos):
-        env_info = {"agent_infos": [joint_agent_action_info[i] for i in range(self.mdp.num_players)]}
-        env_info["sparse_r_by_agent"] = mdp_infos["sparse_reward_by_agent"]
-        env_info["shaped_r_by_agent"] = mdp_infos["shaped_reward_by_agent"]
-        env_info["phi_s"] = mdp_infos.get("phi_s", None)
-        env_info["phi_s_prime"] = mdp_infos.get("phi_s_prime", None)
-        return env_info
-
-    def _add_episode_info(self, env_info):
+    def _episode_summary(self):
+        """The ``episode`` entry of the last transition's info dict (:363-380)."""
         gs = self.game_stats
-        env_info["episode"] = {
-            "ep_game_stats": gs,
-            "ep_sparse_r": sum(gs["cumulative_sparse_rewards_by_agent"]),
-            "ep_shaped_r": sum(gs["cumulative_shaped_rewards_by_agent"]),
-            "ep_sparse_r_by_agent": gs["cumulative_sparse_rewards_by_agent"],
-            "ep_shaped_r_by_agent": gs["cumulative_shaped_rewards_by_agent"],
-            "ep_length": self.state.timestep,
-        }
-        return env_info
-
-    def _update_game_stats(self, infos):
-        self.game_stats["cumulative_sparse_rewards_by_agent"] += np.array(infos["sparse_reward_by_agent"])
-        self.game_stats["cumulative_shaped_rewards_by_agent"] += np.array(infos["shaped_reward_by_agent"])
-        for event_type, by_agent in infos["event_infos"].items():
-            for idx, happened in enumerate(by_agent):
-                if happened:  # timestep is logged before the tick, so events carry 0..horizon-1
-                    self.game_stats[event_type][idx].append(self.state.timestep)
+        sparse, shaped = gs["cumulative_sparse_rewards_by_agent"], gs["cumulative_shaped_rewards_by_agent"]
+        return {"ep_game_stats": gs, "ep_sparse_r": sum(sparse), "ep_shaped_r": sum(shaped),
+                "ep_sparse_r_by_agent": sparse, "ep_shaped_r_by_agent": shaped, "ep_length": self.state.timestep}
 
     def execute_plan(self, start_state, joint_action_plan, display=False):
+        """Runs the plan from ``start_state`` until it ends or the episode does; returns (state reached, done) and
+        leaves the env reset on the same MDP (:407-423)."""
         self.state = start_state
-        done = False
         for joint_action in joint_action_plan:
-            self.step(joint_action)
-            done = self.is_done()
-            if done:
+            if self.step(joint_action)[2]:
                 break
-        successor_state = self.state
+        reached, done = self.state, self.is_done() if len(joint_action_plan) else False
         self.reset(False)
-        return successor_state, done
+        return reached, done
 
 
 class Overcooked(object):

@@ -536,25 +536,14 @@ def compile_layout(layout_name, **params_to_overwrite):
 
 # ---- packed record <-> OvercookedState -----------------------------------------------------------
 def pack_object(obj):
-    """ObjectState / SoupState -> 22-bit object code (include/ovc_b200.h)."""
+    """ObjectState / SoupState -> 22-bit object code (include/ovc_b200.h): the value types already ARE their codes."""
     if obj is None:
         return 0
-    code = OBJ_CODE[obj.name]
-    if code != O_SOUP:
-        return code
-    ings = obj.ingredients
-    if len(ings) > MAX_NUM_INGREDIENTS:
-        raise ValueError("soup with %d ingredients" % len(ings))
-    kinds = 0
-    for i, name in enumerate(ings):
-        if name == TOMATO:
-            kinds |= 1 << i
-        elif name != ONION:
-            raise ValueError("invalid ingredient %r" % name)
-    tick = obj._cooking_tick
-    if not -1 <= tick <= MAX_TICK:
-        raise ValueError("cooking tick %d outside -1..%d" % (tick, MAX_TICK))
-    return O_SOUP | (len(ings) << 3) | (kinds << 5) | ((tick + 1) << 8)
+    if not obj.code:
+        raise KeyError(obj.name)
+    if obj.code & 7 == O_SOUP and not obj.is_valid():
+        raise ValueError("soup with %d ingredients" % len(obj.ingredients))
+    return obj.code & OBJ_MASK
 
 
 def unpack_object(code, position, layout=None):
@@ -563,12 +552,9 @@ def unpack_object(code, position, layout=None):
         return None
     if t != O_SOUP:
         return ObjectState(OBJ_NAME[t], position)
-    n = (code >> 3) & 3
-    kinds = (code >> 5) & 7
-    tick = ((code >> 8) & 0x3FFF) - 1
-    ings = [ObjectState(TOMATO if (kinds >> i) & 1 else ONION, position) for i in range(n)]
-    soup = SoupState(position, ings, tick)
-    if layout is not None and n > 0:
+    soup = SoupState(position)
+    soup.code = code & OBJ_MASK
+    if layout is not None and (code >> 3) & 3:
         soup._cook_time = layout.soup_cook_time(soup)
     return soup
 

@@ -1,65 +1,74 @@
-"""Host-side value types of one Overcooked environment.
+"""Host-side value types of one Overcooked environment, as VIEWS of the engine's packed fields.
 
-These mirror the reference's ``Recipe`` / ``ObjectState`` / ``SoupState`` / ``PlayerState`` /
-``OvercookedState`` (src/overcooked_ai_py/mdp/overcooked_mdp.py:18-1015) closely enough that the
-drop-in adapters can hand callers objects with the same attributes, equality rules and
-``to_dict`` / ``from_dict`` wire format.  They carry no game logic: transitions happen on the
-GPU on the packed int32 record (see include/ovc_b200.h and layout.pack_state / unpack_state).
+The reference's ``Recipe`` / ``ObjectState`` / ``SoupState`` / ``PlayerState`` / ``OvercookedState``
+(src/overcooked_ai_py/mdp/overcooked_mdp.py:18-1015) are what callers of the drop-in surface hold, so the names,
+attributes, equality rules, error types and the ``to_dict`` / ``from_dict`` wire keys below are the reference's.
+The representation is the engine's: an object IS its 22-bit object code of include/ovc_b200.h (type, ingredient count,
+ordered kinds, tick + 1), a recipe IS its row of the per-layout recipe tables, and every property decodes those bit
+fields; ``layout.pack_state`` / ``unpack_state`` move the codes in and out of the int32 record without translating
+them.  No game logic lives here: transitions happen on the GPU.
 
-Deliberate difference: there is no global ``Recipe.configure`` class state (reference quirk Q1,
-overcooked_mdp.py:220-336).  Recipe value / cook time live in the per-layout constant table, so
-several layouts can be alive in one process without changing each other's rewards.
+Deliberate difference: there is no global ``Recipe.configure`` class state (reference quirk Q1, :220-336).  Recipe
+values and cook times are per-layout constants (``layout.CompiledLayout``); a soup that was built without a cook time
+(legacy dicts, ``get_soup``) reports ``DEFAULT_COOK_TIME``, the reference's unconfigured ``Recipe.time`` (:163-188),
+until ``unpack_state`` / ``OvercookedGridworld.soup_cook_time`` gives it its layout's.
 """
-import copy
-
 from overcooked_ai_b200.actions import Direction
 
 ONION = "onion"
 TOMATO = "tomato"
 ALL_INGREDIENTS = [ONION, TOMATO]
 MAX_NUM_INGREDIENTS = 3  # "num_items_for_soup" never reaches Recipe.configure (quirk Q2)
+DEFAULT_COOK_TIME = 20   # Recipe.time with nothing configured (:188)
+
+# object code fields (include/ovc_b200.h)
+_TYPE = {ONION: 1, TOMATO: 2, "dish": 3, "soup": 4}
+_NAME = {v: k for k, v in _TYPE.items()}
+_T_SOUP = 4
+_MAX_TICK = 16382
 
 
 class Recipe(object):
-    """An unordered multiset of 1..3 ingredients (reference :18-116)."""
+    """An unordered multiset of 1..3 ingredients (reference :18-116), held as (n_onion, n_tomato)."""
 
-    __slots__ = ("_ingredients",)
+    __slots__ = ("_o", "_t")
 
     def __init__(self, ingredients):
-        ingredients = tuple(ingredients)
-        if not 0 < len(ingredients) <= MAX_NUM_INGREDIENTS:
+        names = tuple(ingredients)
+        if not 0 < len(names) <= MAX_NUM_INGREDIENTS:
             raise ValueError("Recipe must have 1..%d ingredients" % MAX_NUM_INGREDIENTS)
-        for i in ingredients:
-            if i not in ALL_INGREDIENTS:
-                raise ValueError("Invalid ingredient: %r" % (i,))
-        self._ingredients = tuple(sorted(ingredients))
-
-    @property
-    def ingredients(self):
-        return self._ingredients
+        bad = [i for i in names if i not in _TYPE or _TYPE[i] > 2]
+        if bad:
+            raise ValueError("Invalid ingredient: %r" % (bad[0],))
+        self._o, self._t = names.count(ONION), names.count(TOMATO)
 
     @property
     def counts(self):
         """(n_onion, n_tomato)"""
-        return (self._ingredients.count(ONION), self._ingredients.count(TOMATO))
+        return (self._o, self._t)
 
     @property
     def index(self):
-        """Row of the per-layout recipe tables: n_onion * 4 + n_tomato."""
-        o, t = self.counts
-        return o * 4 + t
+        """Row of the per-layout recipe tables (cook_time / deliver_value / best_value): n_onion * 4 + n_tomato."""
+        return self._o * 4 + self._t
+
+    @property
+    def ingredients(self):
+        return (ONION,) * self._o + (TOMATO,) * self._t  # sorted: "onion" < "tomato"
+
+    _ingredients = ingredients
 
     def __int__(self):
-        # same ordering key as the reference (:71-81), used by sorted(all_orders)
-        o, t = self.counts
-        enc = o + (MAX_NUM_INGREDIENTS + 1) * t
-        return int(bool(o * t)) * enc * (MAX_NUM_INGREDIENTS + 1) ** len(ALL_INGREDIENTS) + enc
+        # the reference's ordering key (:71-81); sorted(all_orders) depends on it
+        base = MAX_NUM_INGREDIENTS + 1
+        enc = self._o + base * self._t
+        return (enc * base ** len(ALL_INGREDIENTS) if self._o and self._t else 0) + enc
 
     def __hash__(self):
-        return hash(self._ingredients)
+        return hash(self.ingredients)
 
     def __eq__(self, other):
-        return isinstance(other, Recipe) and self._ingredients == other._ingredients
+        return isinstance(other, Recipe) and self.counts == other.counts
 
     def __ne__(self, other):
         return not self == other
@@ -68,13 +77,13 @@ class Recipe(object):
         return int(self) < int(other)
 
     def __repr__(self):
-        return repr(self._ingredients)
+        return repr(self.ingredients)
 
     def __iter__(self):
-        return iter(self._ingredients)
+        return iter(self.ingredients)
 
     def to_dict(self):
-        return {"ingredients": self._ingredients}
+        return {"ingredients": self.ingredients}
 
     @classmethod
     def from_dict(cls, d):
@@ -82,19 +91,20 @@ class Recipe(object):
 
     @staticmethod
     def all_recipes():
-        out = []
-        for n in range(1, MAX_NUM_INGREDIENTS + 1):
-            for t in range(0, n + 1):
-                out.append(Recipe([ONION] * (n - t) + [TOMATO] * t))
-        return out
+        return [Recipe([ONION] * (n - t) + [TOMATO] * t) for n in range(1, MAX_NUM_INGREDIENTS + 1) for t in range(n + 1)]
 
 
 class ObjectState(object):
-    """A loose or held onion / tomato / dish (reference :384-430)."""
+    """A loose or held onion / tomato / dish (reference :384-430): ``code`` is its object code (1, 2, 3)."""
 
     def __init__(self, name, position, **kwargs):
-        self.name = name
+        self.code = _TYPE.get(name, 0)
+        self._other_name = None if self.code else name  # not an engine object: kept so that is_valid() can say so
         self._position = tuple(position)
+
+    @property
+    def name(self):
+        return _NAME.get(self.code & 7, self._other_name)
 
     @property
     def position(self):
@@ -105,26 +115,22 @@ class ObjectState(object):
         self._position = tuple(new_pos)
 
     def is_valid(self):
-        return self.name in ("onion", "tomato", "dish")
+        return 1 <= self.code <= 3
 
     def deepcopy(self):
-        return ObjectState(self.name, self.position)
+        return ObjectState(self.name, self._position)
 
     def __eq__(self, other):
-        return (
-            isinstance(other, ObjectState)
-            and self.name == other.name
-            and self.position == other.position
-        )
+        return isinstance(other, ObjectState) and (self.name, self._position) == (other.name, other._position)
 
     def __hash__(self):
-        return hash((self.name, self.position))
+        return hash((self.name, self._position))
 
     def __repr__(self):
-        return "{}@{}".format(self.name, self.position)
+        return "{}@{}".format(self.name, self._position)
 
     def to_dict(self):
-        return {"name": self.name, "position": self.position}
+        return {"name": self.name, "position": self._position}
 
     @classmethod
     def from_dict(cls, obj_dict):
@@ -132,78 +138,70 @@ class ObjectState(object):
 
 
 class SoupState(ObjectState):
-    """A soup: ordered ingredient list + cooking tick (reference :433-693).
-
-    ``cook_time`` is a per-layout constant in this engine; ``unpack_state`` fills it in from the
-    layout's recipe table, ``from_dict`` takes it from the dict like the reference does.
-    """
+    """A soup (reference :433-693): ``code`` carries the ingredient count (bits 3-4), the ORDERED kinds (bit 5 + i set =
+    slot i is a tomato; ``__eq__`` is order sensitive, quirk Q6) and ``_cooking_tick + 1`` (bits 8-21)."""
 
     def __init__(self, position, ingredients=None, cooking_tick=-1, cook_time=None, **kwargs):
-        super(SoupState, self).__init__("soup", position)
-        self._ingredients = list(ingredients) if ingredients is not None else []
+        self._position = tuple(position)
+        self._other_name = None
+        items = list(ingredients) if ingredients is not None else []
+        self._overfull = items[MAX_NUM_INGREDIENTS:]  # cannot be encoded; kept only so is_valid() / len() tell the truth
+        kinds = 0
+        for i, ing in enumerate(items[:MAX_NUM_INGREDIENTS]):
+            if ing.name == TOMATO:
+                kinds |= 1 << i
+            elif ing.name != ONION:
+                raise ValueError("invalid ingredient %r" % (ing.name,))
+        self._stray = any(tuple(ing.position) != self._position for ing in items)  # is_valid (:553-560) looks at this
+        self.code = _T_SOUP | (min(len(items), MAX_NUM_INGREDIENTS) << 3) | (kinds << 5)
         self._cooking_tick = cooking_tick
         self._cook_time = cook_time
 
-    # -- equality exactly as the reference defines it (:458-477): zip truncates (quirk Q6)
-    def __eq__(self, other):
-        return (
-            isinstance(other, SoupState)
-            and self.name == other.name
-            and self.position == other.position
-            and self._cooking_tick == other._cooking_tick
-            and all(a == b for a, b in zip(self._ingredients, other._ingredients))
-        )
+    # ---- bit fields ----
+    @property
+    def _cooking_tick(self):
+        return ((self.code >> 8) & 0x3FFF) - 1
 
-    def __hash__(self):
-        return hash(
-            (
-                ObjectState.__hash__(self),
-                self._cooking_tick,
-                hash(tuple(hash(i) for i in self._ingredients)),
-            )
-        )
+    @_cooking_tick.setter
+    def _cooking_tick(self, tick):
+        if not -1 <= tick <= _MAX_TICK:
+            raise ValueError("cooking tick %d outside -1..%d" % (tick, _MAX_TICK))
+        self.code = (self.code & 0xFF) | ((int(tick) + 1) << 8)
 
-    def __repr__(self):
-        return "{}\nIngredients:\t{}\nCooking Tick:\t{}".format(
-            ObjectState.__repr__(self), self._ingredients, self._cooking_tick
-        )
+    @property
+    def _n(self):
+        return (self.code >> 3) & 3
+
+    @property
+    def ingredients(self):
+        kinds = self.code >> 5
+        return [TOMATO if (kinds >> i) & 1 else ONION for i in range(self._n)] + [i.name for i in self._overfull]
+
+    @property
+    def _ingredients(self):
+        return [ObjectState(name, self._position) for name in self.ingredients]
 
     @property
     def position(self):
         return self._position
 
     @position.setter
-    def position(self, new_pos):
+    def position(self, new_pos):  # the ingredients travel with the soup (:484-488): they are derived from it here
         self._position = tuple(new_pos)
-        for ing in self._ingredients:
-            ing.position = new_pos
+        self._stray = False
 
+    # ---- the reference's predicates ----
     @property
-    def ingredients(self):
-        return [i.name for i in self._ingredients]
-
-    @property
-    def recipe(self):
-        if self.is_idle:
-            raise ValueError("Recipe is not determined until soup begins cooking")
-        return Recipe(self.ingredients)
+    def is_idle(self):
+        return (self.code >> 8) & 0x3FFF == 0
 
     @property
     def cook_time(self):
-        if self._cook_time is None:
-            raise ValueError(
-                "cook_time of this soup is unknown: it is a per-layout constant, "
-                "use OvercookedGridworld.soup_cook_time(soup)"
-            )
-        return self._cook_time
-
-    @property
-    def is_idle(self):
-        return self._cooking_tick < 0
+        return DEFAULT_COOK_TIME if self._cook_time is None else self._cook_time
 
     @property
     def is_ready(self):
-        return (not self.is_idle) and self._cooking_tick >= self.cook_time
+        return not self.is_idle and self._cooking_tick >= self.cook_time
 
     @property
     def is_cooking(self):
@@ -215,71 +213,73 @@ class SoupState(ObjectState):
 
     @property
     def is_full(self):
-        return not self.is_idle or len(self._ingredients) == MAX_NUM_INGREDIENTS
+        return not self.is_idle or len(self.ingredients) == MAX_NUM_INGREDIENTS
+
+    @property
+    def recipe(self):
+        if self.is_idle:
+            raise ValueError("Recipe is not determined until soup begins cooking")
+        return Recipe(self.ingredients)
 
     def is_valid(self):
-        if not all(i.position == self.position for i in self._ingredients):
-            return False
-        return len(self._ingredients) <= MAX_NUM_INGREDIENTS
+        return not self._stray and not self._overfull
 
     def deepcopy(self):
-        return SoupState(
-            self.position,
-            [i.deepcopy() for i in self._ingredients],
-            self._cooking_tick,
-            self._cook_time,
-        )
+        twin = SoupState(self._position, None, -1, self._cook_time)
+        twin.code, twin._overfull, twin._stray = self.code, list(self._overfull), self._stray
+        return twin
 
+    # equality exactly as the reference defines it (:458-477): zip() truncates to the shorter ingredient list
+    def __eq__(self, other):
+        if not isinstance(other, SoupState) or self._position != other._position or self._cooking_tick != other._cooking_tick:
+            return False
+        return all(a == b for a, b in zip(self.ingredients, other.ingredients))
+
+    def __hash__(self):
+        return hash((self._position, self._cooking_tick, tuple(self.ingredients)))
+
+    def __repr__(self):
+        return "{}\nIngredients:\t{}\nCooking Tick:\t{}".format(ObjectState.__repr__(self), self._ingredients, self._cooking_tick)
+
+    # ---- wire format (:615-663) ----
     def to_dict(self):
-        d = ObjectState.to_dict(self)
-        d["_ingredients"] = [i.to_dict() for i in self._ingredients]
-        d["cooking_tick"] = self._cooking_tick
-        d["is_cooking"] = self.is_cooking
-        d["is_ready"] = self.is_ready
-        d["is_idle"] = self.is_idle
-        d["cook_time"] = -1 if self.is_idle else self.cook_time
-        d["_cooking_tick"] = self._cooking_tick  # kept for overcooked-demo, as in the reference
-        return d
+        idle = self.is_idle
+        return {
+            "name": "soup", "position": self._position,
+            "_ingredients": [{"name": n, "position": self._position} for n in self.ingredients],
+            "cooking_tick": self._cooking_tick, "is_cooking": self.is_cooking, "is_ready": self.is_ready, "is_idle": idle,
+            "cook_time": -1 if idle else self.cook_time,
+            "_cooking_tick": self._cooking_tick,  # kept for overcooked-demo, as in the reference
+        }
 
     @classmethod
     def from_dict(cls, obj_dict):
-        obj_dict = copy.deepcopy(obj_dict)
         if obj_dict["name"] != "soup":
             return ObjectState.from_dict(obj_dict)
-        if "state" in obj_dict:
-            # legacy (2019) soup representation, reference :638-656
-            ingredient, num, time = obj_dict["state"]
-            tick = -1 if time == 0 else time
-            n_t = num if ingredient == TOMATO else 0
-            n_o = 0 if ingredient == TOMATO else num
-            return SoupState.get_soup(
-                obj_dict["position"], n_o, n_t, cooking_tick=tick, finished=time >= 20
-            )
-        ings = [ObjectState.from_dict(i) for i in obj_dict["_ingredients"]]
+        if "state" in obj_dict:  # the 2019 format (:638-656): (ingredient, how many, time cooked); 20 = done
+            kind, num, time = obj_dict["state"]
+            # like the reference, the tomato branch leaves get_soup's default of ONE onion in place
+            which = {"num_tomatoes": num} if kind == TOMATO else {"num_onions": num}
+            return cls.get_soup(obj_dict["position"], cooking_tick=time or -1, finished=time >= 20, **which)
         tick = obj_dict.get("cooking_tick", obj_dict.get("_cooking_tick", -1))
         cook_time = obj_dict.get("cook_time", None)
-        if cook_time is not None and cook_time < 0:
-            cook_time = None
-        return cls(obj_dict["position"], ings, tick, cook_time)
+        return cls(obj_dict["position"], [ObjectState.from_dict(i) for i in obj_dict["_ingredients"]], tick,
+                   cook_time if cook_time is not None and cook_time >= 0 else None)
 
     @classmethod
-    def get_soup(
-        cls, position, num_onions=1, num_tomatoes=0, cooking_tick=-1, finished=False,
-        cook_time=None, **kwargs
-    ):
+    def get_soup(cls, position, num_onions=1, num_tomatoes=0, cooking_tick=-1, finished=False, cook_time=None, **kwargs):
+        total = num_onions + num_tomatoes
         if num_onions < 0 or num_tomatoes < 0:
             raise ValueError("Number of active ingredients must be positive")
-        if num_onions + num_tomatoes > MAX_NUM_INGREDIENTS:
+        if total > MAX_NUM_INGREDIENTS:
             raise ValueError("Too many ingredients specified for this soup")
-        if cooking_tick >= 0 and num_onions + num_tomatoes == 0:
+        if cooking_tick >= 0 and total == 0:
             raise ValueError("_cooking_tick must be -1 for empty soup")
-        if finished and num_onions + num_tomatoes == 0:
+        if finished and total == 0:
             raise ValueError("Empty soup cannot be finished")
-        ings = [ObjectState(ONION, position) for _ in range(num_onions)]
-        ings += [ObjectState(TOMATO, position) for _ in range(num_tomatoes)]
-        soup = cls(position, ings, cooking_tick, cook_time)
-        if finished:
-            # auto_finish (:565-569): tick := cook_time; needs the layout's cook time
+        soup = cls(position, [ObjectState(ONION, position)] * num_onions + [ObjectState(TOMATO, position)] * num_tomatoes,
+                   cooking_tick, cook_time)
+        if finished:  # auto_finish (:565-569): the tick jumps to the cook time
             soup._cooking_tick = soup.cook_time
         return soup
 
@@ -288,13 +288,9 @@ class PlayerState(object):
     """Position, facing direction and held object of one chef (reference :696-781)."""
 
     def __init__(self, position, orientation, held_object=None):
-        self.position = tuple(position)
-        self.orientation = tuple(orientation)
-        self.held_object = held_object
+        self.position, self.orientation, self.held_object = tuple(position), tuple(orientation), held_object
         assert self.orientation in Direction.ALL_DIRECTIONS
-        if self.held_object is not None:
-            assert isinstance(self.held_object, ObjectState)
-            assert self.held_object.position == self.position
+        assert held_object is None or (isinstance(held_object, ObjectState) and held_object.position == self.position)
 
     @property
     def pos_and_or(self):
@@ -304,65 +300,55 @@ class PlayerState(object):
         return self.held_object is not None
 
     def get_object(self):
-        assert self.has_object()
+        assert self.held_object is not None
         return self.held_object
 
     def set_object(self, obj):
-        assert not self.has_object()
+        assert self.held_object is None
         obj.position = self.position
         self.held_object = obj
 
     def remove_object(self):
-        assert self.has_object()
+        assert self.held_object is not None
         obj, self.held_object = self.held_object, None
         return obj
 
     def deepcopy(self):
-        held = None if self.held_object is None else self.held_object.deepcopy()
-        return PlayerState(self.position, self.orientation, held)
+        return PlayerState(self.position, self.orientation, self.held_object and self.held_object.deepcopy())
+
+    def _key(self):
+        return (self.position, self.orientation, self.held_object)
 
     def __eq__(self, other):
-        return (
-            isinstance(other, PlayerState)
-            and self.position == other.position
-            and self.orientation == other.orientation
-            and self.held_object == other.held_object
-        )
+        return isinstance(other, PlayerState) and self._key() == other._key()
 
     def __hash__(self):
-        return hash((self.position, self.orientation, self.held_object))
+        return hash(self._key())
 
     def __repr__(self):
-        return "{} facing {} holding {}".format(
-            self.position, self.orientation, str(self.held_object)
-        )
+        return "{} facing {} holding {}".format(self.position, self.orientation, str(self.held_object))
 
     def to_dict(self):
-        return {
-            "position": self.position,
-            "orientation": self.orientation,
-            "held_object": None if self.held_object is None else self.held_object.to_dict(),
-        }
+        return {"position": self.position, "orientation": self.orientation,
+                "held_object": self.held_object.to_dict() if self.held_object is not None else None}
 
     @staticmethod
     def from_dict(player_dict):
-        held = player_dict.get("held_object", None)
-        if held is not None:
-            held = SoupState.from_dict(held)
-        return PlayerState(player_dict["position"], player_dict["orientation"], held)
+        held = player_dict.get("held_object")
+        return PlayerState(player_dict["position"], player_dict["orientation"], SoupState.from_dict(held) if held is not None else None)
+
+
+def _as_recipes(orders):
+    return [o if isinstance(o, Recipe) else Recipe.from_dict(o) for o in orders]
 
 
 class OvercookedState(object):
     """Players + loose objects + order lists + timestep (reference :784-1015)."""
 
     def __init__(self, players, objects, bonus_orders=[], all_orders=[], timestep=0, **kwargs):
-        for pos, obj in objects.items():
-            assert obj.position == pos
-        self.players = tuple(players)
-        self.objects = objects
-        self._bonus_orders = [o if isinstance(o, Recipe) else Recipe.from_dict(o) for o in bonus_orders]
-        self._all_orders = [o if isinstance(o, Recipe) else Recipe.from_dict(o) for o in all_orders]
-        self.timestep = timestep
+        assert all(obj.position == pos for pos, obj in objects.items())
+        self.players, self.objects, self.timestep = tuple(players), objects, timestep
+        self._bonus_orders, self._all_orders = _as_recipes(bonus_orders), _as_recipes(all_orders)
         assert len(set(self._bonus_orders)) == len(self._bonus_orders), "Bonus orders must not have duplicates"
         assert len(set(self._all_orders)) == len(self._all_orders), "All orders must not have duplicates"
         assert set(self.bonus_orders).issubset(set(self.all_orders)), "Bonus orders must be a subset of all orders"
@@ -377,11 +363,11 @@ class OvercookedState(object):
 
     @property
     def players_pos_and_or(self):
-        return tuple(zip(self.player_positions, self.player_orientations))
+        return tuple(p.pos_and_or for p in self.players)
 
     @property
     def all_orders(self):
-        return sorted(self._all_orders) if self._all_orders else sorted(Recipe.all_recipes())
+        return sorted(self._all_orders or Recipe.all_recipes())
 
     @property
     def bonus_orders(self):
@@ -395,7 +381,7 @@ class OvercookedState(object):
 
     def add_object(self, obj, pos=None):
         pos = obj.position if pos is None else tuple(pos)
-        assert not self.has_object(pos)
+        assert pos not in self.objects
         obj.position = pos
         self.objects[pos] = obj
 
@@ -404,52 +390,30 @@ class OvercookedState(object):
 
     @classmethod
     def from_players_pos_and_or(cls, players_pos_and_or, bonus_orders=[], all_orders=[]):
-        return cls(
-            [PlayerState(*pos_or) for pos_or in players_pos_and_or],
-            objects={},
-            bonus_orders=bonus_orders,
-            all_orders=all_orders,
-        )
+        return cls([PlayerState(*po) for po in players_pos_and_or], objects={}, bonus_orders=bonus_orders, all_orders=all_orders)
 
     @classmethod
     def from_player_positions(cls, player_positions, bonus_orders=[], all_orders=[]):
-        return cls.from_players_pos_and_or(
-            [(pos, Direction.NORTH) for pos in player_positions], bonus_orders, all_orders
-        )
+        return cls.from_players_pos_and_or([(pos, Direction.NORTH) for pos in player_positions], bonus_orders, all_orders)
 
     def deepcopy(self):
-        return OvercookedState(
-            players=[p.deepcopy() for p in self.players],
-            objects={pos: obj.deepcopy() for pos, obj in self.objects.items()},
-            bonus_orders=[o.to_dict() for o in self.bonus_orders],
-            all_orders=[o.to_dict() for o in self.all_orders],
-            timestep=self.timestep,
-        )
+        return OvercookedState([p.deepcopy() for p in self.players], {pos: obj.deepcopy() for pos, obj in self.objects.items()},
+                               bonus_orders=self.bonus_orders, all_orders=self.all_orders, timestep=self.timestep)
 
     def time_independent_equal(self, other):
-        return (
-            isinstance(other, OvercookedState)
-            and self.players == other.players
-            and set(self.objects.items()) == set(other.objects.items())
-            and self.all_orders == other.all_orders
-            and self.bonus_orders == other.bonus_orders
-        )
+        return (isinstance(other, OvercookedState) and self.players == other.players
+                and set(self.objects.items()) == set(other.objects.items())
+                and (self.all_orders, self.bonus_orders) == (other.all_orders, other.bonus_orders))
 
     def __eq__(self, other):
         return self.time_independent_equal(other) and self.timestep == other.timestep
 
     def __hash__(self):
-        order_hash = hash(tuple(self.bonus_orders)) + hash(tuple(self.all_orders))
-        return hash((self.players, tuple(self.objects.values()), order_hash))
+        return hash((self.players, tuple(self.objects.values()), hash(tuple(self.bonus_orders)) + hash(tuple(self.all_orders))))
 
     def __str__(self):
         return "Players: {}, Objects: {}, Bonus orders: {} All orders: {} Timestep: {}".format(
-            str(self.players),
-            str(list(self.objects.values())),
-            str(self.bonus_orders),
-            str(self.all_orders),
-            str(self.timestep),
-        )
+            str(self.players), str(list(self.objects.values())), str(self.bonus_orders), str(self.all_orders), str(self.timestep))
 
     def to_dict(self):
         return {
@@ -462,12 +426,7 @@ class OvercookedState(object):
 
     @staticmethod
     def from_dict(state_dict):
-        players = [PlayerState.from_dict(p) for p in state_dict["players"]]
         objs = [SoupState.from_dict(o) for o in state_dict["objects"]]
-        return OvercookedState(
-            players,
-            {o.position: o for o in objs},
-            bonus_orders=state_dict.get("bonus_orders", []),
-            all_orders=state_dict.get("all_orders", []),
-            timestep=state_dict.get("timestep", 0),
-        )
+        return OvercookedState([PlayerState.from_dict(p) for p in state_dict["players"]], {o.position: o for o in objs},
+                               bonus_orders=state_dict.get("bonus_orders", []), all_orders=state_dict.get("all_orders", []),
+                               timestep=state_dict.get("timestep", 0))

@@ -139,6 +139,33 @@ def test_value_types_wire_format():
         Action.to_index((1, 1))
 
 
+def test_soups_without_an_explicit_cook_time_behave_like_the_reference():
+    """Legacy (2019) soup dicts and get_soup(finished=True) carry no cook time: the reference falls back to Recipe.time
+    (20 with nothing configured, overcooked_mdp.py:523-530,565-569,638-656); so do these."""
+    legacy = SoupState.from_dict({"name": "soup", "position": (1, 0), "state": ("onion", 3, 20)})
+    assert legacy.ingredients == ["onion"] * 3 and legacy._cooking_tick == 20 and legacy.is_ready and not legacy.is_cooking
+    assert legacy.to_dict()["cook_time"] == 20 and legacy.cook_time_remaining == 0
+    cooking = SoupState.from_dict({"name": "soup", "position": (1, 0), "state": ("onion", 2, 5)})
+    assert cooking.is_cooking and cooking.to_dict()["is_cooking"] and cooking.cook_time == 20 and cooking.cook_time_remaining == 15
+    idle = SoupState.from_dict({"name": "soup", "position": (1, 0), "state": ("onion", 1, 0)})
+    assert idle.is_idle and idle.to_dict()["cook_time"] == -1
+    tom = SoupState.from_dict({"name": "soup", "position": (1, 0), "state": ("tomato", 2, 7)})
+    assert tom.ingredients == ["onion", "tomato", "tomato"], "the reference's tomato branch keeps get_soup's default onion"
+    with pytest.raises(ValueError):
+        SoupState.from_dict({"name": "soup", "position": (1, 0), "state": ("tomato", 3, 7)})
+    done = SoupState.get_soup((2, 0), 3, 0, finished=True)
+    assert done._cooking_tick == 20 and done.is_ready and done.recipe == Recipe(["onion"] * 3)
+    assert SoupState.get_soup((2, 0), 1, 1, finished=True, cook_time=9)._cooking_tick == 9
+    # a layout's own cook time replaces the fallback once the soup meets its layout
+    cc = L.compile_layout("counter_circuit")
+    rec = L.pack_state(cc, OvercookedState.from_dict({
+        "players": [{"position": p, "orientation": (0, -1), "held_object": None} for p in cc.start_player_positions],
+        "objects": [SoupState.get_soup(cc.slot_positions[0], 1, 1, cooking_tick=3).to_dict()],
+        "bonus_orders": cc.start_bonus_orders, "all_orders": cc.start_all_orders, "timestep": 0}))
+    soup = L.unpack_state(cc, rec).objects[cc.slot_positions[0]]
+    assert soup.cook_time == 15 + 7 and soup.is_cooking and soup.to_dict()["cook_time"] == 22
+
+
 def test_layout_file_in_reference_format(tmp_path):
     p = tmp_path / "tiny.layout"
     p.write_text('{"grid": """XPDX\n             O12S\n             XXXX""", "start_all_orders": [{"ingredients": ["onion"]}], "cook_time": 5, "delivery_reward": 7}')
