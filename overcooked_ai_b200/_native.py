@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libovc_b200.so")
+LIB_PATH = os.environ.get("OVC_B200_LIB") or os.path.join(_HERE, "csrc", "libovc_b200.so")  # OVC_B200_LIB: an experiment build (build.py)
 
 ABI_VERSION = 4
 F_AUTO_RESET = 1

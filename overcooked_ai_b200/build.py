@@ -25,14 +25,19 @@ def find_nvcc():
     return "nvcc"
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, defines=()):
+    """variant / defines: an experiment build next to the library (csrc/libovc_b200_<variant>.so, compiled with the given
+    -D macros); OVC_B200_LIB=<path> makes _native load it instead (tools/k5sweep.py A/B runs)."""
+    out = OUT if variant is None else os.path.join(CSRC, "libovc_b200_%s.so" % variant)
     newest = max(os.path.getmtime(os.path.join(CSRC, d)) for d in DEPS)
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= newest:
-        return OUT
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= newest:
+        return out
+    cmd = [find_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SOURCES
     subprocess.check_call(cmd, cwd=CSRC)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    var = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")]
+    defs = [a[2:] for a in sys.argv if a.startswith("-D")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=var[0] if var else None, defines=defs))

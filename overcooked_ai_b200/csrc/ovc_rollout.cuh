@@ -45,6 +45,10 @@ constexpr int DERIVED_ZERO_CHUNKS = (1024 * 2 + 2048) / 16;  // face + move, zer
 // loaded with tick > cook time (ready; bits 8-21 keep its tick + 1).
 constexpr unsigned POT_FROZEN = 1u << 31;
 constexpr int ROLLOUT_MAX_STEPS = 1 << 22;  // clock field: n_steps + cook time + 1 < 2^23
+#ifndef OVC_ROLLOUT_LAG
+#define OVC_ROLLOUT_LAG 1
+#endif
+constexpr bool ROLLOUT_LAG = OVC_ROLLOUT_LAG != 0;  // lanes on their own timelines (see rollout_kernel)
 
 // ---- shared memory through 32-bit window addresses ----
 // tile words change during the launch: volatile + memory clobber keeps program order
@@ -475,43 +479,28 @@ rollout_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
         load_regs(0u);
 
         RollIO<FMT> io(a, env, live_mask);
-        for (int s = 0; s < T; s++) {
-            int2 nxt = act;
-            io.next_action();
-            if (s + 1 < T) nxt = io.load_action();  // prefetch
-            const int a0 = act.x, a1 = act.y;
-            act = nxt;
-            RollOut o{0, 0, 0, 0u, 0u};
-            // stepping a finished env leaves it untouched and flags it (overcooked_env.py:255)
-            const bool stepped = a.horizon > 0 && t >= a.horizon;
+
+        // one player's interact on the live record (:1446-1577); `second`: the acting player is player 1
+        auto interact = [&](bool second, RollOut &o, bool &pot_dirty) {
+            unsigned pa = second ? p1 : p0;
+            const unsigned pb = second ? p0 : p1;
+            int sh = 0;
+            const unsigned c = interact_v2(r, L, D, pa, (pb >> 10) & 7u, misc, ps, old_dyn, (unsigned)t + toff, o.sparse, sh, pot_dirty);
+            if (second) p1 = pa, o.sh1 = sh, o.c1 = c;
+            else p0 = pa, o.sh0 = sh, o.c0 = c;
+        };
+        // everything of a transition after the interacts: movement, environment effects, outputs, episode end
+        auto finish = [&](int a0, int a1, const RollOut &o, bool stepped, bool pot_dirty) {
             int done = 1;
             if (!stepped) {
-                // ---- resolve_interacts :1446-1577: player 0 then player 1 on the live record.  Two emissions of the body:
-                //      the first serves, per environment, the first interacting player (player 0 if it interacts, else
-                //      player 1), the second serves player 1 where BOTH interact (1 environment in 36 under a uniform
-                //      policy), so most warps skip it ----
-                const bool i0 = a0 == OVC_A_INTERACT, i1 = a1 == OVC_A_INTERACT;
-                bool pot_dirty = false;
-                if (i0 || i1) {
-                    const bool second = !i0;  // the acting player is player 1
-                    unsigned pa = second ? p1 : p0;
-                    const unsigned pb = second ? p0 : p1;
-                    int sh = 0;
-                    const unsigned c = interact_v2(r, L, D, pa, (pb >> 10) & 7u, misc, ps, old_dyn, (unsigned)t + toff, o.sparse, sh, pot_dirty);
-                    if (second) p1 = pa, o.sh1 = sh, o.c1 = c;
-                    else p0 = pa, o.sh0 = sh, o.c0 = c;
-                }
-                if (i0 && i1) o.c1 = interact_v2(r, L, D, p1, (p0 >> 10) & 7u, misc, ps, old_dyn, (unsigned)t + toff, o.sparse, o.sh1, pot_dirty);
                 // ---- resolve_movement :1644-1727; a blocked or collided player still turns (quirk Q8) ----
-                {
-                    const unsigned o0 = p0 & 0xFFu, o1 = p1 & 0xFFu;
-                    unsigned n0 = lds_tbl8(D + OVC_DOFF(move) + ((((unsigned)a0 & 7u) << 8) | o0));
-                    unsigned n1 = lds_tbl8(D + OVC_DOFF(move) + ((((unsigned)a1 & 7u) << 8) | o1));
-                    const bool collide = n0 == n1 || (n0 == o1 && n1 == o0);  // :1673-1683
-                    if (collide) n0 = o0, n1 = o1;
-                    if ((unsigned)a0 < 4u) p0 = (p0 & ~0x3FFu) | ((unsigned)a0 << 8) | n0;
-                    if ((unsigned)a1 < 4u) p1 = (p1 & ~0x3FFu) | ((unsigned)a1 << 8) | n1;
-                }
+                const unsigned o0 = p0 & 0xFFu, o1 = p1 & 0xFFu;
+                unsigned n0 = lds_tbl8(D + OVC_DOFF(move) + ((((unsigned)a0 & 7u) << 8) | o0));
+                unsigned n1 = lds_tbl8(D + OVC_DOFF(move) + ((((unsigned)a1 & 7u) << 8) | o1));
+                const bool collide = n0 == n1 || (n0 == o1 && n1 == o0);  // :1673-1683
+                if (collide) n0 = o0, n1 = o1;
+                if ((unsigned)a0 < 4u) p0 = (p0 & ~0x3FFu) | ((unsigned)a0 << 8) | n0;
+                if ((unsigned)a1 < 4u) p1 = (p1 & ~0x3FFu) | ((unsigned)a1 << 8) | n1;
                 // ---- step_environment_effects :1691-1703: cooking soups carry their ready clock, nothing to advance.
                 //      Old dynamics: an idle soup with 3 ingredients starts by itself (:1696-1701), tick 0 -> 1 in this
                 //      transition, i.e. the same clock as a soup started by an interact of this transition ----
@@ -529,7 +518,7 @@ rollout_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
                 done = a.horizon > 0 && t + 1 >= a.horizon;  // is_done overcooked_env.py:321-325
             }
             io.write(o, done, stepped, mask_s);
-            if (stepped) continue;
+            if (stepped) return;
             if (done && (a.flags & OVC_F_AUTO_RESET)) {
                 const unsigned lid0 = misc & 0xFFu;
                 if (RS && a.has_rs) {
@@ -547,6 +536,61 @@ rollout_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
                 load_regs((unsigned)t + toff + 1u);
             } else {
                 t = t + 1;
+            }
+        };
+
+        if (ROLLOUT_LAG && FMT != FMT_STREAM) {
+            // ---- lanes run their own timelines.  Player 0 then player 1 act on the same live record, so an
+            //      environment in which BOTH interact needs the interact body twice; instead of a second emission that
+            //      most of the warp idles through (59 % of warps ran it for one lane on average), such a lane takes TWO
+            //      trips of the loop for that transition — player 0, then player 1 and the rest — while its neighbours
+            //      move on.  Lanes only share instructions, never data, so nothing needs them in step; a lane ends up
+            //      ~T/36 trips behind under a uniform policy and the warp drains at the end.  (The sparse event stream
+            //      votes across the warp per transition and keeps the lockstep loop below.) ----
+            io.next_action();
+            int2 nxt = act;
+            if (T > 1) nxt = io.load_action();
+            int s = 0;
+            bool pending = false, pot_dirty = false;
+            RollOut o{0, 0, 0, 0u, 0u};
+            while (s < T) {
+                const int a0 = act.x, a1 = act.y;
+                const bool stepped = a.horizon > 0 && t >= a.horizon;  // a finished env: untouched + flagged (overcooked_env.py:255)
+                bool whole = true;
+                if (!stepped) {
+                    const bool i0 = a0 == OVC_A_INTERACT, i1 = a1 == OVC_A_INTERACT;
+                    if (i0 || i1) {
+                        interact(pending || !i0, o, pot_dirty);
+                        whole = pending || !(i0 && i1);
+                        pending = !whole;
+                    }
+                }
+                if (whole) {
+                    finish(a0, a1, o, stepped, pot_dirty);
+                    o = RollOut{0, 0, 0, 0u, 0u}, pot_dirty = false;
+                    s++;
+                    act = nxt;
+                    if (s + 1 < T) io.next_action(), nxt = io.load_action();  // prefetch one transition ahead
+                }
+            }
+        } else {
+            for (int s = 0; s < T; s++) {
+                int2 nxt = act;
+                io.next_action();
+                if (s + 1 < T) nxt = io.load_action();  // prefetch
+                const int a0 = act.x, a1 = act.y;
+                act = nxt;
+                RollOut o{0, 0, 0, 0u, 0u};
+                const bool stepped = a.horizon > 0 && t >= a.horizon;  // a finished env: untouched + flagged (overcooked_env.py:255)
+                bool pot_dirty = false;
+                if (!stepped) {
+                    // two emissions of the interact body: the first serves, per environment, the first interacting player,
+                    // the second player 1 where BOTH interact (1 environment in 36 under a uniform policy)
+                    const bool i0 = a0 == OVC_A_INTERACT, i1 = a1 == OVC_A_INTERACT;
+                    if (i0 || i1) interact(!i0, o, pot_dirty);
+                    if (i0 && i1) interact(true, o, pot_dirty);
+                }
+                finish(a0, a1, o, stepped, pot_dirty);  // ONE program point for the warp votes of the sparse event stream
             }
         }
         // ---- registers and pot clocks back into the tile in the external format ----
