@@ -4,6 +4,7 @@ timeout 600 python tools/k5sweep.py --sizes 65536,262144 --layouts cramped_room 
 timeout 300 python tools/k5sweep.py --sizes 131072 --layouts asymmetric_advantages --tiles 64 --libs nolag >> gpurun_out/r2_k5sweep_lag.jsonl 2>&1
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_1gpu.json 2> gpurun_out/r2_bench_1gpu.err
 timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r2_bench_reference.json 2> gpurun_out/r2_bench_reference.err
+timeout 400 python tools/kbench.py --what k2,k3 --sizes 65536,262144,1048576 --ios 1 > gpurun_out/r2_kbench_obs.jsonl 2>&1
 # ncu: full capture of K5 (config 2 / 3 / 4 shapes) and K1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:rollout_kernel -s 2 -c 1 -o gpurun_out/r2_prof_k5_config2 python tools/prof_kernels.py --which k5 > gpurun_out/r2_ncu_k5_config2.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:rollout_kernel -s 2 -c 1 -o gpurun_out/r2_prof_k5_config4 python tools/prof_kernels.py --which k5 --n 131072 --layouts asymmetric_advantages > gpurun_out/r2_ncu_k5_config4.log 2>&1
