@@ -489,8 +489,9 @@ def policy_leg(dev, rank, world, seed, steps, warmup, envs=0):
     S = env.state_words
     l = env.layouts[0]
     return {
-        "workload": "config5: %s, %d envs/GPU, self-play: K2 lossless encode bf16 -> torch CNN (RllibPPOModel-shaped, random init, shared) -> "
-                    "multinomial -> K1 step, whole transition in one CUDA graph" % ("+".join(layouts), n_envs),
+        "workload": "config5: %s, %d envs/GPU, self-play: K2 lossless encode bf16 -> policy (RllibPPOModel-shaped CNN, random init, shared; "
+                    "every convolution folded into one library GEMM, selfplay.DenseGridPolicy) -> multinomial -> K1 step, whole transition "
+                    "in one CUDA graph" % ("+".join(layouts), n_envs),
         "what": what, "value": tot_steps / (max_ms * 1e-3), "unit": "env-steps/s", "steps": steps, "ms_per_step": max_ms / steps,
         "dtype": "int32 env / bf16 observations / bf16-autocast policy", "gpu_launches": 2 * T * steps,
         "env_only": {"ms_per_400_transitions": max_ms_env, "env_steps_per_s_per_gpu": n_envs * T / (max_ms_env * 1e-3),

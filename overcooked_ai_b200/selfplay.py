@@ -43,19 +43,79 @@ class RllibShapedCNN(nn.Module):
         return self.logits(x), self.value(x).squeeze(-1)
 
 
+class DenseGridPolicy(nn.Module):
+    """The same network as ``RllibShapedCNN`` with every convolution folded into ONE matrix per layer.
+
+    On a 5x4 (or 9x5) grid a 'same' convolution spends most of its taps on padding: conv 5x5x26->25 over 20 cells is
+    325 k MACs per observation, while the linear map it IS — 520 inputs -> 500 outputs — is 260 k.  cuDNN also runs
+    25/26-channel convolutions far below the tensor-core peak, whereas ``[2N, 520] x [520, 500]`` is a plain library
+    GEMM.  The matrices are built once by pushing the identity through each convolution (exact: same weights, same
+    function, only the summation order differs), in the observation kernel's own element order ``[x][y][channel]``, so
+    K2's output is consumed as ``[2N, W*H*26]`` without any permute.  The policy stays a CONSUMER of the hot path
+    (library GEMMs), not part of it."""
+
+    def __init__(self, cnn, width, height):
+        super().__init__()
+        self.W, self.H = width, height
+        with torch.no_grad():
+            mats = []
+            shape = (26, width, height)  # (channels, x, y) as the conv sees it
+            for conv in (cnn.conv_initial, cnn.conv_0, cnn.conv_1):
+                c, w, h = shape
+                n_in = c * w * h
+                # basis vector k of the flat [x][y][c] input -> NCHW image with a single one
+                eye = torch.eye(n_in, dtype=conv.weight.dtype, device=conv.weight.device).view(n_in, w, h, c).permute(0, 3, 1, 2)
+                out = F.conv2d(eye, conv.weight, None, padding=conv.padding)  # (n_in, c_out, w', h'), bias added separately
+                co, wo, ho = out.shape[1:]
+                mats.append((out.permute(0, 2, 3, 1).reshape(n_in, wo * ho * co).t().contiguous(),   # [n_out, n_in], [x][y][c] order
+                             conv.bias.view(1, 1, co).expand(wo, ho, co).reshape(-1).clone()))
+                shape = (co, wo, ho)
+            self.conv_as_linear = nn.ModuleList()
+            for m, b in mats:
+                lin = nn.Linear(m.shape[1], m.shape[0])
+                lin.weight.copy_(m), lin.bias.copy_(b)
+                self.conv_as_linear.append(lin)
+            # the first dense layer consumed conv_1's NCHW flatten (c, x, y): re-order its inputs to [x][y][c]
+            co, wo, ho = shape
+            first = cnn.dense[0]
+            d0 = nn.Linear(first.in_features, first.out_features)
+            d0.weight.copy_(first.weight.view(-1, co, wo, ho).permute(0, 2, 3, 1).reshape(first.out_features, -1))
+            d0.bias.copy_(first.bias)
+            self.dense = nn.ModuleList([d0] + [_clone_linear(d) for d in cnn.dense[1:]])
+            self.logits, self.value = _clone_linear(cnn.logits), _clone_linear(cnn.value)
+
+    def forward(self, obs_flat):
+        """obs_flat: [2N, W*H*26] in K2's element order."""
+        x = obs_flat
+        for lin in self.conv_as_linear:
+            x = F.leaky_relu(lin(x), 0.2)
+        for d in self.dense:
+            x = F.leaky_relu(d(x), 0.3)
+        return self.logits(x), self.value(x).squeeze(-1)
+
+
+def _clone_linear(l):
+    c = nn.Linear(l.in_features, l.out_features)
+    with torch.no_grad():
+        c.weight.copy_(l.weight), c.bias.copy_(l.bias)
+    return c
+
+
 class SelfPlayRollout(object):
     """Policy-in-the-loop rollout: both agents of every environment act from the same network."""
 
     def __init__(self, env, model=None, autocast_dtype=torch.bfloat16, use_graph=True, reward_shaping_factor=1.0,
-                 obs_dtype=None):
+                 obs_dtype=None, dense=True):
         """obs_dtype: element type K2 writes (default: bfloat16 when the policy runs under bf16 autocast — the plane
-        values are exact in bf16 and the conversion pass disappears — else float32)."""
+        values are exact in bf16 and the conversion pass disappears — else float32).
+        dense: evaluate the network through ``DenseGridPolicy`` (one library GEMM per layer) instead of cuDNN convolutions."""
         assert len({(l.width, l.height) for l in env.layouts}) == 1, "one grid shape per rollout (group envs by layout)"
         self.env = env
         l = env.layouts[0]
         self.W, self.H = l.width, l.height
         dev = env.device
         self.model = (model or RllibShapedCNN(self.W, self.H)).to(dev).to(memory_format=torch.channels_last).eval()
+        self.dense_model = DenseGridPolicy(self.model, self.W, self.H).to(dev).eval() if dense else None
         self.autocast_dtype = autocast_dtype
         self.factor = float(reward_shaping_factor)
         N = env.n_envs
@@ -72,9 +132,12 @@ class SelfPlayRollout(object):
     def _transition(self):
         env = self.env
         env.lossless_state_encoding(out=self.obs)  # K2
-        x = self.obs.view(2 * env.n_envs, self.W, self.H, 26).permute(0, 3, 1, 2)  # (2N,26,W,H), channels-last strides
         with torch.no_grad(), torch.autocast("cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
-            logits, value = self.model(x)
+            if self.dense_model is not None:
+                logits, value = self.dense_model(self.obs.view(2 * env.n_envs, self.W * self.H * 26))
+            else:
+                x = self.obs.view(2 * env.n_envs, self.W, self.H, 26).permute(0, 3, 1, 2)  # (2N,26,W,H), channels-last strides
+                logits, value = self.model(x)
         probs = torch.softmax(logits.float(), dim=-1)
         a = torch.multinomial(probs, 1).view(env.n_envs, 2)
         self.actions.copy_(a)

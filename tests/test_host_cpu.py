@@ -486,3 +486,21 @@ def test_grid_validity_rules():
             OvercookedGridworld.from_grid(grid)
     with pytest.raises(ValueError):  # valid for the reference, outside this engine: the batched game is the 2-player game
         OvercookedGridworld.from_grid(["XXPXX", "O   O", "X1  X", "XDXSX"])
+
+
+def test_dense_grid_policy_is_the_same_network_as_the_cnn():
+    """selfplay.DenseGridPolicy folds every convolution of RllibShapedCNN into one matrix per layer (library GEMMs on the
+    observation kernel's own element order): same function, to float32 round-off, on every grid shape of the layouts."""
+    import torch
+
+    from overcooked_ai_b200.selfplay import DenseGridPolicy, RllibShapedCNN
+
+    torch.manual_seed(0)
+    for W, H in ((5, 4), (9, 5), (5, 5), (13, 4)):
+        cnn = RllibShapedCNN(W, H).eval()
+        dense = DenseGridPolicy(cnn, W, H).eval()
+        obs = torch.rand(9, W, H, 26)  # [n][x][y][channel], what lossless_state_encoding writes
+        with torch.no_grad():
+            l1, v1 = cnn(obs.permute(0, 3, 1, 2))
+            l2, v2 = dense(obs.reshape(9, -1))
+        assert torch.allclose(l1, l2, atol=1e-6) and torch.allclose(v1, v2, atol=1e-6)
