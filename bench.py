@@ -137,7 +137,8 @@ def bind_rank_to_numa_share(local, world):
     to its share of the host: the usable CPUs of its GPU's NUMA node, divided by physical core among the ranks whose
     GPUs sit on the same node.  Returns a description for the bench line."""
     cpus = usable_cpus()
-    info = {"usable_cpus": len(cpus), "numa_node": None, "bound_cpus": len(cpus), "ranks_sharing_node": world}
+    info = {"usable_cpus": len(cpus), "numa_node": None, "bound_cpus": len(cpus), "ranks_sharing_node": world,
+            "_original_affinity": sorted(os.sched_getaffinity(0))}
     try:
         node = gpu_numa_node(local)
         mine = cpus
@@ -540,6 +541,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     host = bind_rank_to_numa_share(local, world)  # before any pinned allocation / worker thread exists
+    host_affinity = host.pop("_original_affinity")
     D.init("nccl")
     seed = D.broadcast_seed(20260922, device=dev)
     peak, peak_src = load_peaks()
@@ -731,6 +733,7 @@ def main():
     if configs:
         line["configs"] = configs
     if not args.no_cpu:
+        os.sched_setaffinity(0, set(host_affinity))  # the CPU arm gets every CPU the process may use, like --impl reference
         line["cpu_baseline"] = cpu_baseline(layouts, horizon)
     emit(line)
 
