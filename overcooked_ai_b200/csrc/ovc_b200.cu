@@ -467,7 +467,7 @@ static bool use_rollout_kernel(const StepArgs &a, int io) {
 }
 
 template <int S>
-static int launch_rollout_any(const StepArgs &a, cudaStream_t st) {
+static int launch_rollout_tiled(const StepArgs &a, cudaStream_t st) {
     if constexpr (S > 32) {
         return launch_rollout<S, 64>(a, st);
     } else {
@@ -477,6 +477,35 @@ static int launch_rollout_any(const StepArgs &a, cudaStream_t st) {
         default: return launch_rollout<S, 128>(a, st);
         }
     }
+}
+
+// The rollout kernel addresses its action / output rows with 32-bit element indices: a rollout of more than 2^32
+// env-steps is cut into consecutive launches (same stream, same semantics).
+template <int S>
+static int launch_rollout_any(const StepArgs &a0, cudaStream_t st) {
+    const long long max_steps = 0xFFFFFFFFLL / a0.n_envs - 1;
+    if (a0.n_steps <= max_steps) return launch_rollout_tiled<S>(a0, st);
+    if (max_steps < 1 || (a0.flags & OVC_F_OUT_STREAM)) return fail(OVC_E_UNSUPPORTED, "rollout too large for one launch (n_steps * n_envs must stay below 2^32)");
+    // bytes per env-step of each array in this transfer format (the table of ovc_host.cuh: formats_of)
+    const int f = a0.flags;
+    const int b_act = (f & OVC_F_ACT_PACKED) ? 1 : (f & OVC_F_ACT_U8) ? 2 : 8;
+    int b_sparse = 4, b_shaped = 8, b_done = 4, b_events = 8;
+    if (f & OVC_F_OUT_CODES) b_sparse = 0, b_shaped = 0, b_done = 0, b_events = 2;
+    else if (f & OVC_F_OUT_PACKED) b_sparse = 2, b_shaped = 2, b_done = 0, b_events = 2;
+    else if (f & OVC_F_OUT_NARROW) b_sparse = 2, b_shaped = 2, b_done = 1, b_events = 8;
+    for (long long t0 = 0; t0 < a0.n_steps; t0 += max_steps) {
+        StepArgs a = a0;
+        const long long off = t0 * a0.n_envs;
+        a.n_steps = (int)(a0.n_steps - t0 < max_steps ? a0.n_steps - t0 : max_steps);
+        a.actions = reinterpret_cast<const int32_t *>(reinterpret_cast<const char *>(a0.actions) + off * b_act);
+        if (a0.sparse) a.sparse = reinterpret_cast<int32_t *>(reinterpret_cast<char *>(a0.sparse) + off * b_sparse);
+        if (a0.shaped) a.shaped = reinterpret_cast<int32_t *>(reinterpret_cast<char *>(a0.shaped) + off * b_shaped);
+        if (a0.done) a.done = reinterpret_cast<int32_t *>(reinterpret_cast<char *>(a0.done) + off * b_done);
+        a.events = reinterpret_cast<int32_t *>(reinterpret_cast<char *>(a0.events) + off * b_events);
+        const int rc = launch_rollout_tiled<S>(a, st);
+        if (rc) return rc;
+    }
+    return OVC_OK;
 }
 
 template <int S>

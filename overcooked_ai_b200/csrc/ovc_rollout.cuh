@@ -257,61 +257,48 @@ __device__ __forceinline__ unsigned interact_v2(const R &r, uint32_t L, uint32_t
 // (3 % of a transition when they sat in every instantiation), the sparse event stream carries the warp votes.
 constexpr int FMT_WIDE = 0, FMT_HOST = 1, FMT_STREAM = 2;
 
-// Running output / action pointers of one thread: advanced by one transition (n_envs elements) per step, so the
-// loop carries 64-bit adds instead of 64-bit multiplies.  Element sizes follow the transfer format (ovc_b200.cu).
+// Output / action addressing of one thread: ONE 32-bit element index per stream (outputs, actions), advanced by n_envs
+// per transition; every array address is then a single IMAD.WIDE of that index onto the array's base pointer.  (The
+// host keeps n_steps * n_envs below 2^32 per launch by cutting longer rollouts into several launches.)
 template <int FMT>
 struct RollIO {
     static constexpr bool WIDE = FMT == FMT_WIDE;
-    const char *act;
-    char *sparse, *shaped, *done, *events;
-    long long s_act, s_sparse, s_shaped, s_done, s_events;  // bytes per transition (uniform)
-    int flags;
-    // FMT_STREAM: `events` walks the lane-mask rows uint32[n_steps][n_groups], `sparse` is the group's slice of the
-    // value array uint16[n_groups][cap], `done` (nullable) the dense code words uint16[n_steps][n_envs]
-    unsigned live_mask, cnt, cap, lane_lt;
+    const StepArgs &a;
+    unsigned oi, ai;  // element index of this transition's outputs / of the action row loaded last
+    const unsigned n;
+    // FMT_STREAM: lane-mask rows uint32[n_steps][n_groups] (index mi), the group's slice of uint16[n_groups][cap]
+    unsigned live_mask, cnt, cap, lane_lt, mi, n_groups;
+    unsigned short *vals;
     bool leader;
-    __device__ __forceinline__ RollIO(const StepArgs &a, long long env, unsigned live) {
-        flags = a.flags;
-        live_mask = live, cnt = 0, cap = 0, lane_lt = 0, leader = false;
-        int b_act = 8, b_sparse = 4, b_shaped = 8, b_done = 4, b_events = 8;
-        if (!WIDE) {
-            b_act = (flags & OVC_F_ACT_PACKED) ? 1 : (flags & OVC_F_ACT_U8) ? 2 : 8;
-            if (flags & OVC_F_OUT_CODES) b_sparse = 0, b_shaped = 0, b_done = 0, b_events = 2;
-            else if (flags & OVC_F_OUT_PACKED) b_sparse = 2, b_shaped = 2, b_done = 0, b_events = 2;
-            else if (flags & OVC_F_OUT_NARROW) b_sparse = 2, b_shaped = 2, b_done = 1, b_events = 8;
-        }
-        act = reinterpret_cast<const char *>(a.actions) + env * b_act, s_act = a.n_envs * b_act;
+    __device__ __forceinline__ RollIO(const StepArgs &args, long long env, unsigned live) : a(args), n((unsigned)args.n_envs) {
+        oi = ai = (unsigned)env;
+        live_mask = live, cnt = 0, cap = 0, lane_lt = 0, mi = 0, n_groups = 0, vals = nullptr, leader = false;
         if (FMT == FMT_STREAM) {
-            const long long n_groups = (a.n_envs + 31) >> 5, g = env >> 5;
-            cap = ((unsigned)flags >> OVC_F_STREAM_CAP_SHIFT) & 0xFFFFu;
+            n_groups = (unsigned)((a.n_envs + 31) >> 5);
+            mi = (unsigned)(env >> 5);
+            cap = ((unsigned)a.flags >> OVC_F_STREAM_CAP_SHIFT) & 0xFFFFu;
             const unsigned lane = (unsigned)env & 31u;
             lane_lt = (1u << lane) - 1u, leader = lane == 0;
-            events = reinterpret_cast<char *>(a.events) + g * 4, s_events = n_groups * 4;
-            sparse = reinterpret_cast<char *>(a.sparse) + g * (long long)cap * 2, s_sparse = 0;
-            done = a.done ? reinterpret_cast<char *>(a.done) + env * 2 : nullptr, s_done = a.n_envs * 2;
-            shaped = nullptr, s_shaped = 0;
-            return;
+            vals = reinterpret_cast<unsigned short *>(a.sparse) + (size_t)mi * cap;
         }
-        sparse = reinterpret_cast<char *>(a.sparse) + env * b_sparse, s_sparse = a.n_envs * b_sparse;
-        shaped = reinterpret_cast<char *>(a.shaped) + env * b_shaped, s_shaped = a.n_envs * b_shaped;
-        done = reinterpret_cast<char *>(a.done) + env * b_done, s_done = a.n_envs * b_done;
-        events = reinterpret_cast<char *>(a.events) + env * b_events, s_events = a.n_envs * b_events;
     }
     __device__ __forceinline__ int2 load_action() const {
-        if (!WIDE && (flags & OVC_F_ACT_PACKED)) {
-            const unsigned u = *reinterpret_cast<const unsigned char *>(act);
+        if (!WIDE && (a.flags & OVC_F_ACT_PACKED)) {
+            const unsigned u = reinterpret_cast<const unsigned char *>(a.actions)[ai];
             return make_int2((int)(u & 15u), (int)(u >> 4));
         }
-        if (!WIDE && (flags & OVC_F_ACT_U8)) {
-            const uchar2 u = *reinterpret_cast<const uchar2 *>(act);
+        if (!WIDE && (a.flags & OVC_F_ACT_U8)) {
+            const uchar2 u = reinterpret_cast<const uchar2 *>(a.actions)[ai];
             return make_int2(u.x, u.y);
         }
-        return *reinterpret_cast<const int2 *>(act);
+        return reinterpret_cast<const int2 *>(a.actions)[ai];
     }
-    __device__ __forceinline__ void next_action() { act += s_act; }
-    // Writes this transition's outputs and advances to the next transition.  Called at ONE program point by every
-    // live thread of the warp, once per transition (FMT_STREAM votes across the warp here).
+    __device__ __forceinline__ void next_action() { ai += n; }
+    // Writes this transition's outputs and advances to the next transition.  FMT_STREAM: called at ONE program point by
+    // every live thread of the warp, once per transition (it votes across the warp).
     __device__ __forceinline__ void write(const RollOut &o, int done_v, bool stepped, uint32_t mask) {
+        const unsigned i = oi;
+        oi += n;
         if (FMT == FMT_STREAM) {
             // What a rollout produces is mostly zeros.  Per warp (32 consecutive environments) and transition: ONE
             // 32-bit lane mask of the non-zero code words (__ballot_sync), and the non-zero words compacted behind the
@@ -319,42 +306,39 @@ struct RollIO {
             const unsigned w = o.c0 | (o.c1 << 5) | ((unsigned)done_v << 10) | (stepped ? 1u << 11 : 0u) |
                                (o.sh0 != 0 ? 1u << 12 : 0u) | (o.sh1 != 0 ? 1u << 13 : 0u);
             const unsigned m = __ballot_sync(live_mask, w != 0);
-            if (leader) *reinterpret_cast<unsigned *>(events) = m;
+            if (leader) reinterpret_cast<unsigned *>(a.events)[mi] = m;
+            mi += n_groups;
             if (w != 0) {
                 const unsigned pos = cnt + __popc(m & lane_lt);
-                if (pos < cap) reinterpret_cast<unsigned short *>(sparse)[pos] = (unsigned short)w;  // beyond cap: dropped, the masks tell
+                if (pos < cap) vals[pos] = (unsigned short)w;  // beyond cap: dropped, the masks tell
             }
             cnt += __popc(m);
-            events += s_events;
-            if (done) *reinterpret_cast<unsigned short *>(done) = (unsigned short)w, done += s_done;
+            if (a.done) reinterpret_cast<unsigned short *>(a.done)[i] = (unsigned short)w;  // dense backup
             return;
         }
-        if (!WIDE && (flags & (OVC_F_OUT_CODES | OVC_F_OUT_PACKED))) {
+        if (!WIDE && (a.flags & (OVC_F_OUT_CODES | OVC_F_OUT_PACKED))) {
             unsigned w = o.c0 | (o.c1 << 5) | ((unsigned)done_v << 10) | (stepped ? 1u << 11 : 0u);
-            if (flags & OVC_F_OUT_CODES) {
+            if (a.flags & OVC_F_OUT_CODES) {
                 w |= (o.sh0 != 0 ? 1u << 12 : 0u) | (o.sh1 != 0 ? 1u << 13 : 0u);
             } else {
-                *reinterpret_cast<short *>(sparse) = (short)o.sparse;
-                *reinterpret_cast<char2 *>(shaped) = make_char2((signed char)o.sh0, (signed char)o.sh1);
-                sparse += s_sparse, shaped += s_shaped;
+                reinterpret_cast<short *>(a.sparse)[i] = (short)o.sparse;
+                reinterpret_cast<char2 *>(a.shaped)[i] = make_char2((signed char)o.sh0, (signed char)o.sh1);
             }
-            *reinterpret_cast<unsigned short *>(events) = (unsigned short)w;
-            events += s_events;
+            reinterpret_cast<unsigned short *>(a.events)[i] = (unsigned short)w;
             return;
         }
         const unsigned e0 = stepped ? (unsigned)OVC_EVF_STEPPED_DONE : lds_tbl32(mask + 4u * o.c0);
         const unsigned e1 = stepped ? (unsigned)OVC_EVF_STEPPED_DONE : lds_tbl32(mask + 4u * o.c1);
-        if (!WIDE && (flags & OVC_F_OUT_NARROW)) {
-            *reinterpret_cast<short *>(sparse) = (short)o.sparse;
-            *reinterpret_cast<unsigned char *>(done) = (unsigned char)done_v;
-            *reinterpret_cast<char2 *>(shaped) = make_char2((signed char)o.sh0, (signed char)o.sh1);
+        if (!WIDE && (a.flags & OVC_F_OUT_NARROW)) {
+            reinterpret_cast<short *>(a.sparse)[i] = (short)o.sparse;
+            reinterpret_cast<unsigned char *>(a.done)[i] = (unsigned char)done_v;
+            reinterpret_cast<char2 *>(a.shaped)[i] = make_char2((signed char)o.sh0, (signed char)o.sh1);
         } else {
-            *reinterpret_cast<int *>(sparse) = o.sparse;
-            *reinterpret_cast<int *>(done) = done_v;
-            *reinterpret_cast<int2 *>(shaped) = make_int2(o.sh0, o.sh1);
+            a.sparse[i] = o.sparse;
+            a.done[i] = done_v;
+            reinterpret_cast<int2 *>(a.shaped)[i] = make_int2(o.sh0, o.sh1);
         }
-        *reinterpret_cast<int2 *>(events) = make_int2((int)e0, (int)e1);
-        sparse += s_sparse, shaped += s_shaped, done += s_done, events += s_events;
+        reinterpret_cast<int2 *>(a.events)[i] = make_int2((int)e0, (int)e1);
     }
 };
 
