@@ -4,7 +4,11 @@
 #pragma once
 #include <sched.h>
 #include <stdint.h>
+#include <string.h>
 #include <unistd.h>
+#if defined(__x86_64__) || defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include <condition_variable>
 #include <functional>
@@ -171,57 +175,98 @@ static int expand_codes_host(const uint16_t *codes, int64_t n_steps, int64_t n_e
     return OVC_OK;
 }
 
+// Row segments of the dense arrays are built in a small thread-local buffer (L1 resident) and then written out ONCE with
+// non-temporal stores: the arrays are written, never read, by the expander, so ordinary stores would first fetch every
+// line from DRAM (read-for-ownership) and double the memory traffic — measured: 16 threads expanded 26 M env-steps in
+// 3.3 ms with memset + scatter into the arrays, which is the memory bandwidth of 2 x 131 MB, not the work.
+static bool use_nt_stores() {  // OVC_EXPAND_NT=0 switches the non-temporal stores off (measurement hook)
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("OVC_EXPAND_NT");
+        v = e ? atoi(e) != 0 : 1;
+    }
+    return v != 0;
+}
+
+static inline void stream_out(void *dst, const void *src, size_t bytes) {
+#if defined(__x86_64__) || defined(__SSE2__)
+    if ((((uintptr_t)dst | bytes) & 15) == 0 && use_nt_stores()) {
+        const __m128i *s = (const __m128i *)src;
+        __m128i *d = (__m128i *)dst;
+        for (size_t i = 0; i < bytes / 16; i++) _mm_stream_si128(d + i, _mm_load_si128(s + i));
+        return;
+    }
+#endif
+    memcpy(dst, src, bytes);
+}
+
 // OVC_F_OUT_STREAM -> dense arrays.  A thread owns a range of groups [g0, g1) = environments [32 g0, 32 g1): per
-// transition it zero-fills its segment of every output row and scatters the few non-zero words its masks name,
-// reading each group's value slice sequentially (the cursor restarts at every chunk).
+// transition it builds its segment of every output row (zeros + the few non-zero words its masks name, each group's
+// value slice read sequentially; the cursor restarts at every chunk) and streams it out.
 static void expand_stream_range(const uint32_t *masks, const uint16_t *values, int64_t n_steps, int64_t chunk, int64_t cap,
                                 int64_t n_envs, int64_t G, int64_t g0, int64_t g1, const int32_t *env_layout,
                                 const int32_t *reward_tbl, int16_t *sparse, int8_t *shaped, uint8_t *done, int32_t *events,
                                 const int32_t *mask, int64_t *overflow) {
-    const int64_t e0 = g0 * 32, e1 = g1 * 32 < n_envs ? g1 * 32 : n_envs;
-    if (e1 <= e0) return;
-    std::vector<uint32_t> cur((size_t)(g1 - g0));
+    constexpr int SEG_GROUPS = 32;  // 1024 environments per segment: 2 + 2 + 1 + 8 KB of row buffers
+    alignas(64) int16_t b_sparse[SEG_GROUPS * 32];
+    alignas(64) int8_t b_shaped[SEG_GROUPS * 64];
+    alignas(64) uint8_t b_done[SEG_GROUPS * 32];
+    alignas(64) int32_t b_events[SEG_GROUPS * 64];
     int64_t over = 0;
-    for (int64_t t = 0; t < n_steps; t++) {
-        const int64_t c = t / chunk;
-        if (t % chunk == 0) {
-            for (auto &x : cur) over += x > (uint64_t)cap, x = 0;
-        }
-        const int64_t row = t * n_envs;
-        if (sparse) memset(sparse + row + e0, 0, (size_t)(e1 - e0) * sizeof(int16_t));
-        if (shaped) memset(shaped + 2 * (row + e0), 0, (size_t)(e1 - e0) * 2);
-        if (done) memset(done + row + e0, 0, (size_t)(e1 - e0));
-        if (events) memset(events + 2 * (row + e0), 0, (size_t)(e1 - e0) * 2 * sizeof(int32_t));
-        const uint32_t *mrow = masks + t * G;
-        for (int64_t g = g0; g < g1; g++) {
-            uint32_t m = mrow[g];
-            if (!m) continue;
-            const uint16_t *vals = values + ((size_t)c * (size_t)G + (size_t)g) * (size_t)cap;
-            uint32_t &k = cur[(size_t)(g - g0)];
-            while (m) {
-                const int l = __builtin_ctz(m);
-                m &= m - 1;
-                const uint32_t kk = k++;
-                if (kk >= (uint64_t)cap) continue;  // dropped by the kernel: counted at the chunk boundary
-                const unsigned w = vals[kk];
-                const int64_t e = g * 32 + l, i = row + e;
-                const unsigned c0 = w & 31u, c1 = (w >> 5) & 31u;
-                const int32_t *tb = reward_tbl + (env_layout ? (size_t)env_layout[e] * 64 : 0);
-                if (sparse) sparse[i] = (int16_t)(tb[c0] + tb[c1]);
-                if (shaped) {
-                    shaped[2 * i] = (int8_t)((w >> 12) & 1u ? tb[32 + c0] : 0);
-                    shaped[2 * i + 1] = (int8_t)((w >> 13) & 1u ? tb[32 + c1] : 0);
-                }
-                if (done) done[i] = (uint8_t)((w >> 10) & 1u);
-                if (events) {
-                    const bool stepped = (w >> 11) & 1u;
-                    events[2 * i] = stepped ? (int32_t)OVC_EVF_STEPPED_DONE : mask[c0];
-                    events[2 * i + 1] = stepped ? (int32_t)OVC_EVF_STEPPED_DONE : mask[c1];
+    for (int64_t s0 = g0; s0 < g1; s0 += SEG_GROUPS) {
+        const int64_t s1 = s0 + SEG_GROUPS < g1 ? s0 + SEG_GROUPS : g1;
+        const int64_t e0 = s0 * 32, e1 = s1 * 32 < n_envs ? s1 * 32 : n_envs;
+        if (e1 <= e0) break;
+        const size_t ne = (size_t)(e1 - e0);
+        uint32_t cur[SEG_GROUPS] = {0};
+        for (int64_t t = 0; t < n_steps; t++) {
+            const int64_t c = t / chunk;
+            if (t % chunk == 0)
+                for (int k = 0; k < SEG_GROUPS; k++) over += cur[k] > (uint64_t)cap, cur[k] = 0;
+            if (sparse) memset(b_sparse, 0, ne * sizeof(int16_t));
+            if (shaped) memset(b_shaped, 0, ne * 2);
+            if (done) memset(b_done, 0, ne);
+            if (events) memset(b_events, 0, ne * 2 * sizeof(int32_t));
+            const uint32_t *mrow = masks + t * G;
+            for (int64_t g = s0; g < s1; g++) {
+                uint32_t m = mrow[g];
+                if (!m) continue;
+                const uint16_t *vals = values + ((size_t)c * (size_t)G + (size_t)g) * (size_t)cap;
+                uint32_t &k = cur[g - s0];
+                while (m) {
+                    const int l = __builtin_ctz(m);
+                    m &= m - 1;
+                    const uint32_t kk = k++;
+                    if (kk >= (uint64_t)cap) continue;  // dropped by the kernel: counted at the chunk boundary
+                    const unsigned w = vals[kk];
+                    const int64_t e = g * 32 + l;
+                    const size_t i = (size_t)(e - e0);
+                    const unsigned c0 = w & 31u, c1 = (w >> 5) & 31u;
+                    const int32_t *tb = reward_tbl + (env_layout ? (size_t)env_layout[e] * 64 : 0);
+                    if (sparse) b_sparse[i] = (int16_t)(tb[c0] + tb[c1]);
+                    if (shaped) {
+                        b_shaped[2 * i] = (int8_t)((w >> 12) & 1u ? tb[32 + c0] : 0);
+                        b_shaped[2 * i + 1] = (int8_t)((w >> 13) & 1u ? tb[32 + c1] : 0);
+                    }
+                    if (done) b_done[i] = (uint8_t)((w >> 10) & 1u);
+                    if (events) {
+                        const bool stepped = (w >> 11) & 1u;
+                        b_events[2 * i] = stepped ? (int32_t)OVC_EVF_STEPPED_DONE : mask[c0];
+                        b_events[2 * i + 1] = stepped ? (int32_t)OVC_EVF_STEPPED_DONE : mask[c1];
+                    }
                 }
             }
+            const size_t row = (size_t)t * (size_t)n_envs + (size_t)e0;
+            if (sparse) stream_out(sparse + row, b_sparse, ne * sizeof(int16_t));
+            if (shaped) stream_out(shaped + 2 * row, b_shaped, ne * 2);
+            if (done) stream_out(done + row, b_done, ne);
+            if (events) stream_out(events + 2 * row, b_events, ne * 2 * sizeof(int32_t));
         }
+        for (int k = 0; k < SEG_GROUPS; k++) over += cur[k] > (uint64_t)cap;
     }
-    for (auto &x : cur) over += x > (uint64_t)cap;
+#if defined(__x86_64__) || defined(__SSE2__)
+    _mm_sfence();  // non-temporal stores are weakly ordered: make them visible before the caller is told we are done
+#endif
     if (over) __atomic_fetch_add(overflow, over, __ATOMIC_RELAXED);
 }
 

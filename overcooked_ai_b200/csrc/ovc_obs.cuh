@@ -2,12 +2,11 @@
 //
 // K2  encode_kernel<T>   lossless_state_encoding (reference overcooked_mdp.py:2385-2561):
 //     out[env][player][x][y][26].  A CTA builds the observations of a tile of E environments in
-//     shared memory (the layout's static terrain planes stamped in as a template with vector copies,
-//     then a sparse scatter of what moves: players, objects, urgency) and ships the tile — one
-//     contiguous byte range of the output — with ONE bulk async store (cp.async.bulk.global.shared::cta,
-//     SASS UBLKCP), so every HBM write is a full, coalesced line no matter how scattered the non-zeros
-//     are.  Write-bound: 2*W*H*26*sizeof(T) bytes per environment (4160 B fp32 on cramped_room) against
-//     64-128 B read.
+//     shared memory (zero fill with 16-byte stores, then a sparse scatter of the few non-zero
+//     entries) and ships the tile — one contiguous byte range of the output — with ONE bulk
+//     async store (cp.async.bulk.global.shared::cta, SASS UBLKCP), so every HBM write is a full,
+//     coalesced line no matter how scattered the non-zeros are.  Write-bound: 2*W*H*26*sizeof(T)
+//     bytes per environment (4160 B fp32 on cramped_room) against 64-128 B read.
 // K3  featurize_kernel   featurize_state (:2579-2898) for the default planner parameters,
 //     [env][player][F] float32: per-player feature blocks staged feature-major in shared memory
 //     (conflict free), then assembled and written as coalesced float4 rows.
@@ -78,82 +77,44 @@ __device__ __forceinline__ void put_object(T *obs, int WH26, int H, const ovc_la
     else if (type == OVC_O_TOMATO) put_both(obs, WH26, H, x, y, PL_TOMATOES, 1);
 }
 
-// One transition of an environment changes two player cells and a few objects; the terrain planes (:2449-2465) never
-// change.  So a CTA builds the terrain planes of its layout ONCE, as a template view in shared memory, stamps the
-// template into both views of every environment of its tile with vector copies (instead of zero-filling them and
-// scattering W*H terrain cells per environment), and scatters only what moves: 2 players, the held and loose objects,
-// and the urgency plane of the environments in their last 40 steps.  A tile that mixes layouts (variable-MDP pools of
-// one grid shape) takes the general path: zero fill + every cell.
 template <class T>
 __global__ void __launch_bounds__(256) encode_kernel(const EncodeArgs a) {
     extern __shared__ char smem_raw[];
     T *buf = reinterpret_cast<T *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-    __shared__ int s_n_full;  // environments whose every cell has to be visited (urgency plane / foreign layout)
     const long long env0 = (long long)blockIdx.x * a.E;
     const long long rem = a.n_envs - env0;
     const int ne = (int)(rem < a.E ? rem : a.E);
     const int WH = a.W * a.H, WH26 = WH * N_PLANES;
     const size_t tile_bytes = (size_t)ne * a.obs_elems * sizeof(T);
-    const int view_bytes = WH26 * (int)sizeof(T);
-    T *tmpl = reinterpret_cast<T *>(reinterpret_cast<char *>(buf) + (((size_t)a.E * a.obs_elems * sizeof(T) + 15) & ~(size_t)15));
-    int *full_list = reinterpret_cast<int *>(reinterpret_cast<char *>(tmpl) + ((view_bytes + 15) & ~15));  // [E]
 
-    const unsigned lid0 = (unsigned)__ldg(a.state + env0 * a.S + 3) & 0xFF;
-    bool foreign = false;
-    for (int el = threadIdx.x; el < ne; el += blockDim.x) foreign |= ((unsigned)__ldg(a.state + (env0 + el) * a.S + 3) & 0xFF) != lid0;
-    if (threadIdx.x == 0) s_n_full = 0;
-    const bool mixed = __syncthreads_or(foreign);
-    const ovc_layout_t *__restrict__ L0 = a.layouts + lid0;
-
-    if (!mixed) {
-        // ---- phase A: the template view: zeros + this layout's terrain planes ----
-        for (int i = threadIdx.x; i < (view_bytes + 15) / 16; i += blockDim.x) reinterpret_cast<int4 *>(tmpl)[i] = make_int4(0, 0, 0, 0);
-        __syncthreads();
-        for (int k = threadIdx.x; k < WH; k += blockDim.x) {
-            const int x = (int)__umulhi((unsigned)k, a.inv_h), y = k - x * a.H;
-            const int terr = __ldg(&L0->cell[(y << 4) | x]) & 7;
-            const int plane = (int)((0x0F0A0E0D0C0B00ull >> (terr * 8)) & 0xFF);  // X 11, O 12, T 13, D 14, P 10, S 15 (0 = none)
-            if (terr != OVC_T_FLOOR && terr != OVC_T_OUTSIDE) tmpl[k * N_PLANES + plane] = plane_value<T>(1);
-        }
-        __syncthreads();
-        // ---- phase B: stamp it into every view of the tile (widest vector the view size allows) ----
-        const int n_views = 2 * ne, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
-        if ((view_bytes & 15) == 0) {
-            for (int v = warp; v < n_views; v += n_warps)
-                for (int j = lane; j < view_bytes / 16; j += 32)
-                    reinterpret_cast<int4 *>(reinterpret_cast<char *>(buf) + (size_t)v * view_bytes)[j] = reinterpret_cast<const int4 *>(tmpl)[j];
-        } else if ((view_bytes & 7) == 0) {
-            for (int v = warp; v < n_views; v += n_warps)
-                for (int j = lane; j < view_bytes / 8; j += 32)
-                    reinterpret_cast<int2 *>(reinterpret_cast<char *>(buf) + (size_t)v * view_bytes)[j] = reinterpret_cast<const int2 *>(tmpl)[j];
-        } else if ((view_bytes & 3) == 0) {
-            for (int v = warp; v < n_views; v += n_warps)
-                for (int j = lane; j < view_bytes / 4; j += 32)
-                    reinterpret_cast<int *>(reinterpret_cast<char *>(buf) + (size_t)v * view_bytes)[j] = reinterpret_cast<const int *>(tmpl)[j];
-        } else {  // odd cell counts with 1-byte planes: 2-byte pieces (26 planes per cell keep every view 2-byte aligned)
-            for (int v = warp; v < n_views; v += n_warps)
-                for (int j = lane; j < view_bytes / 2; j += 32)
-                    reinterpret_cast<short *>(reinterpret_cast<char *>(buf) + (size_t)v * view_bytes)[j] = reinterpret_cast<const short *>(tmpl)[j];
-        }
-    } else {
+    // ---- phase A: zero fill (16-byte stores; the buffer is 128-byte aligned and padded) ----
+    {
         int4 *b4 = reinterpret_cast<int4 *>(buf);
         const int n16 = (int)((tile_bytes + 15) / 16);
         for (int i = threadIdx.x; i < n16; i += blockDim.x) b4[i] = make_int4(0, 0, 0, 0);
     }
     __syncthreads();
 
-    // ---- phase C: what moves.  Work items per environment: 2 players + one per object-capable cell (an upper bound
-    //      S-4 is used so the item count is layout independent); item 0 also decides whether the environment needs
-    //      the every-cell pass.  The integer divisions are multiplications by host-computed reciprocals. ----
-    const int items_per_env = 2 + (a.S - 4);
+    // ---- phase B: scatter.  Work items per environment: W*H terrain cells, 2 players, n_slots
+    //      object cells (an upper bound S-4 is used so the item count is layout independent).
+    //      The two integer divisions per item (item -> environment, cell -> column) are multiplications by
+    //      host-computed reciprocals.  (A variant with a power-of-two lane group per environment measured
+    //      slower: its idle lanes cost more than the divisions did.) ----
+    const int items_per_env = WH + 2 + (a.S - 4);
     for (int it = threadIdx.x; it < ne * items_per_env; it += blockDim.x) {
         const int el = (int)__umulhi((unsigned)it, a.inv_items), k = it - el * items_per_env;
         const int32_t *__restrict__ rec = a.state + (env0 + el) * a.S;
         const ovc_layout_t *__restrict__ L = a.layouts + (__ldg(rec + 3) & 0xFF);
         T *obs = buf + (size_t)el * a.obs_elems;
-        if (k < 2) {  // player layers :2468-2479 (+ the held object, at the holder's cell)
-            if (k == 0 && (mixed || a.horizon - __ldg(rec) < 40)) full_list[atomicAdd(&s_n_full, 1)] = el;
-            const int j = k;
+        if (k < WH) {  // static terrain planes :2449-2465 and the urgency plane :2446-2447
+            const int x = (int)__umulhi((unsigned)k, a.inv_h), y = k - x * a.H;
+            const int terr = __ldg(&L->cell[(y << 4) | x]) & 7;
+            // terrain code -> plane: X 11, O 12, T 13, D 14, P 10, S 15 (0 = none)
+            const int plane = (int)((0x0F0A0E0D0C0B00ull >> (terr * 8)) & 0xFF);
+            if (terr != OVC_T_FLOOR && terr != OVC_T_OUTSIDE) put_both(obs, WH26, a.H, x, y, plane, 1);
+            if (a.horizon - __ldg(rec) < 40) put_both(obs, WH26, a.H, x, y, PL_URGENCY, 1);
+        } else if (k < WH + 2) {  // player layers :2468-2479 (+ the held object, at the holder's cell)
+            const int j = k - WH;
             const unsigned w = (unsigned)__ldg(rec + 1 + j);
             const int x = w & 15, y = (w >> 4) & 15, ori = (w >> 8) & 3;
             const int base = (x * a.H + y) * N_PLANES;
@@ -167,7 +128,7 @@ __global__ void __launch_bounds__(256) encode_kernel(const EncodeArgs a) {
             obs[(size_t)(1 - own) * WH26 + base + PL_ORI + 4 + ori] = one;
             put_object(obs, WH26, a.H, L, w >> 10, x, y, false);
         } else {  // loose objects: one per object-capable cell
-            const int slot = k - 2;
+            const int slot = k - WH - 2;
             if (slot < __ldg(&L->n_slots)) {
                 const unsigned code = (unsigned)__ldg(rec + 4 + slot) & OVC_OBJ_MASK;
                 if (code) {
@@ -177,26 +138,8 @@ __global__ void __launch_bounds__(256) encode_kernel(const EncodeArgs a) {
             }
         }
     }
-    __syncthreads();
-    // ---- phase D: every cell of the few environments that need it: the urgency plane :2446-2447 (all ones in the
-    //      last 40 steps) and, in a mixed tile, the terrain planes of each environment's own layout ----
-    const int n_full = s_n_full;
-    for (int it = threadIdx.x; it < n_full * WH; it += blockDim.x) {
-        const int f = it / WH, k = it - f * WH;
-        const int el = full_list[f];
-        const int32_t *__restrict__ rec = a.state + (env0 + el) * a.S;
-        T *obs = buf + (size_t)el * a.obs_elems;
-        const int x = (int)__umulhi((unsigned)k, a.inv_h), y = k - x * a.H;
-        if (mixed) {
-            const ovc_layout_t *__restrict__ L = a.layouts + (__ldg(rec + 3) & 0xFF);
-            const int terr = __ldg(&L->cell[(y << 4) | x]) & 7;
-            const int plane = (int)((0x0F0A0E0D0C0B00ull >> (terr * 8)) & 0xFF);
-            if (terr != OVC_T_FLOOR && terr != OVC_T_OUTSIDE) put_both(obs, WH26, a.H, x, y, plane, 1);
-        }
-        if (a.horizon - __ldg(rec) < 40) put_both(obs, WH26, a.H, x, y, PL_URGENCY, 1);
-    }
 
-    // ---- phase E: ship the tile ----
+    // ---- phase C: ship the tile ----
     char *dst = reinterpret_cast<char *>(a.out) + (size_t)env0 * a.obs_elems * sizeof(T);
     if ((tile_bytes & 15) == 0) {
         fence_async_smem();
@@ -229,7 +172,7 @@ static int encode_lossless_impl(const ovc_layout_t *layouts, const int32_t *stat
     a.layouts = layouts, a.state = state, a.view_swap = view_swap, a.out = out, a.n_envs = n_envs;
     a.S = S, a.W = W, a.H = H, a.horizon = horizon;
     a.obs_elems = 2 * W * H * N_PLANES;
-    a.inv_items = (unsigned)((0x100000000ull + (unsigned)(2 + (S - 4)) - 1) / (unsigned)(2 + (S - 4)));
+    a.inv_items = (unsigned)((0x100000000ull + (unsigned)(W * H + 2 + (S - 4)) - 1) / (unsigned)(W * H + 2 + (S - 4)));
     a.inv_h = (unsigned)((0x100000000ull + (unsigned)H - 1) / (unsigned)H);
     const int obs_bytes = a.obs_elems * esize;
     // Tile buffer size.  Measured on B200 (tools/kbench.py, 262 144 envs, fp32): 16 KB 85 %, 24 KB 105 %,
@@ -247,8 +190,7 @@ static int encode_lossless_impl(const ovc_layout_t *layouts, const int32_t *stat
     E -= E % mult;
     if (E < mult) E = mult;
     a.E = E;
-    // tile + the template view + the list of environments that need the every-cell pass
-    const size_t smem = (((size_t)E * obs_bytes + 15) & ~(size_t)15) + ((size_t)(obs_bytes / 2 + 15) & ~(size_t)15) + (size_t)E * 4 + 128 + 16;
+    const size_t smem = (size_t)E * obs_bytes + 128 + 16;
     const unsigned grid = (unsigned)((n_envs + E - 1) / E);
     cudaError_t e;
 #define OVC_LAUNCH_ENCODE(TT)                                                                                    \

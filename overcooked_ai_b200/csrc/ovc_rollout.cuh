@@ -46,9 +46,10 @@ constexpr int DERIVED_ZERO_CHUNKS = (1024 * 2 + 2048) / 16;  // face + move, zer
 constexpr unsigned POT_FROZEN = 1u << 31;
 constexpr int ROLLOUT_MAX_STEPS = 1 << 22;  // clock field: n_steps + cook time + 1 < 2^23
 #ifndef OVC_ROLLOUT_LAG
-#define OVC_ROLLOUT_LAG 1
+#define OVC_ROLLOUT_LAG 0
 #endif
-constexpr bool ROLLOUT_LAG = OVC_ROLLOUT_LAG != 0;  // lanes on their own timelines (see rollout_kernel)
+// Experiment, OFF: lanes on their own timelines (see rollout_kernel).  Measured 2-3x SLOWER (profiles/r2_k5_experiments.md).
+constexpr bool ROLLOUT_LAG = OVC_ROLLOUT_LAG != 0;
 
 // ---- shared memory through 32-bit window addresses ----
 // tile words change during the launch: volatile + memory clobber keeps program order
@@ -524,13 +525,13 @@ rollout_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
         };
 
         if (ROLLOUT_LAG && FMT != FMT_STREAM) {
-            // ---- lanes run their own timelines.  Player 0 then player 1 act on the same live record, so an
-            //      environment in which BOTH interact needs the interact body twice; instead of a second emission that
-            //      most of the warp idles through (59 % of warps ran it for one lane on average), such a lane takes TWO
-            //      trips of the loop for that transition — player 0, then player 1 and the rest — while its neighbours
-            //      move on.  Lanes only share instructions, never data, so nothing needs them in step; a lane ends up
-            //      ~T/36 trips behind under a uniform policy and the warp drains at the end.  (The sparse event stream
-            //      votes across the warp per transition and keeps the lockstep loop below.) ----
+            // ---- EXPERIMENT (compiled out: OVC_ROLLOUT_LAG=0).  Lanes run their own timelines: an environment in which
+            //      BOTH players interact takes TWO trips of the loop for that transition (player 0, then player 1 and the
+            //      rest) instead of a second emission of the interact body that most of the warp idles through.  It removes
+            //      ~20 % of the issued instructions and MEASURED 2-3x SLOWER (65 536 envs: 0.69 ms against 0.37 ms per 400
+            //      transitions; 262 144 envs: 3.1 against 1.0 ms): once the lanes of a warp sit at different transitions,
+            //      every action load and every output store of the warp touches up to 32 sectors instead of 8 / 4, and
+            //      the sector traffic, not the instruction count, sets the pace.  Kept as the record of that measurement. ----
             io.next_action();
             int2 nxt = act;
             if (T > 1) nxt = io.load_action();

@@ -471,10 +471,9 @@ def test_sparse_event_stream_carries_the_whole_result():
     want = [_np(x) for x in env_a.rollout(torch.from_numpy(acts).cuda())]
     masks, values, dense_words = env_b.rollout_stream(torch.from_numpy(wire.pack_actions(acts)).cuda(), cap=T * 32, dense_backup=True)
     assert torch.equal(env_b.state, env_a.state)
-    codes = env_a.alloc_rollout_out(T, codes=True)
-    env_a.reset(), env_b.reset()
-    env_a.rollout(torch.from_numpy(wire.pack_actions(acts)).cuda(), out=codes)
-    env_b.rollout(torch.from_numpy(acts).cuda())
+    env_c = BatchedOvercookedEnv(names, n, **kw)  # a third copy of the same start states for the dense code words
+    codes = env_c.alloc_rollout_out(T, codes=True)
+    env_c.rollout(torch.from_numpy(wire.pack_actions(acts)).cuda(), out=codes)
     assert torch.equal(dense_words, codes[3]), "the dense backup is the OVC_F_OUT_CODES word"
     nz = _np(codes[3]) != 0
     m = _np(masks).view(np.uint32)
@@ -484,27 +483,28 @@ def test_sparse_event_stream_carries_the_whole_result():
     assert over == 0
     for k, w in zip(("sparse", "shaped", "done", "events"), want):
         assert np.array_equal(got[k].numpy(), w), k
-    # too small a capacity: nothing is written out of bounds, the overflow is counted
-    per_group = bits.reshape(T, -1)[:, : (n // 32) * 32].reshape(T, n // 32, 32).sum((0, 2))
+    # too small a capacity: nothing is written out of bounds, the overflow is counted (a fresh env: the same trajectory)
+    env_d = BatchedOvercookedEnv(names, n, **kw)
+    G = env_d.n_groups()
+    per_group = np.pad(bits, ((0, 0), (0, G * 32 - n))).reshape(T, G, 32).sum((0, 2))
     cap = int(per_group.max()) - 1
-    env_b.reset(), env_a.reset()
-    guard = torch.full((env_b.n_groups() * cap + 64,), 0x5A5A, dtype=torch.int16, device="cuda")
-    out = (torch.zeros((T, env_b.n_groups()), dtype=torch.int32, device="cuda"), guard[: env_b.n_groups() * cap].view(1, env_b.n_groups(), cap), None)
-    env_b.rollout_stream(torch.from_numpy(acts).cuda(), cap=cap, out=out)
-    assert (guard[env_b.n_groups() * cap:] == 0x5A5A).all()
-    _, over = env_b.expand_stream(out[0].cpu(), out[1].cpu().contiguous())
+    guard = torch.full((G * cap + 64,), 0x5A5A, dtype=torch.int16, device="cuda")
+    out = (torch.zeros((T, G), dtype=torch.int32, device="cuda"), guard[: G * cap].view(1, G, cap), None)
+    env_d.rollout_stream(torch.from_numpy(acts).cuda(), cap=cap, out=out)
+    assert (guard[G * cap:] == 0x5A5A).all() and torch.equal(env_d.state, env_a.state)
+    _, over = env_d.expand_stream(out[0].cpu(), out[1].cpu().contiguous())
     assert over == int((per_group > cap).sum()) >= 1
     # ---- the host pipeline: chunks, two overlapping passes, and an overflow recovered from the device-side backup ----
-    env_a.reset(), env_b.reset()
-    want = [_np(x) for x in env_a.rollout(torch.from_numpy(acts).cuda())]
-    want2 = [_np(x) for x in env_a.rollout(torch.from_numpy(acts[::-1].copy()).cuda())]
-    pipe = HostRolloutPipeline(env_b, T, chunk=40, stream=True, stream_fill=0.5, host_buffers=2)
+    env_e, env_f = BatchedOvercookedEnv(names, n, **kw), BatchedOvercookedEnv(names, n, **kw)
+    want1 = [_np(x) for x in env_e.rollout(torch.from_numpy(acts).cuda())]
+    want2 = [_np(x) for x in env_e.rollout(torch.from_numpy(acts[::-1].copy()).cuda())]
+    pipe = HostRolloutPipeline(env_f, T, chunk=40, stream=True, stream_fill=0.5, host_buffers=2)
     assert pipe.stream_cap == 640 and pipe.h2d_bytes_per_step == n
     fwd, rev = torch.from_numpy(wire.pack_actions(acts)).pin_memory(), torch.from_numpy(wire.pack_actions(acts[::-1])).pin_memory()
     (h1, e1), s1 = pipe.run(fwd, wait=False), pipe._last_set
     (h2, e2), s2 = pipe.run(rev, wait=False), pipe._last_set
     assert s1 != s2
-    for h, e, st, w in ((h1, e1, s1, want), (h2, e2, s2, want2)):
+    for h, e, st, w in ((h1, e1, s1, want1), (h2, e2, s2, want2)):
         e.synchronize()
         dense = pipe.expand(h, codes_set=st, events=True)
         assert pipe.last_overflow == 0
@@ -512,10 +512,10 @@ def test_sparse_event_stream_carries_the_whole_result():
             assert np.array_equal(dense[k].numpy(), x), k
     pipe.join()
     torch.cuda.synchronize()
-    assert torch.equal(env_b.state, env_a.state)
+    assert torch.equal(env_f.state, env_e.state)
     pipe.close()
-    env_a.reset(), env_b.reset()
-    pipe = HostRolloutPipeline(env_b, T, chunk=40, stream=True, stream_fill=0.02, packed_actions=False)  # 26 slots per group and chunk
+    env_g = BatchedOvercookedEnv(names, n, **kw)
+    pipe = HostRolloutPipeline(env_g, T, chunk=40, stream=True, stream_fill=0.02, packed_actions=False)  # 26 slots per group and chunk
     h = pipe.run(torch.from_numpy(acts.astype(np.uint8)).pin_memory())
     torch.cuda.synchronize()
     dense = pipe.expand(h, events=True)
