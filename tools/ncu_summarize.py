@@ -31,7 +31,7 @@ METRICS = [
     ("stall no_instruction / issue", "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", 1.0),
     ("stall not_selected / issue", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", 1.0),
     ("stall math_pipe_throttle / issue", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", 1.0),
-    ("shared bank-conflict wavefronts (%)", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", 1.0),
+    ("shared bank conflicts (count)", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", 1.0),
 ]
 TO_BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
