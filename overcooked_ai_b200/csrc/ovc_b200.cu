@@ -432,27 +432,28 @@ static int launch_rollout(const StepArgs &a, cudaStream_t st) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = (a.flags & OVC_F_PDL) ? 1 : 0;
+    // Programmatic dependent launch is for the microsecond-long per-transition kernel.  Here it only lets the next launch's
+    // CTAs sit on the SMs beside a kernel that runs for hundreds of microseconds: measured 0.46 ms instead of 0.36 ms per
+    // launch with back-to-back launches of 1-warp CTAs (profiles/r2_k5_experiments.md), nothing with larger CTAs.  Not used.
+    cfg.numAttrs = 0;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap, a);
     if (e != cudaSuccess) return cuda_fail(e, "rollout kernel launch");
     return OVC_OK;
 }
 
-// environments per CTA of the rollout kernel (measured, profiles/r2_k5_tile_sweep.md): one warp per CTA spreads a small
-// batch most evenly over the 148 SMs (65 536 envs = 13.8 warps per SM); bigger batches amortise the per-CTA table
-// derivation better with 2-4 warps per CTA, and a many-layout table set (4.5 KB of shared memory per layout and CTA)
-// wants the largest tile.  OVC_K5_TILE overrides (tuning hook).
+// environments per CTA of the rollout kernel (measured, profiles/r2_k5_experiments.md): 2 warps per CTA; a many-layout
+// table set (4.5 KB of shared memory per layout and CTA) wants the largest tile so that enough CTAs fit an SM.  One warp
+// per CTA is as fast at 65 536 environments and slower above.  OVC_K5_TILE overrides (tuning hook).
 static int rollout_tile(int S, long long n_envs, int n_layouts) {
     static int forced = -1;
     if (forced < 0) {
         const char *e = getenv("OVC_K5_TILE");
         forced = e ? atoi(e) : 0;
     }
+    (void)n_envs;
     if (S > 32) return 64;
     if (forced == 32 || forced == 64 || forced == 128) return forced;
-    if (n_layouts >= 3) return 128;
-    if (S == 16 && n_envs <= 148LL * 16 * 32) return 32;
-    return 64;
+    return n_layouts >= 3 ? 128 : 64;
 }
 
 // true: handled by the rollout kernel; false: the caller falls back to step_kernel with n_steps > 1

@@ -6,8 +6,8 @@
 #include <stdint.h>
 #include <string.h>
 #include <unistd.h>
-#if defined(__x86_64__) || defined(__SSE2__)
-#include <emmintrin.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
 #endif
 
 #include <condition_variable>
@@ -188,13 +188,30 @@ static bool use_nt_stores() {  // OVC_EXPAND_NT=0 switches the non-temporal stor
     return v != 0;
 }
 
+#if defined(__x86_64__)
+// whole cache lines per store where the CPU has 512-bit vectors (one write-combining buffer per instruction)
+__attribute__((target("avx512f"))) static void stream_out_avx512(void *dst, const void *src, size_t bytes) {
+    const __m512i *s = (const __m512i *)src;
+    __m512i *d = (__m512i *)dst;
+    for (size_t i = 0; i < bytes / 64; i++) _mm512_stream_si512(d + i, _mm512_load_si512(s + i));
+}
+static bool cpu_has_avx512() {
+    static int v = -1;
+    if (v < 0) v = __builtin_cpu_supports("avx512f") ? 1 : 0;
+    return v != 0;
+}
+#endif
+
 static inline void stream_out(void *dst, const void *src, size_t bytes) {
-#if defined(__x86_64__) || defined(__SSE2__)
-    if ((((uintptr_t)dst | bytes) & 15) == 0 && use_nt_stores()) {
-        const __m128i *s = (const __m128i *)src;
-        __m128i *d = (__m128i *)dst;
-        for (size_t i = 0; i < bytes / 16; i++) _mm_stream_si128(d + i, _mm_load_si128(s + i));
-        return;
+#if defined(__x86_64__)
+    if (use_nt_stores()) {
+        if ((((uintptr_t)dst | (uintptr_t)src | bytes) & 63) == 0 && cpu_has_avx512()) return stream_out_avx512(dst, src, bytes);
+        if ((((uintptr_t)dst | bytes) & 15) == 0) {
+            const __m128i *s = (const __m128i *)src;
+            __m128i *d = (__m128i *)dst;
+            for (size_t i = 0; i < bytes / 16; i++) _mm_stream_si128(d + i, _mm_load_si128(s + i));
+            return;
+        }
     }
 #endif
     memcpy(dst, src, bytes);
@@ -264,7 +281,7 @@ static void expand_stream_range(const uint32_t *masks, const uint16_t *values, i
         }
         for (int k = 0; k < SEG_GROUPS; k++) over += cur[k] > (uint64_t)cap;
     }
-#if defined(__x86_64__) || defined(__SSE2__)
+#if defined(__x86_64__)
     _mm_sfence();  // non-temporal stores are weakly ordered: make them visible before the caller is told we are done
 #endif
     if (over) __atomic_fetch_add(overflow, over, __ATOMIC_RELAXED);

@@ -566,7 +566,14 @@ rollout_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
                 const int a0 = act.x, a1 = act.y;
                 act = nxt;
                 RollOut o{0, 0, 0, 0u, 0u};
-                const bool stepped = a.horizon > 0 && t >= a.horizon;  // a finished env: untouched + flagged (overcooked_env.py:255)
+                bool stepped = a.horizon > 0 && t >= a.horizon;  // a finished env: untouched + flagged (overcooked_env.py:255)
+                if (FMT != FMT_STREAM) {  // its own exit: the common path below then carries no "stepped" selects
+                    if (stepped) {
+                        io.write(o, 1, true, mask_s);
+                        continue;
+                    }
+                    stepped = false;
+                }
                 bool pot_dirty = false;
                 if (!stepped) {
                     // two emissions of the interact body: the first serves, per environment, the first interacting player,
@@ -575,7 +582,8 @@ rollout_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
                     if (i0 || i1) interact(!i0, o, pot_dirty);
                     if (i0 && i1) interact(true, o, pot_dirty);
                 }
-                finish(a0, a1, o, stepped, pot_dirty);  // ONE program point for the warp votes of the sparse event stream
+                // FMT_STREAM: ONE program point for the warp votes, so finished environments go through it as well
+                finish(a0, a1, o, FMT == FMT_STREAM && stepped, pot_dirty);
             }
         }
         // ---- registers and pot clocks back into the tile in the external format ----

@@ -280,7 +280,8 @@ def test_host_expander_of_code_words_matches_the_numpy_decoder():
     assert np.array_equal(wire.pack_actions(np.array([[5, 3], [0, 4]])), np.array([0x35, 0x40], np.uint8))
 
 
-def test_host_expander_of_the_sparse_event_stream():
+@pytest.mark.parametrize("N", [1000, 1024], ids=["ragged_rows", "cache_line_aligned_rows"])
+def test_host_expander_of_the_sparse_event_stream(N):
     """ovc_expand_stream_host (host code of the library, no GPU involved): lane masks + compacted non-zero words built
     here with numpy from random code words, chunked as the pipeline chunks them; the expansion must equal the expansion
     of the dense words, count overflowing (chunk, group) slices, and read dropped words as zero."""
@@ -290,7 +291,7 @@ def test_host_expander_of_the_sparse_event_stream():
     layouts = [L.compile_layout(n) for n in ("cramped_room", "counter_circuit")]
     tbl = wire.code_reward_table(layouts)
     rng = np.random.RandomState(3)
-    T, N, chunk = 23, 1000, 8  # N not a multiple of 32: the last group is partial
+    T, chunk = 23, 8  # N = 1000: the last group is partial and rows are unaligned (memcpy path); 1024: streaming stores
     G, n_chunks = (N + 31) // 32, -(-T // chunk)
     w = (rng.randint(0, 32, (T, N)) | (rng.randint(0, 32, (T, N)) << 5) | (rng.randint(0, 2, (T, N)) << 10)
          | (rng.randint(0, 4, (T, N)) << 12)).astype(np.uint16)

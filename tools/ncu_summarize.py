@@ -70,6 +70,8 @@ def main():
             v = float(v.replace(",", ""))
             if m.startswith("dram__bytes"):
                 v = v * TO_BYTES.get(u, 1.0) / 1e6
+            if m == "gpu__time_duration.sum":
+                v = v * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(u, 1.0)
             col[label] = v
         wi = col["warp instructions"] / (n_envs / 32.0 * n_steps)
         dram = (col["DRAM read (MB)"] + col["DRAM written (MB)"]) * 1e6
