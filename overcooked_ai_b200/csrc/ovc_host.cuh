@@ -179,14 +179,15 @@ static int expand_codes_host(const uint16_t *codes, int64_t n_steps, int64_t n_e
 // non-temporal stores: the arrays are written, never read, by the expander, so ordinary stores would first fetch every
 // line from DRAM (read-for-ownership) and double the memory traffic — measured: 16 threads expanded 26 M env-steps in
 // 3.3 ms with memset + scatter into the arrays, which is the memory bandwidth of 2 x 131 MB, not the work.
-static bool use_nt_stores() {  // OVC_EXPAND_NT=0 switches the non-temporal stores off (measurement hook)
+static int nt_store_mode() {  // OVC_EXPAND_NT (measurement hook): 0 = ordinary stores, 1 = 16-byte streaming stores only, unset = widest
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("OVC_EXPAND_NT");
-        v = e ? atoi(e) != 0 : 1;
+        v = e ? atoi(e) : 2;
     }
-    return v != 0;
+    return v;
 }
+static bool use_nt_stores() { return nt_store_mode() != 0; }
 
 #if defined(__x86_64__)
 // whole cache lines per store where the CPU has 512-bit vectors (one write-combining buffer per instruction)
@@ -205,7 +206,7 @@ static bool cpu_has_avx512() {
 static inline void stream_out(void *dst, const void *src, size_t bytes) {
 #if defined(__x86_64__)
     if (use_nt_stores()) {
-        if ((((uintptr_t)dst | (uintptr_t)src | bytes) & 63) == 0 && cpu_has_avx512()) return stream_out_avx512(dst, src, bytes);
+        if (nt_store_mode() >= 2 && (((uintptr_t)dst | (uintptr_t)src | bytes) & 63) == 0 && cpu_has_avx512()) return stream_out_avx512(dst, src, bytes);
         if ((((uintptr_t)dst | bytes) & 15) == 0) {
             const __m128i *s = (const __m128i *)src;
             __m128i *d = (__m128i *)dst;
