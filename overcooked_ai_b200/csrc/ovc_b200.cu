@@ -484,7 +484,15 @@ static int launch_rollout_tiled(const StepArgs &a, cudaStream_t st) {
 // env-steps is cut into consecutive launches (same stream, same semantics).
 template <int S>
 static int launch_rollout_any(const StepArgs &a0, cudaStream_t st) {
-    const long long max_steps = 0xFFFFFFFFLL / a0.n_envs - 1;
+    long long max_steps = 0xFFFFFFFFLL / a0.n_envs - 1;
+    {
+        static long long cap = -1;  // OVC_K5_MAX_LAUNCH_STEPS: test hook, cuts rollouts into launches of at most that many transitions
+        if (cap < 0) {
+            const char *e = getenv("OVC_K5_MAX_LAUNCH_STEPS");
+            cap = e ? atoll(e) : 0;
+        }
+        if (cap > 0 && cap < max_steps && !(a0.flags & OVC_F_OUT_STREAM)) max_steps = cap;
+    }
     if (a0.n_steps <= max_steps) return launch_rollout_tiled<S>(a0, st);
     if (max_steps < 1 || (a0.flags & OVC_F_OUT_STREAM)) return fail(OVC_E_UNSUPPORTED, "rollout too large for one launch (n_steps * n_envs must stay below 2^32)");
     // bytes per env-step of each array in this transfer format (the table of ovc_host.cuh: formats_of)

@@ -733,3 +733,44 @@ def test_two_ranks_mixed_batch_on_gpus():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, PYTHONPATH=root, OMP_NUM_THREADS="1"))
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert "DIST_GPU_OK" in out.stdout
+
+
+def test_long_rollouts_are_cut_into_launches():
+    """The rollout kernel addresses its rows with 32-bit element indices, so ovc_rollout cuts a rollout of more than 2^32
+    env-steps into consecutive launches.  The cut itself (pointer arithmetic per transfer format, pot clocks across the
+    cut) is exercised at a small size through the library's test hook, in a child process (the hook is read once)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    code = r"""
+import numpy as np, torch
+from oracle import cpu
+from overcooked_ai_b200 import wire
+from overcooked_ai_b200.batched import BatchedOvercookedEnv
+names, n, T = ["cramped_room", "counter_circuit"], 777, 53
+rng = np.random.RandomState(2)
+acts = rng.randint(0, 6, size=(T, n, 2)).astype(np.int32); acts[rng.rand(T, n, 2) < 0.4] = 5
+env = BatchedOvercookedEnv(names, n, horizon=25, auto_reset=True)
+state = env.state.cpu().numpy().copy()
+want = cpu.rollout(env._tab_host, env._starts_host, state, acts, horizon=25, flags=1, n_threads=2)
+got = env.rollout(torch.from_numpy(acts).cuda())                      # int32 formats, 8 launches of <= 7 transitions
+for g, w in zip(got, want):
+    assert np.array_equal(g.cpu().numpy(), w)
+assert np.array_equal(env.state.cpu().numpy(), state)
+env.reset()
+out = env.alloc_rollout_out(T, codes=True)                            # one-byte actions in, 2-byte code words out
+env.rollout(torch.from_numpy(wire.pack_actions(acts)).cuda(), out=out)
+dense = env.expand_codes(out[3].cpu(), events=True)
+for k, w in zip(("sparse", "shaped", "done", "events"), want):
+    assert np.array_equal(dense[k].numpy(), w), k
+env.reset()
+out = env.alloc_rollout_out(T, packed=True)                           # uint8 actions, packed outputs
+env.rollout(torch.from_numpy(acts.astype(np.uint8)).cuda(), out=out)
+assert np.array_equal(out[0].cpu().numpy(), want[0]) and np.array_equal(out[1].cpu().numpy(), want[1])
+print("CUT_OK")
+"""
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, PYTHONPATH=root, OVC_K5_MAX_LAUNCH_STEPS="7"))
+    assert out.returncode == 0 and "CUT_OK" in out.stdout, out.stdout[-1000:] + out.stderr[-3000:]
