@@ -165,6 +165,14 @@ def bind_rank_to_numa_share(local, world):
                 mine = sorted(c for key in part for c in cores[key])
         os.sched_setaffinity(0, set(mine))
         info["bound_cpus"], info["ranks_sharing_node"] = len(mine), len(sharing)
+        if info["numa_node"] is not None:  # and prefer that node's memory for what is allocated from here on (pinned buffers)
+            try:
+                import ctypes
+                mask = ctypes.c_ulong(1 << info["numa_node"])
+                rc = ctypes.CDLL(None, use_errno=True).syscall(238, 1, ctypes.byref(mask), 65)  # set_mempolicy(MPOL_PREFERRED)
+                info["mempolicy"] = "preferred node %d" % info["numa_node"] if rc == 0 else "set_mempolicy failed (errno %d)" % ctypes.get_errno()
+            except Exception as e:
+                info["mempolicy"] = "unavailable: %r" % (e,)
     except Exception as e:  # never let placement break the measurement
         info["error"] = repr(e)[:120]
     return info
