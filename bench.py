@@ -140,16 +140,23 @@ def bind_rank_to_numa_share(local, world):
     info = {"usable_cpus": len(cpus), "numa_node": None, "bound_cpus": len(cpus), "ranks_sharing_node": world,
             "_original_affinity": sorted(os.sched_getaffinity(0))}
     try:
-        node = gpu_numa_node(local)
-        mine = cpus
-        sharing = list(range(world))
-        if node is not None:
-            node_cpus = set(_parse_cpulist(open("/sys/devices/system/node/node%d/cpulist" % node).read()))
-            local_cpus = [c for c in cpus if c in node_cpus]
-            if local_cpus:
-                mine = local_cpus
-                sharing = [g for g in range(world) if gpu_numa_node(g) == node]
-                info["numa_node"] = node
+        # every rank's candidate CPUs: the usable CPUs of its GPU's NUMA node, or all usable CPUs where the lease has none there;
+        # ranks with the SAME candidates share them (by physical core) — 8 ranks on a whole box get 16 CPUs each, two ranks
+        # of a small lease whose CPUs all sit on one node get half of it each
+        def candidates(g):
+            nd = gpu_numa_node(g)
+            if nd is not None:
+                on_node = set(_parse_cpulist(open("/sys/devices/system/node/node%d/cpulist" % nd).read()))
+                loc = [c for c in cpus if c in on_node]
+                if loc:
+                    return nd, tuple(loc)
+            return None, tuple(cpus)
+
+        cands = [candidates(g) for g in range(world)]
+        node, mine = cands[local] if local < world else candidates(local)
+        mine = list(mine)
+        sharing = [g for g in range(world) if cands[g][1] == tuple(mine)] or [local]
+        info["numa_node"] = node
         if len(sharing) > 1 and local in sharing:
             cores = {}
             for c in mine:  # group hardware threads by physical core
@@ -423,7 +430,14 @@ def engine_leg(name, dev, rank, world, seed, steps, warmup, peak, peak_src, ncu_
     D.barrier()
     ms = e0.elapsed_time(e1)
     if sampler is not None:
+        # the timed region lasts a few milliseconds, less than one nvidia-smi sampling period: keep the SAME launches going
+        # (untimed) for ~0.4 s so that the clock / throttle record really is taken under this load
+        n_more = max(10, int(400.0 / max(ms / steps, 1e-3)))
+        for _ in range(n_more):
+            env.rollout(actions, out=out)
+        torch.cuda.synchronize(dev)
         clocks = sampler.stop()
+        clocks["sampled_over"] = "the timed region and %d more launches of the same kernel (~0.4 s, untimed)" % n_more
     steps_local = float(n_envs) * T * steps
     tot_steps, max_ms, tot_reward = D.reduce_counters(steps_local, ms, float(out[0].sum().item()), device=dev)
     env.reset()
