@@ -653,7 +653,7 @@ int ovc_encode_lossless(const void *layouts, int n_layouts, const int32_t *state
                         void *stream) {
     int rc = ovc::check_common(layouts, n_layouts, state, n_envs, state_words);
     if (rc) return rc;
-    return ovc::encode_lossless_impl((const ovc_layout_t *)layouts, n_layouts, state, view_swap, out, dtype, n_envs, state_words,
+    return ovc::encode_lossless_impl((const ovc_layout_t *)layouts, state, view_swap, out, dtype, n_envs, state_words,
                                      width, height, horizon, (cudaStream_t)stream);
 }
 

@@ -157,109 +157,9 @@ __global__ void __launch_bounds__(256) encode_kernel(const EncodeArgs a) {
     }
 }
 
-// Single-layout batches (n_layouts == 1: configs 2, 4, 5 and every per-layout segment encode of a mixed batch is NOT this
-// case — those tables hold several layouts): the terrain planes (:2449-2465) never change, so the CTA builds them ONCE as a
-// template view and stamps the template into both views of every environment of its tile with 16 / 8 / 4-byte copies —
-// instead of zero-filling the tile and scattering W*H terrain cells per environment — and scatters only what moves: 2
-// players, the held and loose objects, and the urgency plane of the environments in their last 40 steps.  No record is
-// read before the stamp is done, so the only dependent global loads are the ones the scatter needs anyway.
-template <class T>
-__global__ void __launch_bounds__(256) encode_kernel_1layout(const EncodeArgs a) {
-    extern __shared__ char smem_raw[];
-    T *buf = reinterpret_cast<T *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-    const long long env0 = (long long)blockIdx.x * a.E;
-    const long long rem = a.n_envs - env0;
-    const int ne = (int)(rem < a.E ? rem : a.E);
-    const int WH = a.W * a.H, WH26 = WH * N_PLANES;
-    const size_t tile_bytes = (size_t)ne * a.obs_elems * sizeof(T);
-    const int view_bytes = WH26 * (int)sizeof(T);
-    T *tmpl = reinterpret_cast<T *>(reinterpret_cast<char *>(buf) + (((size_t)a.E * a.obs_elems * sizeof(T) + 15) & ~(size_t)15));
-    const ovc_layout_t *__restrict__ L = a.layouts;
-
-    // ---- phase A: the template view: zeros + the layout's terrain planes ----
-    for (int i = threadIdx.x; i < (view_bytes + 15) / 16; i += blockDim.x) reinterpret_cast<int4 *>(tmpl)[i] = make_int4(0, 0, 0, 0);
-    __syncthreads();
-    for (int k = threadIdx.x; k < WH; k += blockDim.x) {
-        const int x = (int)__umulhi((unsigned)k, a.inv_h), y = k - x * a.H;
-        const int terr = __ldg(&L->cell[(y << 4) | x]) & 7;
-        const int plane = (int)((0x0F0A0E0D0C0B00ull >> (terr * 8)) & 0xFF);  // X 11, O 12, T 13, D 14, P 10, S 15 (0 = none)
-        if (terr != OVC_T_FLOOR && terr != OVC_T_OUTSIDE) tmpl[k * N_PLANES + plane] = plane_value<T>(1);
-    }
-    __syncthreads();
-    // ---- phase B: stamp it into every view of the tile: the tile is n_views copies of the template back to back, so
-    //      piece i of the tile is piece (i mod pieces-per-view) of the template ----
-    {
-        const int vw = (view_bytes & 15) == 0 ? 16 : (view_bytes & 7) == 0 ? 8 : (view_bytes & 3) == 0 ? 4 : 2;
-        const int ppv = view_bytes / vw, total = 2 * ne * ppv;
-        const unsigned inv_ppv = (unsigned)((0x100000000ull + (unsigned)ppv - 1) / (unsigned)ppv);
-        for (int i = threadIdx.x; i < total; i += blockDim.x) {
-            const int j = i - (int)__umulhi((unsigned)i, inv_ppv) * ppv;
-            if (vw == 16) reinterpret_cast<int4 *>(buf)[i] = reinterpret_cast<const int4 *>(tmpl)[j];
-            else if (vw == 8) reinterpret_cast<int2 *>(buf)[i] = reinterpret_cast<const int2 *>(tmpl)[j];
-            else if (vw == 4) reinterpret_cast<int *>(buf)[i] = reinterpret_cast<const int *>(tmpl)[j];
-            else reinterpret_cast<short *>(buf)[i] = reinterpret_cast<const short *>(tmpl)[j];
-        }
-    }
-    __syncthreads();
-    // ---- phase C: what moves.  Items per environment: 2 players, one per object-capable cell (upper bound S-4), and W*H
-    //      urgency cells that do nothing unless the environment is in its last 40 steps ----
-    const int items_per_env = 2 + (a.S - 4);
-    for (int it = threadIdx.x; it < ne * items_per_env; it += blockDim.x) {
-        const int el = (int)__umulhi((unsigned)it, a.inv_items), k = it - el * items_per_env;
-        const int32_t *__restrict__ rec = a.state + (env0 + el) * a.S;
-        T *obs = buf + (size_t)el * a.obs_elems;
-        if (k < 2) {  // player layers :2468-2479 (+ the held object, at the holder's cell)
-            const unsigned w = (unsigned)__ldg(rec + 1 + k);
-            const int x = w & 15, y = (w >> 4) & 15, ori = (w >> 8) & 3;
-            const int base = (x * a.H + y) * N_PLANES;
-            const int own = (a.view_swap && __ldg(a.view_swap + env0 + el)) ? 1 - k : k;
-            const T one = plane_value<T>(1);
-            obs[(size_t)own * WH26 + base + PL_LOC] = one;
-            obs[(size_t)own * WH26 + base + PL_ORI + ori] = one;
-            obs[(size_t)(1 - own) * WH26 + base + PL_LOC + 1] = one;
-            obs[(size_t)(1 - own) * WH26 + base + PL_ORI + 4 + ori] = one;
-            put_object(obs, WH26, a.H, L, w >> 10, x, y, false);
-        } else {  // loose objects: one per object-capable cell
-            const int slot = k - 2;
-            if (slot < __ldg(&L->n_slots)) {
-                const unsigned code = (unsigned)__ldg(rec + 4 + slot) & OVC_OBJ_MASK;
-                if (code) {
-                    const int pb = __ldg(&L->slot_pos[slot]);
-                    put_object(obs, WH26, a.H, L, code, pb & 15, pb >> 4, slot < __ldg(&L->n_pots));
-                }
-            }
-        }
-    }
-    // urgency plane :2446-2447 (all ones in the last 40 steps): one pass over (environment, cell), a no-op for most
-    for (int it = threadIdx.x; it < ne * WH; it += blockDim.x) {
-        const int el = it / WH, k = it - el * WH;
-        if (a.horizon - __ldg(a.state + (env0 + el) * a.S) < 40) {
-            const int x = (int)__umulhi((unsigned)k, a.inv_h), y = k - x * a.H;
-            put_both(buf + (size_t)el * a.obs_elems, WH26, a.H, x, y, PL_URGENCY, 1);
-        }
-    }
-
-    // ---- phase D: ship the tile ----
-    char *dst = reinterpret_cast<char *>(a.out) + (size_t)env0 * a.obs_elems * sizeof(T);
-    if ((tile_bytes & 15) == 0) {
-        fence_async_smem();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            bulk_store_1d(dst, buf, (uint32_t)tile_bytes);
-            bulk_commit();
-            bulk_wait_read<0>();
-        }
-    } else {
-        __syncthreads();
-        T *d = reinterpret_cast<T *>(dst);
-        const int n = ne * a.obs_elems;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = buf[i];
-    }
-}
-
 static int gcd_int(int a, int b) { return b ? gcd_int(b, a % b) : a; }
 
-static int encode_lossless_impl(const ovc_layout_t *layouts, int n_layouts, const int32_t *state, const int32_t *view_swap, void *out,
+static int encode_lossless_impl(const ovc_layout_t *layouts, const int32_t *state, const int32_t *view_swap, void *out,
                                 int dtype, long long n_envs, int S, int W, int H, int horizon, cudaStream_t st) {
     if (!out) return fail(OVC_E_BADARG, "null output pointer");
     if (((uintptr_t)out & 15) != 0) return fail(OVC_E_BADARG, "output must be 16-byte aligned");
@@ -272,16 +172,7 @@ static int encode_lossless_impl(const ovc_layout_t *layouts, int n_layouts, cons
     a.layouts = layouts, a.state = state, a.view_swap = view_swap, a.out = out, a.n_envs = n_envs;
     a.S = S, a.W = W, a.H = H, a.horizon = horizon;
     a.obs_elems = 2 * W * H * N_PLANES;
-    // one layout in the table: the template kernel (terrain planes stamped, only moving items scattered); OVC_ENC_TEMPLATE=0/1
-    // overrides (measurement hook)
-    static int tmpl_mode = -1;
-    if (tmpl_mode < 0) {
-        const char *env = getenv("OVC_ENC_TEMPLATE");
-        tmpl_mode = env ? atoi(env) : 2;
-    }
-    const bool use_tmpl = n_layouts == 1 && (tmpl_mode == 1 || (tmpl_mode == 2 && esize < 4));
-    const int items = use_tmpl ? 2 + (S - 4) : W * H + 2 + (S - 4);
-    a.inv_items = (unsigned)((0x100000000ull + (unsigned)items - 1) / (unsigned)items);
+    a.inv_items = (unsigned)((0x100000000ull + (unsigned)(W * H + 2 + (S - 4)) - 1) / (unsigned)(W * H + 2 + (S - 4)));
     a.inv_h = (unsigned)((0x100000000ull + (unsigned)H - 1) / (unsigned)H);
     const int obs_bytes = a.obs_elems * esize;
     // Tile buffer size.  Measured on B200 (tools/kbench.py, 262 144 envs, fp32): 16 KB 85 %, 24 KB 105 %,
@@ -299,15 +190,14 @@ static int encode_lossless_impl(const ovc_layout_t *layouts, int n_layouts, cons
     E -= E % mult;
     if (E < mult) E = mult;
     a.E = E;
-    const size_t smem = (((size_t)E * obs_bytes + 15) & ~(size_t)15) + (use_tmpl ? ((size_t)(obs_bytes / 2 + 15) & ~(size_t)15) : 0) + 128 + 16;
+    const size_t smem = (size_t)E * obs_bytes + 128 + 16;
     const unsigned grid = (unsigned)((n_envs + E - 1) / E);
     cudaError_t e;
-#define OVC_LAUNCH_ENCODE(TT)                                                                                                    \
-    do {                                                                                                                         \
-        auto kern = use_tmpl ? encode_kernel_1layout<TT> : encode_kernel<TT>;                                                    \
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                  \
-        if (e != cudaSuccess) return cuda_fail(e, "encode kernel attribute");                                                    \
-        kern<<<grid, 256, smem, st>>>(a);                                                                                        \
+#define OVC_LAUNCH_ENCODE(TT)                                                                                    \
+    do {                                                                                                         \
+        e = cudaFuncSetAttribute(encode_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+        if (e != cudaSuccess) return cuda_fail(e, "encode kernel attribute");                                    \
+        encode_kernel<TT><<<grid, 256, smem, st>>>(a);                                                           \
     } while (0)
     if (dtype == OVC_DT_F32) OVC_LAUNCH_ENCODE(float);
     else if (dtype == OVC_DT_U8) OVC_LAUNCH_ENCODE(uint8_t);
