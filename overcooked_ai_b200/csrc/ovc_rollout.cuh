@@ -160,32 +160,36 @@ struct RollOut {
     unsigned c0, c1;  // event codes
 };
 
-// Aggregates of the pot snapshot (get_pot_states :1809-1838) that the usefulness predicates consume:
-//   bit 0  every pot is full (cooking, ready or idle with 3 ingredients; get_full_pots :1875-1880)
-//   bit 1  no pot is full
-//   bits 4..  number of pots a dish is useful for (ready + cooking + idle with 1 or 2; is_dish_pickup_useful :2199-2203)
+// Aggregates of the pot snapshot (get_pot_states :1809-1838) that the usefulness predicates consume, in one register:
+//   bits 0-3  n_full: pots that are full (cooking, ready, or idle with 3 ingredients; get_full_pots :1875-1880)
+//   bits 4-7  n_dish: pots a dish is useful for (ready + cooking + idle with 1 or 2; is_dish_pickup_useful :2199-2203)
+// Computed from the pot words when a record is loaded; afterwards every pot change updates it by its known effect:
+//   ingredient into an empty pot / onto 1 ingredient / onto 2:  n_dish + 1 / nothing / n_full + 1, n_dish - 1
+//   cooking starts on 1-2 ingredients / on 3:                    n_full + 1 / n_dish + 1
+//   a ready soup is plated:                                      n_full - 1, n_dish - 1
+constexpr unsigned PS_FULL = 1u, PS_DISH = 1u << 4;
 template <class R>
 __device__ __forceinline__ unsigned pot_summary(const R &r, int n_pots) {
-    int n_full = 0, nd = 0;
+    unsigned ps = 0;
 #pragma unroll 1
     for (int k = 0; k < n_pots; k++) {
         const unsigned w = r.ldw(4 + k);
         const bool soup = (w & 7u) == OVC_O_SOUP;
         const bool idle = (w >> 8) == 0;
         const unsigned n = (w >> 3) & 3u;
-        n_full += soup && (!idle || n == 3u);
-        nd += soup && (!idle || n == 1u || n == 2u);
+        if (soup && (!idle || n == 3u)) ps += PS_FULL;
+        if (soup && (!idle || n == 1u || n == 2u)) ps += PS_DISH;
     }
-    return (n_full == n_pots ? 1u : 0u) | (n_full == 0 ? 2u : 0u) | ((unsigned)nd << 4);
+    return ps;
 }
 
-// One player's INTERACT (:1446-1577) -> the player's event code.  `ps`: pot_summary() as it was before either player
-// acted in this transition (quirk Q3).  `s` = the environment's clock: index of this transition among those it has run
-// in this launch.
+// One player's INTERACT (:1446-1577) -> the player's event code.  `ps`: pot_summary as it was before either player
+// acted in this transition (quirk Q3); pot changes go to `psn`, which becomes the next transition's snapshot.
+// `s` = the environment's clock: index of this transition among those it has run in this launch.
 template <class R>
 __device__ __forceinline__ unsigned interact_v2(const R &r, uint32_t L, uint32_t D, unsigned &me, const unsigned other_t,
-                                                unsigned &misc, const unsigned ps, const bool old_dyn, const unsigned s,
-                                                int &sparse, int &shaped, bool &pot_dirty) {
+                                                unsigned &misc, const unsigned ps, unsigned &psn, const int n_pots,
+                                                const bool old_dyn, const unsigned s, int &sparse, int &shaped) {
     const unsigned cell = lds_tbl16(D + OVC_DOFF(face) + 2u * (me & 0x3FFu));
     const unsigned terr = cell & 7u;
     unsigned held = me >> 10;
@@ -200,11 +204,12 @@ __device__ __forceinline__ unsigned interact_v2(const R &r, uint32_t L, uint32_t
         const bool drop = ctr && held != 0 && cw == 0;
         if (pick || drop) {
             const unsigned ot = (held | cw) & 7u;  // the object that changes hands
-            const bool oD = other_t == OVC_O_DISH;
-            bool u = false;
-            if (ot <= OVC_O_TOMATO) u = pick != ((ps & 1u) && !oD);  // is_ingredient_pickup_useful :2223-2237 / _drop_ :2239-2254
-            else if (ot == OVC_O_DISH)                               // is_dish_pickup_useful :2180-2204 / is_dish_drop_useful :2206-2221
-                u = pick ? ((misc & 0xFF00u) == 0 && (unsigned)oD < (ps >> 4)) : ((ps & 2u) && other_t != OVC_O_ONION);
+            const unsigned n_full = ps & 15u;
+            bool u;
+            if (ot == OVC_O_DISH)  // is_dish_pickup_useful :2180-2204 / is_dish_drop_useful :2206-2221
+                u = pick ? ((misc & 0xFF00u) == 0 && (other_t == OVC_O_DISH ? 1u : 0u) < (ps >> 4)) : (n_full == 0 && other_t != OVC_O_ONION);
+            else  // is_ingredient_pickup_useful :2223-2237 / _drop_ :2239-2254 (a soup: never)
+                u = ot <= OVC_O_TOMATO && pick != (n_full == (unsigned)n_pots && other_t != OVC_O_DISH);
             code = 2u * ot + (pick ? 0xFFFFFFFFu : 6u) + (unsigned)u;  // pickup codes 1-7, drop codes 8-14
             if (ctr) {
                 sts_tile(wa, held);  // drop: the object; pickup: 0
@@ -219,10 +224,11 @@ __device__ __forceinline__ unsigned interact_v2(const R &r, uint32_t L, uint32_t
         const uint32_t wa = r.addr(4 + (int)(cell >> 8));
         const unsigned w = lds_tile(wa);
         const unsigned k5 = (w >> 3) & 31u;
+        const unsigned n = k5 & 3u;
         if (ht == 0) {  // :1515-1522 start cooking an idle, non-empty soup (new dynamics only): tick 0 now, ready `cook` transitions on
-            if (!old_dyn && (w & ~0xF8u) == OVC_O_SOUP && (w & 0x18u) != 0) {
+            if (!old_dyn && (w & ~0xF8u) == OVC_O_SOUP && n != 0) {
                 sts_tile(wa, w | ((s + lds_tbl32(D + OVC_DOFF(cook5) + 4u * k5) + 1u) << 8));
-                pot_dirty = true;
+                psn += n == 3u ? PS_DISH : PS_FULL;
             }
         } else if (ht == OVC_O_DISH) {  // :1525-1539 plate a ready soup
             const unsigned g = w >> 8;
@@ -231,17 +237,16 @@ __device__ __forceinline__ unsigned interact_v2(const R &r, uint32_t L, uint32_t
                 held = pot_to_ext(w, D, s);   // a ready soup leaves the pot with tick == cook time (or its frozen tick)
                 sts_tile(wa, 0u);
                 shaped += (int)lds_tbl32(L + OVC_LOFF(rew_soup_pickup));
-                pot_dirty = true;
+                psn -= PS_FULL + PS_DISH;
             }
         } else if (ht <= OVC_O_TOMATO) {  // :1541-1568 add an ingredient (an empty pot gets a fresh soup first)
-            const unsigned n = k5 & 3u;
             if ((w >> 8) == 0 && n < 3u) {
                 const unsigned tom = ht == OVC_O_TOMATO;
                 code = lds_tbl8(D + OVC_DOFF(potcode5) + 2u * k5 + tom);
                 sts_tile(wa, ((w ? w : (unsigned)OVC_O_SOUP) + 8u) | (tom << (5 + n)));
                 shaped += (int)lds_tbl32(L + OVC_LOFF(rew_placement_in_pot));
                 held = 0;
-                pot_dirty = true;
+                psn += n == 0 ? PS_DISH : n == 2u ? PS_FULL - PS_DISH : 0u;
             }
         }
     } else if (terr == OVC_T_SERVE && ht == OVC_O_SOUP) {  // :1570-1577, deliver_soup :1631-1642
@@ -444,7 +449,7 @@ rollout_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
         int t;
         unsigned toff;  // environment clock = t + toff: transitions this environment has RUN in this launch (a finished,
                         // un-reset environment stands still, and so do its soups)
-        unsigned p0, p1, misc, ps;
+        unsigned p0, p1, misc, ps, psn;  // ps: pot snapshot of this transition, psn: what the next one will see
         uint32_t L, D;  // shared-window addresses of the thread's ovc_layout_t / Derived
         int n_pots;
         bool old_dyn;
@@ -459,23 +464,23 @@ rollout_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
             old_dyn = (lds_tbl32(L + OVC_LOFF(flags)) & OVC_LAYOUT_OLD_DYNAMICS) != 0;
 #pragma unroll 1
             for (int k = 0; k < n_pots; k++) r.stw(4 + k, pot_to_chip(r.ldw(4 + k), D, clk));
-            ps = pot_summary(r, n_pots);
+            ps = psn = pot_summary(r, n_pots);
         };
         load_regs(0u);
 
         RollIO<FMT> io(a, env, live_mask);
 
         // one player's interact on the live record (:1446-1577); `second`: the acting player is player 1
-        auto interact = [&](bool second, RollOut &o, bool &pot_dirty) {
+        auto interact = [&](bool second, RollOut &o) {
             unsigned pa = second ? p1 : p0;
             const unsigned pb = second ? p0 : p1;
             int sh = 0;
-            const unsigned c = interact_v2(r, L, D, pa, (pb >> 10) & 7u, misc, ps, old_dyn, (unsigned)t + toff, o.sparse, sh, pot_dirty);
+            const unsigned c = interact_v2(r, L, D, pa, (pb >> 10) & 7u, misc, ps, psn, n_pots, old_dyn, (unsigned)t + toff, o.sparse, sh);
             if (second) p1 = pa, o.sh1 = sh, o.c1 = c;
             else p0 = pa, o.sh0 = sh, o.c0 = c;
         };
         // everything of a transition after the interacts: movement, environment effects, outputs, episode end
-        auto finish = [&](int a0, int a1, const RollOut &o, bool stepped, bool pot_dirty) {
+        auto finish = [&](int a0, int a1, const RollOut &o, bool stepped) {
             int done = 1;
             if (!stepped) {
                 // ---- resolve_movement :1644-1727; a blocked or collided player still turns (quirk Q8) ----
@@ -495,11 +500,11 @@ rollout_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
                         const unsigned w = r.ldw(4 + k);
                         if ((w & ~0xE0u) == (OVC_O_SOUP | (3u << 3))) {
                             r.stw(4 + k, w | (((unsigned)t + toff + lds_tbl32(D + OVC_DOFF(cook5) + 4u * ((w >> 3) & 31u)) + 1u) << 8));
-                            pot_dirty = true;
+                            psn += PS_DISH;  // idle with 3 (full, no dish wanted) -> cooking (full, a dish will be wanted)
                         }
                     }
                 }
-                if (pot_dirty) ps = pot_summary(r, n_pots);  // next transition's snapshot
+                ps = psn;  // next transition's snapshot
                 done = a.horizon > 0 && t + 1 >= a.horizon;  // is_done overcooked_env.py:321-325
             }
             io.write(o, done, stepped, mask_s);
@@ -536,7 +541,7 @@ rollout_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
             int2 nxt = act;
             if (T > 1) nxt = io.load_action();
             int s = 0;
-            bool pending = false, pot_dirty = false;
+            bool pending = false;
             RollOut o{0, 0, 0, 0u, 0u};
             while (s < T) {
                 const int a0 = act.x, a1 = act.y;
@@ -545,14 +550,14 @@ rollout_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
                 if (!stepped) {
                     const bool i0 = a0 == OVC_A_INTERACT, i1 = a1 == OVC_A_INTERACT;
                     if (i0 || i1) {
-                        interact(pending || !i0, o, pot_dirty);
+                        interact(pending || !i0, o);
                         whole = pending || !(i0 && i1);
                         pending = !whole;
                     }
                 }
                 if (whole) {
-                    finish(a0, a1, o, stepped, pot_dirty);
-                    o = RollOut{0, 0, 0, 0u, 0u}, pot_dirty = false;
+                    finish(a0, a1, o, stepped);
+                    o = RollOut{0, 0, 0, 0u, 0u};
                     s++;
                     act = nxt;
                     if (s + 1 < T) io.next_action(), nxt = io.load_action();  // prefetch one transition ahead
@@ -574,16 +579,15 @@ rollout_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
                     }
                     stepped = false;
                 }
-                bool pot_dirty = false;
                 if (!stepped) {
                     // two emissions of the interact body: the first serves, per environment, the first interacting player,
                     // the second player 1 where BOTH interact (1 environment in 36 under a uniform policy)
                     const bool i0 = a0 == OVC_A_INTERACT, i1 = a1 == OVC_A_INTERACT;
-                    if (i0 || i1) interact(!i0, o, pot_dirty);
-                    if (i0 && i1) interact(true, o, pot_dirty);
+                    if (i0 || i1) interact(!i0, o);
+                    if (i0 && i1) interact(true, o);
                 }
                 // FMT_STREAM: ONE program point for the warp votes, so finished environments go through it as well
-                finish(a0, a1, o, FMT == FMT_STREAM && stepped, pot_dirty);
+                finish(a0, a1, o, FMT == FMT_STREAM && stepped);
             }
         }
         // ---- registers and pot clocks back into the tile in the external format ----
