@@ -12,8 +12,8 @@
 //   * NO per-transition pot work: while on chip a pot soup carries the index (among the transitions its environment runs in
 //     this launch) of the transition at which it becomes ready instead of a tick that has to be advanced (step_environment_effects :1691-1703 turns into a
 //     comparison made only when somebody holds a dish against the pot), and the aggregates of get_pot_states
-//     (:1809-1838) that the usefulness predicates consume are kept in registers and recomputed only after a
-//     transition that changed a pot; the external tick + 1 form is restored on the way out;
+//     (:1809-1838) that the usefulness predicates consume are kept in a register that every pot change updates by
+//     its known effect; the external tick + 1 form is restored on the way out;
 //   * an agent produces at most one interaction per transition, so the interact logic (resolve_interacts
 //     :1432-1579) computes the agent's 5-bit EVENT CODE (include/ovc_b200.h, OVC_F_OUT_PACKED) directly; the 25-bit
 //     event masks of the int32 format are one shared-memory table lookup of that code, and the 2-byte host-transfer
