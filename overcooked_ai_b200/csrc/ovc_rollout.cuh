@@ -45,11 +45,6 @@ constexpr int DERIVED_ZERO_CHUNKS = (1024 * 2 + 2048) / 16;  // face + move, zer
 // loaded with tick > cook time (ready; bits 8-21 keep its tick + 1).
 constexpr unsigned POT_FROZEN = 1u << 31;
 constexpr int ROLLOUT_MAX_STEPS = 1 << 22;  // clock field: n_steps + cook time + 1 < 2^23
-#ifndef OVC_ROLLOUT_LAG
-#define OVC_ROLLOUT_LAG 0
-#endif
-// Experiment, OFF: lanes on their own timelines (see rollout_kernel).  Measured 2-3x SLOWER (profiles/r2_k5_experiments.md).
-constexpr bool ROLLOUT_LAG = OVC_ROLLOUT_LAG != 0;
 
 // ---- shared memory through 32-bit window addresses ----
 // tile words change during the launch: volatile + memory clobber keeps program order
@@ -529,66 +524,30 @@ rollout_kernel(const __grid_constant__ CUtensorMap tmap, const StepArgs a) {
             }
         };
 
-        if (ROLLOUT_LAG && FMT != FMT_STREAM) {
-            // ---- EXPERIMENT (compiled out: OVC_ROLLOUT_LAG=0).  Lanes run their own timelines: an environment in which
-            //      BOTH players interact takes TWO trips of the loop for that transition (player 0, then player 1 and the
-            //      rest) instead of a second emission of the interact body that most of the warp idles through.  It removes
-            //      ~20 % of the issued instructions and MEASURED 2-3x SLOWER (65 536 envs: 0.69 ms against 0.37 ms per 400
-            //      transitions; 262 144 envs: 3.1 against 1.0 ms): once the lanes of a warp sit at different transitions,
-            //      every action load and every output store of the warp touches up to 32 sectors instead of 8 / 4, and
-            //      the sector traffic, not the instruction count, sets the pace.  Kept as the record of that measurement. ----
-            io.next_action();
+        for (int s = 0; s < T; s++) {
             int2 nxt = act;
-            if (T > 1) nxt = io.load_action();
-            int s = 0;
-            bool pending = false;
+            io.next_action();
+            if (s + 1 < T) nxt = io.load_action();  // prefetch
+            const int a0 = act.x, a1 = act.y;
+            act = nxt;
             RollOut o{0, 0, 0, 0u, 0u};
-            while (s < T) {
-                const int a0 = act.x, a1 = act.y;
-                const bool stepped = a.horizon > 0 && t >= a.horizon;  // a finished env: untouched + flagged (overcooked_env.py:255)
-                bool whole = true;
-                if (!stepped) {
-                    const bool i0 = a0 == OVC_A_INTERACT, i1 = a1 == OVC_A_INTERACT;
-                    if (i0 || i1) {
-                        interact(pending || !i0, o);
-                        whole = pending || !(i0 && i1);
-                        pending = !whole;
-                    }
+            bool stepped = a.horizon > 0 && t >= a.horizon;  // a finished env: untouched + flagged (overcooked_env.py:255)
+            if (FMT != FMT_STREAM) {  // its own exit: the common path below then carries no "stepped" selects
+                if (stepped) {
+                    io.write(o, 1, true, mask_s);
+                    continue;
                 }
-                if (whole) {
-                    finish(a0, a1, o, stepped);
-                    o = RollOut{0, 0, 0, 0u, 0u};
-                    s++;
-                    act = nxt;
-                    if (s + 1 < T) io.next_action(), nxt = io.load_action();  // prefetch one transition ahead
-                }
+                stepped = false;
             }
-        } else {
-            for (int s = 0; s < T; s++) {
-                int2 nxt = act;
-                io.next_action();
-                if (s + 1 < T) nxt = io.load_action();  // prefetch
-                const int a0 = act.x, a1 = act.y;
-                act = nxt;
-                RollOut o{0, 0, 0, 0u, 0u};
-                bool stepped = a.horizon > 0 && t >= a.horizon;  // a finished env: untouched + flagged (overcooked_env.py:255)
-                if (FMT != FMT_STREAM) {  // its own exit: the common path below then carries no "stepped" selects
-                    if (stepped) {
-                        io.write(o, 1, true, mask_s);
-                        continue;
-                    }
-                    stepped = false;
-                }
-                if (!stepped) {
-                    // two emissions of the interact body: the first serves, per environment, the first interacting player,
-                    // the second player 1 where BOTH interact (1 environment in 36 under a uniform policy)
-                    const bool i0 = a0 == OVC_A_INTERACT, i1 = a1 == OVC_A_INTERACT;
-                    if (i0 || i1) interact(!i0, o);
-                    if (i0 && i1) interact(true, o);
-                }
-                // FMT_STREAM: ONE program point for the warp votes, so finished environments go through it as well
-                finish(a0, a1, o, FMT == FMT_STREAM && stepped);
+            if (!stepped) {
+                // two emissions of the interact body: the first serves, per environment, the first interacting player,
+                // the second player 1 where BOTH interact (1 environment in 36 under a uniform policy)
+                const bool i0 = a0 == OVC_A_INTERACT, i1 = a1 == OVC_A_INTERACT;
+                if (i0 || i1) interact(!i0, o);
+                if (i0 && i1) interact(true, o);
             }
+            // FMT_STREAM: ONE program point for the warp votes, so finished environments go through it as well
+            finish(a0, a1, o, FMT == FMT_STREAM && stepped);
         }
         // ---- registers and pot clocks back into the tile in the external format ----
 #pragma unroll 1

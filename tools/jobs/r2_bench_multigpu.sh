@@ -1,3 +1,4 @@
+# Multi-GPU run (gpurun --gpus N -- bash tools/jobs/r2_bench_multigpu.sh N): the GPU tests that need >= 2 GPUs, bench.py and its reference arm under torchrun.
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q --timeout 600 -k "two_ranks or long_rollouts or sparse_event or golden_trajectories" 2>&1 | tail -15 > gpurun_out/r2_pytest_gpu_2gpu.log
 N=${1:-2}

@@ -1,3 +1,5 @@
+# The round-2 validation run on one B200 (gpurun --timeout 3000 -- bash tools/jobs/r2_validate_1gpu.sh): GPU tests, smoke, bench (both arms),
+# K5 sweep, ncu captures of K5 at four launch shapes, the bench launch list, compute-sanitizer.  Outputs under gpurun_out/.
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q --timeout 600 2>&1 | tail -8 > gpurun_out/r2_pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke.log 2>&1
