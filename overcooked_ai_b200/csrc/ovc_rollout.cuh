@@ -9,19 +9,20 @@
 //     tile: face[(orientation, pos)] -> the faced cell, move[(action, pos)] -> position after the move (floor test
 //     folded in), and the recipe tables re-keyed by the 5-bit (count, kinds) field of a soup code, so the hot loop
 //     never does direction arithmetic, terrain tests or popcounts;
-//   * NO per-transition pot work: while on chip a pot soup carries the index (among the transitions its environment runs in
-//     this launch) of the transition at which it becomes ready instead of a tick that has to be advanced (step_environment_effects :1691-1703 turns into a
-//     comparison made only when somebody holds a dish against the pot), and the aggregates of get_pot_states
-//     (:1809-1838) that the usefulness predicates consume are kept in a register that every pot change updates by
-//     its known effect; the external tick + 1 form is restored on the way out;
+//   * NO per-transition pot work: while on chip a pot soup carries the index — on its environment's own clock of
+//     transitions run in this launch — of the transition at which it becomes ready, instead of a tick that has to
+//     be advanced (step_environment_effects :1691-1703 turns into a comparison made only when somebody holds a dish
+//     against the pot), and the aggregates of get_pot_states (:1809-1838) that the usefulness predicates consume are
+//     kept in a register that every pot change updates by its known effect; the external tick + 1 form is restored
+//     on the way out;
 //   * an agent produces at most one interaction per transition, so the interact logic (resolve_interacts
 //     :1432-1579) computes the agent's 5-bit EVENT CODE (include/ovc_b200.h, OVC_F_OUT_PACKED) directly; the 25-bit
 //     event masks of the int32 format are one shared-memory table lookup of that code, and the 2-byte host-transfer
 //     word is the two codes side by side.
 //
 // One thread owns one environment; the interact body is emitted twice (first interacting player of an environment,
-// then player 1 where both interact: most warps skip the second).  Results are bit-identical to step_kernel (tests replay every fixture
-// through both).  Included by ovc_b200.cu after the PTX helpers and StepArgs.
+// then player 1 where both interact: most warps skip the second).  Results are bit-identical to step_kernel (tests
+// replay every fixture through both).  Included by ovc_b200.cu after the PTX helpers and StepArgs.
 #pragma once
 
 namespace ovc {
@@ -40,9 +41,9 @@ constexpr int DERIVED_ZERO_CHUNKS = (1024 * 2 + 2048) / 16;  // face + move, zer
 #define OVC_DOFF(field) ((uint32_t)offsetof(Derived, field))
 #define OVC_LOFF(field) ((uint32_t)offsetof(ovc_layout_t, field))
 
-// On-chip pot word: bits 0-7 as in the record (type, count, kinds); bits 8-30 "clock": 0 = idle, else 1 + the
-// index (environment clock: transitions the environment has run in this launch) of the first transition whose interacts see the soup ready; bit 31 "frozen": the soup was
-// loaded with tick > cook time (ready; bits 8-21 keep its tick + 1).
+// On-chip pot word: bits 0-7 as in the record (type, count, kinds); bits 8-30 "clock": 0 = idle, else 1 + the index
+// (environment clock: transitions the environment has run in this launch) of the first transition whose interacts
+// see the soup ready; bit 31 "frozen": the soup was loaded with tick > cook time (ready; bits 8-21 keep its tick + 1).
 constexpr unsigned POT_FROZEN = 1u << 31;
 constexpr int ROLLOUT_MAX_STEPS = 1 << 22;  // clock field: n_steps + cook time + 1 < 2^23
 
