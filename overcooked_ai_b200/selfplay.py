@@ -51,12 +51,19 @@ class DenseGridPolicy(nn.Module):
     25/26-channel convolutions far below the tensor-core peak, whereas ``[2N, 520] x [520, 500]`` is a plain library
     GEMM.  The matrices are built once by pushing the identity through each convolution (exact: same weights, same
     function, only the summation order differs), in the observation kernel's own element order ``[x][y][channel]``, so
-    K2's output is consumed as ``[2N, W*H*26]`` without any permute.  The policy stays a CONSUMER of the hot path
+    K2's output is consumed as ``[2N, W*H*26]`` without any permute.
+
+    ``pad_to``: every layer's width is rounded up to a multiple of it with zero weights and zero biases (leaky ReLU of 0
+    is 0, the next layer's extra input columns are zero too: the function is unchanged).  Widths of 500 / 150 bf16
+    elements give rows that are not 16-byte multiples, which sends the library to its Ampere-era ``align2`` mma.sync
+    kernels (measured: 160 us for the first layer at 65 536 rows, profiles/r2_selfplay.md); 512 / 160 reach the sm_100
+    kernels.  The two heads are one matrix (6 logits + 1 value, padded to 8).  The policy stays a CONSUMER of the hot path
     (library GEMMs), not part of it."""
 
-    def __init__(self, cnn, width, height):
+    def __init__(self, cnn, width, height, pad_to=1):
         super().__init__()
         self.W, self.H = width, height
+        up = lambda n: -(-n // pad_to) * pad_to
         with torch.no_grad():
             mats = []
             shape = (26, width, height)  # (channels, x, y) as the conv sees it
@@ -70,81 +77,115 @@ class DenseGridPolicy(nn.Module):
                 mats.append((out.permute(0, 2, 3, 1).reshape(n_in, wo * ho * co).t().contiguous(),   # [n_out, n_in], [x][y][c] order
                              conv.bias.view(1, 1, co).expand(wo, ho, co).reshape(-1).clone()))
                 shape = (co, wo, ho)
-            self.conv_as_linear = nn.ModuleList()
-            for m, b in mats:
-                lin = nn.Linear(m.shape[1], m.shape[0])
-                lin.weight.copy_(m), lin.bias.copy_(b)
-                self.conv_as_linear.append(lin)
             # the first dense layer consumed conv_1's NCHW flatten (c, x, y): re-order its inputs to [x][y][c]
             co, wo, ho = shape
             first = cnn.dense[0]
-            d0 = nn.Linear(first.in_features, first.out_features)
-            d0.weight.copy_(first.weight.view(-1, co, wo, ho).permute(0, 2, 3, 1).reshape(first.out_features, -1))
-            d0.bias.copy_(first.bias)
-            self.dense = nn.ModuleList([d0] + [_clone_linear(d) for d in cnn.dense[1:]])
-            self.logits, self.value = _clone_linear(cnn.logits), _clone_linear(cnn.value)
+            mats.append((first.weight.view(-1, co, wo, ho).permute(0, 2, 3, 1).reshape(first.out_features, -1), first.bias))
+            mats += [(d.weight, d.bias) for d in cnn.dense[1:]]
+            mats.append((torch.cat([cnn.logits.weight, cnn.value.weight]), torch.cat([cnn.logits.bias, cnn.value.bias])))
+            self.n_actions = cnn.logits.out_features
+            layers, n_in = [], mats[0][0].shape[1]  # the input width is K2's row: never padded
+            for m, bias in mats:
+                lin = nn.Linear(n_in, up(m.shape[0]))
+                lin.weight.zero_(), lin.bias.zero_()
+                lin.weight[:m.shape[0], :m.shape[1]].copy_(m), lin.bias[:m.shape[0]].copy_(bias)
+                layers.append(lin)
+                n_in = lin.out_features
+            self.conv_as_linear = nn.ModuleList(layers[:3])
+            self.dense = nn.ModuleList(layers[3:-1])
+            self.heads = layers[-1]
 
     def forward(self, obs_flat):
-        """obs_flat: [2N, W*H*26] in K2's element order."""
+        """obs_flat: [2N, W*H*26] in K2's element order.  Returns (logits [2N, 6], value [2N]) as views of one matrix."""
         x = obs_flat
         for lin in self.conv_as_linear:
-            x = F.leaky_relu(lin(x), 0.2)
+            x = F.leaky_relu(lin(x), 0.2, inplace=True)
         for d in self.dense:
-            x = F.leaky_relu(d(x), 0.3)
-        return self.logits(x), self.value(x).squeeze(-1)
+            x = F.leaky_relu(d(x), 0.3, inplace=True)
+        hv = self.heads(x)
+        return hv[:, :self.n_actions], hv[:, self.n_actions]
 
 
-def _clone_linear(l):
-    c = nn.Linear(l.in_features, l.out_features)
-    with torch.no_grad():
-        c.weight.copy_(l.weight), c.bias.copy_(l.bias)
-    return c
+def sample_categorical(logits, noise):
+    """One draw per row from softmax(logits) by the Gumbel-max rule: argmax_i (logit_i - log E_i) with E_i ~ Exp(1) picks i
+    with probability softmax(logits)_i — four small kernels where softmax + ``torch.multinomial`` launch about twenty
+    (profiles/r2_selfplay.md).  ``logits`` (float32) is overwritten with the perturbed scores, ``noise`` is scratch of
+    the same shape."""
+    logits.sub_(noise.exponential_().log_())
+    return torch.argmax(logits, dim=-1)
 
 
 class SelfPlayRollout(object):
     """Policy-in-the-loop rollout: both agents of every environment act from the same network."""
 
     def __init__(self, env, model=None, autocast_dtype=torch.bfloat16, use_graph=True, reward_shaping_factor=1.0,
-                 obs_dtype=None, dense=True):
-        """obs_dtype: element type K2 writes (default: bfloat16 when the policy runs under bf16 autocast — the plane
-        values are exact in bf16 and the conversion pass disappears — else float32).
-        dense: evaluate the network through ``DenseGridPolicy`` (one library GEMM per layer) instead of cuDNN convolutions."""
+                 obs_dtype=None, dense=True, sub_batches=1):
+        """obs_dtype: element type K2 writes (default: bfloat16 when the policy runs in bf16 — the plane values are exact
+        in bf16 and the conversion pass disappears — else float32).
+        dense: evaluate the network through ``DenseGridPolicy`` (one library GEMM per layer, widths padded to 16-byte rows,
+        weights held in ``autocast_dtype``: what autocast computes, without its per-call weight casts) instead of cuDNN
+        convolutions under autocast.
+        sub_batches: the policy runs over this many row blocks one after the other, so that a block's activations
+        (rows x 512 bf16) are still in L2 when the activation pass and the next layer read them."""
         assert len({(l.width, l.height) for l in env.layouts}) == 1, "one grid shape per rollout (group envs by layout)"
         self.env = env
         l = env.layouts[0]
         self.W, self.H = l.width, l.height
         dev = env.device
         self.model = (model or RllibShapedCNN(self.W, self.H)).to(dev).to(memory_format=torch.channels_last).eval()
-        self.dense_model = DenseGridPolicy(self.model, self.W, self.H).to(dev).eval() if dense else None
         self.autocast_dtype = autocast_dtype
+        self.dense_model = None
+        if dense:
+            self.dense_model = DenseGridPolicy(self.model, self.W, self.H, pad_to=16).to(dev).eval()
+            if autocast_dtype is not None:
+                self.dense_model = self.dense_model.to(autocast_dtype)
         self.factor = float(reward_shaping_factor)
         N = env.n_envs
         if obs_dtype is None:
             obs_dtype = torch.bfloat16 if autocast_dtype == torch.bfloat16 else torch.float32
+        if dense and autocast_dtype is not None:
+            assert obs_dtype == autocast_dtype, "the dense policy consumes K2's rows as they are"
         self.obs = torch.empty((N, 2, self.W, self.H, 26), dtype=obs_dtype, device=dev)
         self.actions = torch.zeros((N, 2), dtype=torch.int32, device=dev)
         self.ret_sparse = torch.zeros(N, dtype=torch.int64, device=dev)      # running episode return (sparse)
         self.ret_mixed = torch.zeros(N, dtype=torch.float32, device=dev)    # sparse + factor * shaped (rllib.py:328-329)
         self.values = torch.zeros((N, 2), dtype=torch.float32, device=dev)
+        self._noise = torch.empty((2 * N, 6), dtype=torch.float32, device=dev)
+        self._scores = torch.empty((2 * N, 6), dtype=torch.float32, device=dev)
+        self.sub_batches = int(sub_batches)
+        assert (2 * N) % self.sub_batches == 0
         self.graph = None
         self.use_graph = use_graph
+
+    def _policy(self):
+        """(scores float32 [2N, 6] = logits, values written to self.values) for the observations in self.obs."""
+        env = self.env
+        rows = 2 * env.n_envs
+        with torch.no_grad():
+            if self.dense_model is not None:
+                flat = self.obs.view(rows, self.W * self.H * 26)
+                vals = self.values.view(rows)
+                step = rows // self.sub_batches
+                for b in range(0, rows, step):
+                    logits, value = self.dense_model(flat[b:b + step])
+                    self._scores[b:b + step].copy_(logits)
+                    vals[b:b + step].copy_(value)
+            else:
+                with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
+                    x = self.obs.view(rows, self.W, self.H, 26).permute(0, 3, 1, 2)  # (2N,26,W,H), channels-last strides
+                    logits, value = self.model(x)
+                self._scores.copy_(logits)
+                self.values.view(rows).copy_(value)
+        return self._scores
 
     def _transition(self):
         env = self.env
         env.lossless_state_encoding(out=self.obs)  # K2
-        with torch.no_grad(), torch.autocast("cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
-            if self.dense_model is not None:
-                logits, value = self.dense_model(self.obs.view(2 * env.n_envs, self.W * self.H * 26))
-            else:
-                x = self.obs.view(2 * env.n_envs, self.W, self.H, 26).permute(0, 3, 1, 2)  # (2N,26,W,H), channels-last strides
-                logits, value = self.model(x)
-        probs = torch.softmax(logits.float(), dim=-1)
-        a = torch.multinomial(probs, 1).view(env.n_envs, 2)
-        self.actions.copy_(a)
-        self.values.copy_(value.float().view(env.n_envs, 2))
+        scores = self._policy()
+        self.actions.copy_(sample_categorical(scores, self._noise).view(env.n_envs, 2))
         sparse, shaped, done, events = env.step(self.actions)  # K1 (auto-reset inside)
-        self.ret_sparse += sparse
-        self.ret_mixed += sparse.float() + self.factor * shaped.sum(-1).float()
+        self.ret_sparse.add_(sparse)
+        self.ret_mixed.add_(sparse).add_(shaped[:, 0], alpha=self.factor).add_(shaped[:, 1], alpha=self.factor)
 
     def run(self, n_steps):
         """Advance every environment n_steps transitions; returns the number of env-steps done."""

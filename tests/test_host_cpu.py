@@ -505,3 +505,35 @@ def test_dense_grid_policy_is_the_same_network_as_the_cnn():
             l1, v1 = cnn(obs.permute(0, 3, 1, 2))
             l2, v2 = dense(obs.reshape(9, -1))
         assert torch.allclose(l1, l2, atol=1e-6) and torch.allclose(v1, v2, atol=1e-6)
+
+
+def test_sample_categorical_follows_the_softmax():
+    """selfplay.sample_categorical (Gumbel-max) draws index i with probability softmax(logits)_i."""
+    import torch
+
+    from overcooked_ai_b200.selfplay import sample_categorical
+
+    torch.manual_seed(1)
+    row = torch.tensor([0.0, 1.0, 2.0, -1.0, 0.5, -30.0])
+    n = 400000
+    a = sample_categorical(row.repeat(n, 1), torch.empty(n, 6))
+    freq = torch.bincount(a, minlength=6).double() / n
+    want = torch.softmax(row.double(), -1)
+    assert freq[5] == 0 and torch.all((freq - want).abs() < 4 * torch.sqrt(want * (1 - want) / n) + 1e-9), (freq, want)
+
+
+def test_dense_grid_policy_padding_keeps_the_function():
+    """Width padding (16-byte rows for the library's sm_100 GEMM kernels) adds zero weights only; merged heads."""
+    import torch
+
+    from overcooked_ai_b200.selfplay import DenseGridPolicy, RllibShapedCNN
+
+    torch.manual_seed(2)
+    cnn = RllibShapedCNN(5, 4).eval()
+    plain, padded = DenseGridPolicy(cnn, 5, 4).eval(), DenseGridPolicy(cnn, 5, 4, pad_to=16).eval()
+    assert [l.out_features for l in plain.conv_as_linear] == [500, 500, 150] and plain.heads.out_features == 7
+    assert [l.out_features for l in padded.conv_as_linear] == [512, 512, 160] and padded.heads.out_features == 16
+    obs = torch.rand(11, 520)
+    with torch.no_grad():
+        (l1, v1), (l2, v2) = plain(obs), padded(obs)
+    assert l2.shape == (11, 6) and torch.allclose(l1, l2, atol=1e-6) and torch.allclose(v1, v2, atol=1e-6)

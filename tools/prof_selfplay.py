@@ -1,0 +1,74 @@
+#!/usr/bin/env python
+"""Config 5 (policy in the loop), kernel by kernel: a few EAGER transitions of selfplay.SelfPlayRollout so that
+    ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file out.csv python tools/prof_selfplay.py
+lists every launch of one transition; without ncu it prints CUDA-event times of the stages (encode / policy / sample / step)
+and of the graph replay."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from overcooked_ai_b200.batched import BatchedOvercookedEnv  # noqa: E402
+from overcooked_ai_b200.selfplay import SelfPlayRollout  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--n", type=int, default=32768)
+ap.add_argument("--eager", type=int, default=3, help="eager transitions (what ncu lists)")
+ap.add_argument("--stages", action="store_true", help="time the stages with CUDA events")
+ap.add_argument("--dense", type=int, default=1)
+ap.add_argument("--sub-batches", type=int, default=1)
+args = ap.parse_args()
+env = BatchedOvercookedEnv(["cramped_room"], args.n, horizon=400, auto_reset=True)
+sp = SelfPlayRollout(env, use_graph=False, dense=bool(args.dense), sub_batches=args.sub_batches)
+for _ in range(args.eager):
+    sp._transition()
+torch.cuda.synchronize()
+if args.stages:
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps * 1e3  # us
+
+    N, W, H = env.n_envs, sp.W, sp.H
+    out = {"n_envs": N, "dense": bool(args.dense), "sub_batches": args.sub_batches}
+    out["encode_us"] = timed(lambda: env.lossless_state_encoding(out=sp.obs))
+    out["policy_us"] = timed(sp._policy)
+    if sp.dense_model is not None:
+        x = sp.obs.view(2 * N, W * H * 26)
+        with torch.no_grad():
+            layers = list(sp.dense_model.conv_as_linear) + list(sp.dense_model.dense) + [sp.dense_model.heads]
+            for i, lin in enumerate(layers):
+                out["layer%d_%dx%d_linear_us" % (i, lin.in_features, lin.out_features)] = timed(lambda: lin(x))
+                y = lin(x)
+                if i < len(layers) - 1:
+                    out["layer%d_lrelu_us" % i] = timed(lambda: torch.nn.functional.leaky_relu(y, 0.2, inplace=True))
+                x = y
+    from overcooked_ai_b200.selfplay import sample_categorical
+    out["sample_us"] = timed(lambda: sample_categorical(sp._scores, sp._noise))
+    out["step_us"] = timed(lambda: env.step(sp.actions))
+    sparse, shaped = env.sparse, env.shaped
+
+    def book():
+        sp.ret_sparse.add_(sparse)
+        sp.ret_mixed.add_(sparse).add_(shaped[:, 0], alpha=sp.factor).add_(shaped[:, 1], alpha=sp.factor)
+    out["bookkeeping_us"] = timed(book)
+    out["transition_eager_us"] = timed(sp._transition)
+    for sb in sorted({1, 2, 4, 8, args.sub_batches}):
+        spg = SelfPlayRollout(env, use_graph=True, dense=bool(args.dense), sub_batches=sb)
+        spg.run(4)
+        out["transition_graph_sub%d_us" % sb] = timed(lambda: spg.run(1))
+    print(json.dumps(out))
+print("done")
