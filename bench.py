@@ -512,14 +512,17 @@ def policy_leg(dev, rank, world, seed, steps, warmup, envs=0):
     S = env.state_words
     l = env.layouts[0]
     return {
-        "workload": "config5: %s, %d envs/GPU, self-play: K2 lossless encode bf16 -> policy (RllibPPOModel-shaped CNN, random init, shared; "
-                    "every convolution folded into one library GEMM, selfplay.DenseGridPolicy) -> multinomial -> K1 step, whole transition "
-                    "in one CUDA graph" % ("+".join(layouts), n_envs),
+        "workload": "config5: %s, %d envs/GPU, self-play: %s -> policy (RllibPPOModel-shaped CNN, random init, shared; "
+                    "every convolution folded into one matrix, selfplay.DenseGridPolicy; library GEMMs) -> Gumbel-max sampling -> K1 step, "
+                    "whole transition in one CUDA graph" % ("+".join(layouts), n_envs,
+                    "K7 (lossless encoding + first layer + leaky ReLU from the packed records, observation never materialised)"
+                    if sp.fused_first_layer else "K2 lossless encode bf16"),
         "what": what, "value": tot_steps / (max_ms * 1e-3), "unit": "env-steps/s", "steps": steps, "ms_per_step": max_ms / steps,
-        "dtype": "int32 env / bf16 observations / bf16-autocast policy", "gpu_launches": 2 * T * steps,
+        "dtype": "int32 env / bf16 activations / bf16 policy", "gpu_launches": 2 * T * steps,
         "env_only": {"ms_per_400_transitions": max_ms_env, "env_steps_per_s_per_gpu": n_envs * T / (max_ms_env * 1e-3),
                      "share_of_pipeline_time": max_ms_env / (max_ms / steps),
-                     "algorithmic_bytes_per_env_step": 2 * 4 * S + 32 + 4 * S + 2 * l.width * l.height * 26 * sp.obs.element_size()},
+                     "algorithmic_bytes_per_env_step": 2 * 4 * S + 32 + 4 * S + (2 * sp._act0.shape[1] * 2 if sp.fused_first_layer else
+                                                                                  2 * l.width * l.height * 26 * sp.obs.element_size())},
         "spot_check": ("ok" if not bad else "MISMATCH in " + ",".join(bad)) if ok_all == world else "MISMATCH on some rank",
         "spot_check_envs_per_rank": len(ids), "sparse_reward_sum": tot_reward,
     }

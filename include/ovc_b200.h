@@ -54,7 +54,7 @@
 extern "C" {
 #endif
 
-#define OVC_ABI_VERSION 4
+#define OVC_ABI_VERSION 5
 
 /* ---- action indices: Action.INDEX_TO_ACTION, actions.py:47-57 ---- */
 #define OVC_A_NORTH 0
@@ -398,6 +398,41 @@ int ovc_reset(const void *layouts, int n_layouts, const int32_t *start_records, 
 int ovc_encode_lossless(const void *layouts, int n_layouts, const int32_t *state, const int32_t *view_swap,
                         void *out, int dtype, int64_t n_envs, int state_words, int width, int height,
                         int horizon, void *stream);
+
+/*
+ * The first layer of a policy on lossless_state_encoding, evaluated from the packed record WITHOUT materialising the
+ * observation (what the reference's rollout workers do per transition: lossless_state_encoding :2385-2561 feeding the
+ * first convolution of the PPO model, human_aware_rl/ppo/ppo_rllib.py:43-79 — any first layer that is linear in the
+ * observation, a 'same' convolution included, is one matrix over the flattened observation):
+ *   out[2 env + view][:] = leaky_relu(W . obs[env][view].flatten() + bias, neg_slope)       bfloat16 [2 n_envs][n_out]
+ *   wt    bfloat16 [width*height*26][n_out]: W TRANSPOSED, row index = the observation's element order
+ *         (x*height + y)*26 + plane, 16-byte aligned;   bias  float32 [n_out];   n_out a multiple of 64;
+ *   neg_slope in [0, 1] (0: ReLU, 1: no activation);   accumulation in float32;   view_swap / horizon as above.
+ * The encoding is sparse (a few player / object entries per view; terrain planes are layout constants), so the kernel
+ * gathers ~10 rows of `wt` per environment from shared memory instead of multiplying by width*height*26 inputs.
+ * At most 8 layouts per call (one grid shape); OVC_E_UNSUPPORTED if the table of a grid does not fit shared memory.
+ */
+int ovc_encode_linear(const void *layouts, int n_layouts, const int32_t *state, const int32_t *view_swap,
+                      const void *wt, const float *bias, void *out, int64_t n_envs, int state_words, int width,
+                      int height, int horizon, int n_out, float neg_slope, void *stream);
+
+/*
+ * The two ends of a policy-in-the-loop transition around ovc_step (the reference's rollout worker samples the joint
+ * action from the policy's action distribution and mixes the rewards, human_aware_rl/rllib/rllib.py:302-342):
+ *
+ * ovc_sample_actions: actions[r] ~ softmax(scores[r][0..n_actions)) for r in [0, n_rows) by the Gumbel-max rule,
+ *   argmax_i (scores[r][i] - log(-log u_i)), u_i = ((draw_i >> 9) + 0.5) / 2^23 with draw_i word i of Philox4x32-10,
+ *   key = seed, counter = (r low, r high, step low, 2 * step high + i / 4).  scores float32 [n_rows][ld], n_actions <= 8.
+ *   `counter` is DEVICE memory uint64[2]: [0] = step (advanced by one per launch by the last CTA to finish, so a
+ *   captured CUDA graph draws fresh numbers at every replay), [1] = scratch that must start at 0.  With rows ordered
+ *   [env][agent] `actions` is the int32[n_envs][2] that ovc_step takes.
+ * ovc_accumulate_returns: ret_sparse[e] += sparse[e] (int64);  ret_mixed[e] += sparse[e] + factor * shaped[e][0] +
+ *   factor * shaped[e][1] (float32; rllib.py:328-329) from ovc_step's int32 outputs; either accumulator may be NULL.
+ */
+int ovc_sample_actions(const float *scores, int ld, int n_actions, int64_t n_rows, uint64_t seed, uint64_t *counter,
+                       int32_t *actions, void *stream);
+int ovc_accumulate_returns(const int32_t *sparse, const int32_t *shaped, float factor, int64_t n_envs, int64_t *ret_sparse,
+                           float *ret_mixed, void *stream);
 
 /*
  * featurize_state (:2579-2898) with the default planner parameters (NO_COUNTERS_PARAMS,

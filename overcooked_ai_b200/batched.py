@@ -390,6 +390,50 @@ class BatchedOvercookedEnv(object):
             outs.append(o)
         return outs[0] if len(shapes) == 1 else outs
 
+    def encoded_linear(self, wt, bias, out=None, neg_slope=0.2, view_swap=None):
+        """First policy layer on ``lossless_state_encoding`` without the observation tensor (kernel K7, ovc_encode_linear):
+        ``out[2 env + view] = leaky_relu(obs[env, view].flatten() @ wt + bias, neg_slope)`` as bfloat16 ``[2N, n_out]``.
+        ``wt``: bfloat16 CUDA tensor ``[W*H*26, n_out]`` (the layer's matrix TRANSPOSED, rows in the observation's own
+        element order ``[x][y][plane]`` — for a convolution, the matrix ``selfplay.DenseGridPolicy`` builds), ``bias``
+        float32 ``[n_out]``, ``n_out`` a multiple of 64.  All environments must share one grid shape."""
+        assert len({(l.width, l.height) for l in self.layouts}) == 1, "one grid shape per call (group envs by layout)"
+        W, H = self.layouts[0].width, self.layouts[0].height
+        assert wt.is_cuda and wt.dtype == torch.bfloat16 and wt.is_contiguous() and wt.shape[0] == W * H * 26, wt.shape
+        n_out = wt.shape[1]
+        assert bias.is_cuda and bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == n_out
+        if view_swap is not None:
+            assert view_swap.dtype == torch.int32 and view_swap.is_cuda and view_swap.is_contiguous() and view_swap.numel() == self.n_envs
+        if out is None:
+            out = torch.empty((2 * self.n_envs, n_out), dtype=torch.bfloat16, device=self.device)
+        assert out.is_cuda and out.dtype == torch.bfloat16 and out.is_contiguous() and out.numel() == 2 * self.n_envs * n_out
+        _native.check(self._lib.ovc_encode_linear(
+            self.tables.data_ptr(), self.n_layouts, self.state.data_ptr(), 0 if view_swap is None else view_swap.data_ptr(),
+            wt.data_ptr(), bias.data_ptr(), out.data_ptr(), self.n_envs, self.state_words, W, H,
+            self.horizon if self.horizon > 0 else 2**31 - 1, n_out, float(neg_slope), self._stream()))
+        return out
+
+    def sample_actions(self, scores, counter, seed=0, out=None):
+        """Joint actions drawn from the policy's logits (ovc_sample_actions: Gumbel-max on Philox draws, one kernel).
+        ``scores`` float32 ``[2N, ld]`` (rows ordered [env][agent], the first 6 columns are the logits), ``counter`` an
+        int64 CUDA tensor of 2 zeros that the kernel advances (one step per call; graph-replay safe).  Returns int32 [N, 2]."""
+        assert scores.is_cuda and scores.dtype == torch.float32 and scores.dim() == 2 and scores.stride(1) == 1 and scores.shape[0] == 2 * self.n_envs
+        assert counter.is_cuda and counter.dtype == torch.int64 and counter.numel() == 2 and counter.is_contiguous()
+        if out is None:
+            out = torch.empty((self.n_envs, 2), dtype=torch.int32, device=self.device)
+        assert out.is_cuda and out.dtype == torch.int32 and out.is_contiguous() and out.numel() == 2 * self.n_envs
+        _native.check(self._lib.ovc_sample_actions(scores.data_ptr(), scores.stride(0), 6, 2 * self.n_envs, int(seed) & (2**64 - 1),
+                                                   counter.data_ptr(), out.data_ptr(), self._stream()))
+        return out
+
+    def accumulate_returns(self, ret_sparse, ret_mixed, factor=1.0):
+        """``ret_sparse += sparse`` (int64 [N]) and ``ret_mixed += sparse + factor * (shaped[:, 0] + shaped[:, 1])`` (float32 [N])
+        from the last ``step``'s outputs, in one kernel (ovc_accumulate_returns; rllib.py:328-329)."""
+        for t, dt in ((ret_sparse, torch.int64), (ret_mixed, torch.float32)):
+            assert t is None or (t.is_cuda and t.dtype == dt and t.is_contiguous() and t.numel() == self.n_envs)
+        _native.check(self._lib.ovc_accumulate_returns(self.sparse.data_ptr(), self.shaped.data_ptr(), float(factor), self.n_envs,
+                                                       0 if ret_sparse is None else ret_sparse.data_ptr(),
+                                                       0 if ret_mixed is None else ret_mixed.data_ptr(), self._stream()))
+
     def feature_lut(self):
         if self._lut is None:
             lut = np.stack([l.feature_lut() for l in self.layouts]).view(np.uint8).reshape(self.n_layouts, -1)

@@ -9,7 +9,8 @@
 //     IO = 3  no staging: each thread reads / writes its record's chunks in global memory.
 // K5  rollout_kernel<S, IO>  T transitions with the tile resident in shared memory.
 // K4  reset_kernel           masked copy of the per-layout start record.
-// The observation kernels (K2 lossless encode, K3 featurize) live in ovc_obs.cuh.
+// The observation kernels (K2 lossless encode, K3 featurize) live in ovc_obs.cuh, K7 (first policy layer on the
+// encoding, evaluated from the record) in ovc_encfc.cuh.
 //
 // The path is integer, branchy and HBM-bound (no contraction anywhere): no tensor cores.
 #include <cuda.h>
@@ -599,6 +600,7 @@ static int step_impl(const void *layouts, int n_layouts, const int32_t *start_re
 }  // namespace ovc
 
 #include "ovc_obs.cuh"
+#include "ovc_encfc.cuh"
 #include "ovc_potential.cuh"
 #include "ovc_host.cuh"
 
@@ -655,6 +657,25 @@ int ovc_encode_lossless(const void *layouts, int n_layouts, const int32_t *state
     if (rc) return rc;
     return ovc::encode_lossless_impl((const ovc_layout_t *)layouts, state, view_swap, out, dtype, n_envs, state_words,
                                      width, height, horizon, (cudaStream_t)stream);
+}
+
+int ovc_encode_linear(const void *layouts, int n_layouts, const int32_t *state, const int32_t *view_swap, const void *wt,
+                      const float *bias, void *out, int64_t n_envs, int state_words, int width, int height, int horizon,
+                      int n_out, float neg_slope, void *stream) {
+    int rc = ovc::check_common(layouts, n_layouts, state, n_envs, state_words);
+    if (rc) return rc;
+    return ovc::encode_linear_impl((const ovc_layout_t *)layouts, n_layouts, state, view_swap, wt, bias, out, n_envs,
+                                   state_words, width, height, horizon, n_out, neg_slope, (cudaStream_t)stream);
+}
+
+int ovc_sample_actions(const float *scores, int ld, int n_actions, int64_t n_rows, uint64_t seed, uint64_t *counter,
+                       int32_t *actions, void *stream) {
+    return ovc::sample_actions_impl(scores, ld, n_actions, n_rows, seed, (unsigned long long *)counter, actions, (cudaStream_t)stream);
+}
+
+int ovc_accumulate_returns(const int32_t *sparse, const int32_t *shaped, float factor, int64_t n_envs, int64_t *ret_sparse,
+                           float *ret_mixed, void *stream) {
+    return ovc::accumulate_returns_impl(sparse, shaped, factor, n_envs, (long long *)ret_sparse, ret_mixed, (cudaStream_t)stream);
 }
 
 int ovc_featurize(const void *layouts, int n_layouts, const void *lut, const int32_t *state,

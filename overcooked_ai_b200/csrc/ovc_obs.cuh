@@ -184,9 +184,15 @@ static int encode_lossless_impl(const ovc_layout_t *layouts, const int32_t *stat
         buf_kb = env ? atoi(env) : 24;
         if (buf_kb < 4 || buf_kb > 200) buf_kb = 24;
     }
+    static int e_override = -1;
+    if (e_override < 0) {
+        const char *env = getenv("OVC_ENC_E");  // experiments: environments per tile, overrides the byte budget
+        e_override = env ? atoi(env) : 0;
+    }
     const int BUF = buf_kb * 1024;
     const int mult = 16 / gcd_int(16, obs_bytes);    // tiles must start 16-byte aligned in the output
-    int E = BUF / obs_bytes;
+    int E = e_override > 0 ? e_override : BUF / obs_bytes;
+    if ((size_t)E * obs_bytes > 200 * 1024) E = 200 * 1024 / obs_bytes;
     E -= E % mult;
     if (E < mult) E = mult;
     a.E = E;

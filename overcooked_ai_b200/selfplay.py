@@ -4,8 +4,11 @@ The reference collects PPO rollouts with Ray workers that each run one Python en
 the policy (human_aware_rl/rllib/rllib.py:293-342, ppo/ppo_rllib.py:7-80).  Here one process per GPU
 keeps N environments on the device and runs, per transition,
 
-    lossless_state_encoding (K2, fp32 [N,2,W,H,26])  ->  policy CNN (torch)  ->  multinomial
+    lossless_state_encoding (K2, [N,2,W,H,26])  ->  policy CNN (torch)  ->  sampling
     ->  ovc_step (K1)  ->  reward accumulation
+
+or, with the dense bf16 policy, K7 in place of K2 + the first layer: encoding, first layer and its leaky ReLU evaluated
+from the packed records (``ovc_encode_linear``), the observation tensor never written
 
 with no host round trip; the whole transition can be captured in one CUDA graph.  The observation
 tensor is consumed zero-copy: ``[N,2,W,H,26]`` viewed as ``(2N, 26, W, H)`` is exactly torch's
@@ -97,8 +100,18 @@ class DenseGridPolicy(nn.Module):
 
     def forward(self, obs_flat):
         """obs_flat: [2N, W*H*26] in K2's element order.  Returns (logits [2N, 6], value [2N]) as views of one matrix."""
-        x = obs_flat
-        for lin in self.conv_as_linear:
+        return self.forward_from(obs_flat, 0)
+
+    def first_layer_table(self):
+        """(wt bfloat16 [W*H*26, n_out], bias float32 [n_out]) of the first layer in the form ``ovc_encode_linear`` (K7)
+        takes: the matrix transposed, rows in the observation's element order."""
+        lin = self.conv_as_linear[0]
+        return lin.weight.detach().t().contiguous().to(torch.bfloat16), lin.bias.detach().float().contiguous()
+
+    def forward_from(self, x, first):
+        """The layers from index ``first`` on (0: the whole network from the observation; 1: from the first layer's
+        activations, e.g. K7's output)."""
+        for lin in self.conv_as_linear[first:]:
             x = F.leaky_relu(lin(x), 0.2, inplace=True)
         for d in self.dense:
             x = F.leaky_relu(d(x), 0.3, inplace=True)
@@ -119,14 +132,20 @@ class SelfPlayRollout(object):
     """Policy-in-the-loop rollout: both agents of every environment act from the same network."""
 
     def __init__(self, env, model=None, autocast_dtype=torch.bfloat16, use_graph=True, reward_shaping_factor=1.0,
-                 obs_dtype=None, dense=True, sub_batches=1):
+                 obs_dtype=None, dense=True, sub_batches=1, fused_first_layer=None, native_glue=True, seed=0):
         """obs_dtype: element type K2 writes (default: bfloat16 when the policy runs in bf16 — the plane values are exact
         in bf16 and the conversion pass disappears — else float32).
         dense: evaluate the network through ``DenseGridPolicy`` (one library GEMM per layer, widths padded to 16-byte rows,
         weights held in ``autocast_dtype``: what autocast computes, without its per-call weight casts) instead of cuDNN
         convolutions under autocast.
         sub_batches: the policy runs over this many row blocks one after the other, so that a block's activations
-        (rows x 512 bf16) are still in L2 when the activation pass and the next layer read them."""
+        (rows x 512 bf16) are still in L2 when the activation pass and the next layer read them.
+        fused_first_layer (default: on for the dense bf16 policy): the observation is never materialised — kernel K7
+        (``env.encoded_linear``) evaluates encoding + first layer + leaky ReLU from the packed records, and the library
+        GEMMs start at the second layer.
+        native_glue: the joint action is drawn by ``ovc_sample_actions`` (Gumbel-max on Philox draws keyed by ``seed``,
+        one kernel) and the rewards are folded into the returns by ``ovc_accumulate_returns`` (one kernel) instead of five
+        and four tensor-library kernels."""
         assert len({(l.width, l.height) for l in env.layouts}) == 1, "one grid shape per rollout (group envs by layout)"
         self.env = env
         l = env.layouts[0]
@@ -139,17 +158,27 @@ class SelfPlayRollout(object):
             self.dense_model = DenseGridPolicy(self.model, self.W, self.H, pad_to=16).to(dev).eval()
             if autocast_dtype is not None:
                 self.dense_model = self.dense_model.to(autocast_dtype)
+        if fused_first_layer is None:
+            fused_first_layer = dense and autocast_dtype == torch.bfloat16
+        assert not fused_first_layer or (dense and autocast_dtype == torch.bfloat16), "K7 feeds the dense bf16 policy"
+        self.fused_first_layer = bool(fused_first_layer)
         self.factor = float(reward_shaping_factor)
         N = env.n_envs
         if obs_dtype is None:
             obs_dtype = torch.bfloat16 if autocast_dtype == torch.bfloat16 else torch.float32
         if dense and autocast_dtype is not None:
             assert obs_dtype == autocast_dtype, "the dense policy consumes K2's rows as they are"
-        self.obs = torch.empty((N, 2, self.W, self.H, 26), dtype=obs_dtype, device=dev)
+        self.obs = None if self.fused_first_layer else torch.empty((N, 2, self.W, self.H, 26), dtype=obs_dtype, device=dev)
+        if self.fused_first_layer:
+            self._wt0, self._b0 = self.dense_model.first_layer_table()
+            self._act0 = torch.empty((2 * N, self._wt0.shape[1]), dtype=torch.bfloat16, device=dev)
         self.actions = torch.zeros((N, 2), dtype=torch.int32, device=dev)
         self.ret_sparse = torch.zeros(N, dtype=torch.int64, device=dev)      # running episode return (sparse)
         self.ret_mixed = torch.zeros(N, dtype=torch.float32, device=dev)    # sparse + factor * shaped (rllib.py:328-329)
         self.values = torch.zeros((N, 2), dtype=torch.float32, device=dev)
+        self.native_glue = bool(native_glue)
+        self.seed = int(seed)
+        self._draw_counter = torch.zeros(2, dtype=torch.int64, device=dev)  # [step, scratch] of ovc_sample_actions
         self._noise = torch.empty((2 * N, 6), dtype=torch.float32, device=dev)
         self._scores = torch.empty((2 * N, 6), dtype=torch.float32, device=dev)
         self.sub_batches = int(sub_batches)
@@ -163,11 +192,14 @@ class SelfPlayRollout(object):
         rows = 2 * env.n_envs
         with torch.no_grad():
             if self.dense_model is not None:
-                flat = self.obs.view(rows, self.W * self.H * 26)
+                if self.fused_first_layer:
+                    flat, first = env.encoded_linear(self._wt0, self._b0, out=self._act0, neg_slope=0.2), 1  # K7
+                else:
+                    flat, first = self.obs.view(rows, self.W * self.H * 26), 0
                 vals = self.values.view(rows)
                 step = rows // self.sub_batches
                 for b in range(0, rows, step):
-                    logits, value = self.dense_model(flat[b:b + step])
+                    logits, value = self.dense_model.forward_from(flat[b:b + step], first)
                     self._scores[b:b + step].copy_(logits)
                     vals[b:b + step].copy_(value)
             else:
@@ -180,8 +212,14 @@ class SelfPlayRollout(object):
 
     def _transition(self):
         env = self.env
-        env.lossless_state_encoding(out=self.obs)  # K2
+        if not self.fused_first_layer:
+            env.lossless_state_encoding(out=self.obs)  # K2
         scores = self._policy()
+        if self.native_glue:
+            env.sample_actions(scores, self._draw_counter, seed=self.seed, out=self.actions)
+            env.step(self.actions)  # K1 (auto-reset inside)
+            env.accumulate_returns(self.ret_sparse, self.ret_mixed, self.factor)
+            return
         self.actions.copy_(sample_categorical(scores, self._noise).view(env.n_envs, 2))
         sparse, shaped, done, events = env.step(self.actions)  # K1 (auto-reset inside)
         self.ret_sparse.add_(sparse)
@@ -191,7 +229,7 @@ class SelfPlayRollout(object):
         """Advance every environment n_steps transitions; returns the number of env-steps done."""
         if self.use_graph and self.graph is None:
             # warm-up + capture must not advance the environments: snapshot, then restore
-            saved = (self.env.state.clone(), self.ret_sparse.clone(), self.ret_mixed.clone())
+            saved = (self.env.state.clone(), self.ret_sparse.clone(), self.ret_mixed.clone(), self._draw_counter.clone())
             s = torch.cuda.Stream(self.env.device)
             s.wait_stream(torch.cuda.current_stream(self.env.device))
             with torch.cuda.stream(s):
@@ -201,7 +239,7 @@ class SelfPlayRollout(object):
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self._transition()
-            self.env.state.copy_(saved[0]), self.ret_sparse.copy_(saved[1]), self.ret_mixed.copy_(saved[2])
+            self.env.state.copy_(saved[0]), self.ret_sparse.copy_(saved[1]), self.ret_mixed.copy_(saved[2]), self._draw_counter.copy_(saved[3])
         for _ in range(n_steps):
             if self.graph is not None:
                 self.graph.replay()
@@ -213,6 +251,9 @@ class SelfPlayRollout(object):
         """The same transitions without the policy: encode + step with the last sampled actions
         (used to report the env-only share of the pipeline)."""
         for _ in range(n_steps):
-            self.env.lossless_state_encoding(out=self.obs)
+            if self.fused_first_layer:
+                self.env.encoded_linear(self._wt0, self._b0, out=self._act0, neg_slope=0.2)
+            else:
+                self.env.lossless_state_encoding(out=self.obs)
             self.env.step(self.actions)
         return n_steps * self.env.n_envs

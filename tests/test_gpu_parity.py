@@ -337,6 +337,150 @@ def test_selfplay_policy_rollout_matches_oracle_replay():
     assert sp2.run(30) == 30 * n and (_np(env2.state)[:, 0] == 30 % 20).all()
 
 
+def _k7_reference(obs, wt, bias, slope):
+    """float64 restatement of ovc_encode_linear on a materialised observation: leaky_relu(obs @ wt + bias)."""
+    z = obs.reshape(obs.shape[0] * 2, -1).astype(np.float64) @ wt.astype(np.float64) + bias.astype(np.float64)
+    return np.where(z > 0, z, z * slope)
+
+
+def _k7_close(got, want):
+    # bf16 output (8 significant bits, round to nearest) of a float32 accumulation
+    return np.abs(got - want) <= np.abs(want) * 2.0 ** -8 + 1e-4
+
+
+@pytest.mark.parametrize("path", TRACE_FILES, ids=TRACE_IDS)
+def test_k7_encode_linear_vs_reference_encoding(path):
+    """K7 (first layer evaluated from the packed record) against W . (the REFERENCE's lossless_state_encoding, from the
+    fixtures) on every layout's trace states: held soups, idle / cooking / ready pots, objects on counters."""
+    tr = Trace(path)
+    d = tr.data
+    st = d["obs_states"]
+    W, H = tr.layout.width, tr.layout.height
+    env = _env_for_trace(tr, len(st), 0, horizon=400)
+    env.state.copy_(torch.from_numpy(st))
+    rng = np.random.RandomState(W * 31 + H)
+    for n_out, slope in ((64, 0.2), (256, 0.0), (512, 0.2)):
+        wt = torch.from_numpy(rng.uniform(-0.05, 0.05, size=(W * H * 26, n_out)).astype(np.float32)).cuda().to(torch.bfloat16)
+        bias = torch.from_numpy(rng.uniform(-0.1, 0.1, size=n_out).astype(np.float32)).cuda()
+        if W * H * 19 * 64 * 2 > 226 * 1024:  # the table of this grid does not fit shared memory: refused, not wrong
+            with pytest.raises(RuntimeError, match="shared memory"):
+                env.encoded_linear(wt, bias, neg_slope=slope)
+            continue
+        got = _np(env.encoded_linear(wt, bias, neg_slope=slope).float())
+        want = _k7_reference(d["obs_lossless"], _np(wt.float()), _np(bias), slope)
+        assert got.shape == want.shape and _k7_close(got, want).all(), (n_out, np.abs(got - want).max())
+
+
+def test_k7_encode_linear_views_urgency_layout_mix_and_ragged_sizes():
+    """view_swap, the urgency plane (horizon - t < 40), two layouts of one grid shape in one call, batch sizes that are not
+    multiples of a warp / the CTA's warps: K7 == W . K2 (K2 itself is tested against the reference's encoding)."""
+    rng = np.random.RandomState(5)
+    for layouts, n, horizon in ((["cramped_room", "cramped_room_tomato"], 2 * 333 + 1, 60), (["asymmetric_advantages"], 1027, 60),
+                                (["cramped_room"], 1, 400)):
+        env = BatchedOvercookedEnv(layouts, n, horizon=horizon, auto_reset=True)
+        env.rollout(torch.from_numpy(_random_actions(rng, 30, n, 0.5)).cuda())
+        env.reset(torch.from_numpy((rng.rand(n) < 0.5).astype(np.int32)).cuda())  # half of them start over: timesteps 15 and 45
+        env.rollout(torch.from_numpy(_random_actions(rng, 15, n, 0.5)).cuda())
+        W, H = env.layouts[0].width, env.layouts[0].height
+        wt = torch.from_numpy(rng.uniform(-0.05, 0.05, size=(W * H * 26, 128)).astype(np.float32)).cuda().to(torch.bfloat16)
+        bias = torch.from_numpy(rng.uniform(-0.1, 0.1, size=128).astype(np.float32)).cuda()
+        swap = torch.from_numpy((rng.rand(n) < 0.5).astype(np.int32)).cuda()
+        for vs in (None, swap):
+            obs = _np(env.lossless_state_encoding(dtype=torch.float32, view_swap=vs))
+            assert n == 1 or (obs[..., 25].any() and not obs[..., 25].all())  # some environments are in their last 40 steps
+            got = _np(env.encoded_linear(wt, bias, neg_slope=0.3, view_swap=vs).float())
+            want = _k7_reference(obs, _np(wt.float()), _np(bias), 0.3)
+            assert _k7_close(got, want).all(), np.abs(got - want).max()
+    lib = _native.lib()
+    rc = lib.ovc_encode_linear(env.tables.data_ptr(), 1, env.state.data_ptr(), 0, wt.data_ptr(), bias.data_ptr(), wt.data_ptr(), 1, 16, 5, 4,
+                               400, 100, 0.2, 0)
+    assert rc == -1 and b"multiple of 64" in lib.ovc_last_error()
+
+
+def test_selfplay_fused_first_layer_equals_unfused_policy():
+    """Config 5 with K7 in front of the dense policy == the same policy on K2's observation tensor (same weights; bf16
+    activations, so logits agree to bf16 accuracy), and the environments follow the oracle on the sampled actions."""
+    from overcooked_ai_b200.selfplay import SelfPlayRollout
+
+    n = 777
+    torch.manual_seed(3)
+    env = BatchedOvercookedEnv("cramped_room", n, horizon=30, auto_reset=True)
+    rng = np.random.RandomState(9)
+    env.rollout(torch.from_numpy(_random_actions(rng, 17, n, 0.5)).cuda())
+    fused = SelfPlayRollout(env, use_graph=False)
+    assert fused.fused_first_layer and fused.obs is None
+    plain = SelfPlayRollout(env, model=fused.model, use_graph=False, fused_first_layer=False)
+    env.lossless_state_encoding(out=plain.obs)
+    a, b = _np(fused._policy().clone()), _np(plain._policy().clone())
+    assert np.abs(a - b).max() < 0.02 and np.abs(a).max() > 0.01, np.abs(a - b).max()
+    ref_state = _np(env.state).copy()
+    for t in range(20):
+        fused.run(1)
+        cpu.step(env._tab_host, env._starts_host, ref_state, _np(fused.actions), horizon=30, flags=1)
+        assert np.array_equal(_np(env.state), ref_state), t
+    g = SelfPlayRollout(env, model=fused.model, use_graph=True)
+    assert g.run(12) == 12 * n
+
+
+def _philox4x32_10(key, c):
+    """numpy restatement of Philox4x32-10 (Salmon et al.): key uint64, c uint32[n, 4] -> uint32[n, 4]."""
+    c = [c[:, i].astype(np.uint64) for i in range(4)]
+    k0, k1 = np.uint64(key & 0xFFFFFFFF), np.uint64(key >> 32)
+    M = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = np.uint64(0xD2511F53) * c[0], np.uint64(0xCD9E8D57) * c[2]
+        c = [(p1 >> np.uint64(32)) ^ c[1] ^ k0, p1 & M, (p0 >> np.uint64(32)) ^ c[3] ^ k1, p0 & M]
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & M, (k1 + np.uint64(0xBB67AE85)) & M
+    return np.stack(c, 1).astype(np.uint32)
+
+
+def test_sample_actions_kernel_matches_its_definition_and_softmax():
+    """ovc_sample_actions: the draw is the documented function of (seed, step, row) — numpy restatement of the Philox
+    counter plan and the Gumbel-max rule; the step advances by one per launch; frequencies follow softmax(logits)."""
+    n = 40000
+    env = BatchedOvercookedEnv("cramped_room", n, horizon=400)
+    rng = np.random.RandomState(2)
+    scores = torch.from_numpy(rng.normal(size=(2 * n, 8)).astype(np.float32)).cuda()
+    counter = torch.zeros(2, dtype=torch.int64, device="cuda")
+    seed = 0x1234567890ABCDEF
+    rows = np.arange(2 * n, dtype=np.uint64)
+    freq = np.zeros(6)
+    for step in range(3):
+        a = _np(env.sample_actions(scores, counter, seed=seed)).reshape(-1)
+        assert _np(counter).tolist() == [step + 1, 0]
+        ctr = np.stack([rows & np.uint64(0xFFFFFFFF), rows >> np.uint64(32), np.full_like(rows, step), np.zeros_like(rows)], 1).astype(np.uint32)
+        d = np.concatenate([_philox4x32_10(seed, ctr), _philox4x32_10(seed, ctr | np.array([0, 0, 0, 1], np.uint32))], 1)[:, :6]
+        u = ((d >> np.uint32(9)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -23)
+        v = _np(scores)[:, :6] - np.log(-np.log(u))
+        want = v.argmax(1)
+        top2 = np.sort(v, 1)[:, -2:]
+        clear = top2[:, 1] - top2[:, 0] > 1e-4  # libm and the device logf differ in the last bits: near-ties may flip
+        assert clear.mean() > 0.999 and np.array_equal(a[clear], want[clear])
+        assert a.min() >= 0 and a.max() <= 5
+        freq += np.bincount(a, minlength=6)
+    # one fixed logit row for everybody: empirical frequencies == softmax within sampling error
+    scores[:] = torch.tensor([0.5, -1.0, 2.0, 0.0, 1.0, -0.5, 99.0, 99.0], device="cuda")
+    a = np.concatenate([_np(env.sample_actions(scores, counter, seed=7)).reshape(-1) for _ in range(5)])
+    p = np.exp([0.5, -1.0, 2.0, 0.0, 1.0, -0.5])
+    p /= p.sum()
+    f = np.bincount(a, minlength=6) / a.size
+    assert np.abs(f - p).max() < 4 * np.sqrt(0.25 / a.size), (f, p)
+
+
+def test_accumulate_returns_kernel():
+    n = 3001
+    env = BatchedOvercookedEnv("cramped_room", n, horizon=400, auto_reset=True)
+    rng = np.random.RandomState(4)
+    rs, rm = torch.zeros(n, dtype=torch.int64, device="cuda"), torch.zeros(n, dtype=torch.float32, device="cuda")
+    ws, wm = np.zeros(n, np.int64), np.zeros(n, np.float64)
+    for t in range(120):
+        sp, sh, dn, ev = env.step(torch.from_numpy(_random_actions(rng, 1, n, 0.6)[0]).cuda())
+        env.accumulate_returns(rs, rm, 0.75)
+        ws += _np(sp)
+        wm += _np(sp) + 0.75 * _np(sh).sum(1)
+    assert ws.sum() >= 0 and wm.max() > 0 and np.array_equal(_np(rs), ws) and np.allclose(_np(rm), wm, rtol=1e-6, atol=1e-4)
+
+
 @pytest.mark.parametrize("gamma_idx,gamma", [(0, 0.99), (1, 0.9)])
 def test_potential_kernel_bit_exact_vs_reference(gamma_idx, gamma):
     """K6: phi(s) equals the reference's potential_function float for float (fixture from the reference)."""

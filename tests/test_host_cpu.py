@@ -26,7 +26,7 @@ def test_native_library_loads_and_exports_every_declared_symbol():
     lib = _native.lib()
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.ovc_abi_version() == _native.ABI_VERSION == 4
+    assert lib.ovc_abi_version() == _native.ABI_VERSION == 5
     assert lib.ovc_layout_table_size() == L.LAYOUT_DTYPE.itemsize == 1024
     assert lib.ovc_feat_lut_entry_size() == L.FEAT_LUT_DTYPE.itemsize == 12
 

@@ -20,9 +20,11 @@ ap.add_argument("--eager", type=int, default=3, help="eager transitions (what nc
 ap.add_argument("--stages", action="store_true", help="time the stages with CUDA events")
 ap.add_argument("--dense", type=int, default=1)
 ap.add_argument("--sub-batches", type=int, default=1)
+ap.add_argument("--glue", type=int, default=1, help="ovc_sample_actions / ovc_accumulate_returns instead of tensor-library ops")
+ap.add_argument("--fused", type=int, default=1, help="K7 (encoding + first layer from the record) instead of K2 + first GEMM")
 args = ap.parse_args()
 env = BatchedOvercookedEnv(["cramped_room"], args.n, horizon=400, auto_reset=True)
-sp = SelfPlayRollout(env, use_graph=False, dense=bool(args.dense), sub_batches=args.sub_batches)
+sp = SelfPlayRollout(env, use_graph=False, dense=bool(args.dense), sub_batches=args.sub_batches, fused_first_layer=bool(args.fused and args.dense), native_glue=bool(args.glue))
 for _ in range(args.eager):
     sp._transition()
 torch.cuda.synchronize()
@@ -44,10 +46,16 @@ if args.stages:
 
     N, W, H = env.n_envs, sp.W, sp.H
     out = {"n_envs": N, "dense": bool(args.dense), "sub_batches": args.sub_batches}
-    out["encode_us"] = timed(lambda: env.lossless_state_encoding(out=sp.obs))
+    obs = sp.obs if sp.obs is not None else torch.empty((N, 2, W, H, 26), dtype=torch.bfloat16, device=env.device)
+    out["fused_first_layer"] = sp.fused_first_layer
+    out["encode_us"] = timed(lambda: env.lossless_state_encoding(out=obs))
+    if sp.dense_model is not None:
+        wt0, b0 = sp.dense_model.first_layer_table()
+        act0 = torch.empty((2 * N, wt0.shape[1]), dtype=torch.bfloat16, device=env.device)
+        out["k7_encode_linear_us"] = timed(lambda: env.encoded_linear(wt0, b0, out=act0, neg_slope=0.2))
     out["policy_us"] = timed(sp._policy)
     if sp.dense_model is not None:
-        x = sp.obs.view(2 * N, W * H * 26)
+        x = obs.view(2 * N, W * H * 26)
         with torch.no_grad():
             layers = list(sp.dense_model.conv_as_linear) + list(sp.dense_model.dense) + [sp.dense_model.heads]
             for i, lin in enumerate(layers):
@@ -57,17 +65,20 @@ if args.stages:
                     out["layer%d_lrelu_us" % i] = timed(lambda: torch.nn.functional.leaky_relu(y, 0.2, inplace=True))
                 x = y
     from overcooked_ai_b200.selfplay import sample_categorical
-    out["sample_us"] = timed(lambda: sample_categorical(sp._scores, sp._noise))
+    out["native_glue"] = sp.native_glue
+    out["sample_torch_us"] = timed(lambda: sp.actions.copy_(sample_categorical(sp._scores, sp._noise).view(N, 2)))
+    out["sample_native_us"] = timed(lambda: env.sample_actions(sp._scores, sp._draw_counter, seed=1, out=sp.actions))
     out["step_us"] = timed(lambda: env.step(sp.actions))
     sparse, shaped = env.sparse, env.shaped
 
     def book():
         sp.ret_sparse.add_(sparse)
         sp.ret_mixed.add_(sparse).add_(shaped[:, 0], alpha=sp.factor).add_(shaped[:, 1], alpha=sp.factor)
-    out["bookkeeping_us"] = timed(book)
+    out["bookkeeping_torch_us"] = timed(book)
+    out["accumulate_native_us"] = timed(lambda: env.accumulate_returns(sp.ret_sparse, sp.ret_mixed, sp.factor))
     out["transition_eager_us"] = timed(sp._transition)
-    for sb in sorted({1, 2, 4, 8, args.sub_batches}):
-        spg = SelfPlayRollout(env, use_graph=True, dense=bool(args.dense), sub_batches=sb)
+    for sb in sorted({1, 2, args.sub_batches}):
+        spg = SelfPlayRollout(env, use_graph=True, dense=bool(args.dense), sub_batches=sb, fused_first_layer=sp.fused_first_layer, native_glue=sp.native_glue)
         spg.run(4)
         out["transition_graph_sub%d_us" % sb] = timed(lambda: spg.run(1))
     print(json.dumps(out))
