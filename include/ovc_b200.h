@@ -435,6 +435,23 @@ int ovc_accumulate_returns(const int32_t *sparse, const int32_t *shaped, float f
                            float *ret_mixed, void *stream);
 
 /*
+ * ovc_policy_tail: the narrow end of the rollout policy and the action draw in one kernel (reference model:
+ * human_aware_rl/ppo/ppo_rllib.py:64-79 — dense layers of 64 after the convolutions, then the action / value heads):
+ *   a = leaky_relu(x, in_slope)                          x bfloat16 [n_rows][k0], k0 a multiple of 32 in 32..256
+ *   a = leaky_relu(a . w_first^T + b_first, slope)       w_first bfloat16 [64][k0], biases float32
+ *   a = leaky_relu(a . w_hidden[l]^T + b_hidden[l], slope)   l < n_hidden, w_hidden bfloat16 [n_hidden][64][64]
+ *   s = a . w_heads^T + b_heads                          w_heads bfloat16 [8][64]: heads 0..n_actions-1 are the logits,
+ *                                                        head n_actions (<= 7) is the value
+ *   actions[r] ~ softmax(s[r][0..n_actions)) exactly as ovc_sample_actions draws it (same seed / counter semantics);
+ *   values[r] = s[r][n_actions] (nullable);  scores float32 [n_rows][8] = s (nullable).
+ * Activations are rounded to bfloat16 between layers, accumulation is float32 (mma.sync m16n8k16).
+ */
+int ovc_policy_tail(const void *x, int64_t n_rows, int k0, float in_slope, const void *w_first, const float *b_first,
+                    const void *w_hidden, const float *b_hidden, int n_hidden, const void *w_heads, const float *b_heads,
+                    float slope, int n_actions, uint64_t seed, uint64_t *counter, int32_t *actions, float *values,
+                    float *scores, void *stream);
+
+/*
  * featurize_state (:2579-2898) with the default planner parameters (NO_COUNTERS_PARAMS,
  * planners.py:27-34): out float32[n_envs][2][F],
  * F = 2*(num_pots*10+28), lut = ovc_feat_lut_entry_t[n_layouts][256][4].  view_swap as above.

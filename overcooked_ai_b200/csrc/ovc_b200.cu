@@ -10,7 +10,8 @@
 // K5  rollout_kernel<S, IO>  T transitions with the tile resident in shared memory.
 // K4  reset_kernel           masked copy of the per-layout start record.
 // The observation kernels (K2 lossless encode, K3 featurize) live in ovc_obs.cuh, K7 (first policy layer on the
-// encoding, evaluated from the record) in ovc_encfc.cuh.
+// encoding, evaluated from the record) and the draw / return kernels in ovc_encfc.cuh, K8 (dense tail of the policy +
+// the draw, one kernel) in ovc_tail.cuh.
 //
 // The path is integer, branchy and HBM-bound (no contraction anywhere): no tensor cores.
 #include <cuda.h>
@@ -601,6 +602,7 @@ static int step_impl(const void *layouts, int n_layouts, const int32_t *start_re
 
 #include "ovc_obs.cuh"
 #include "ovc_encfc.cuh"
+#include "ovc_tail.cuh"
 #include "ovc_potential.cuh"
 #include "ovc_host.cuh"
 
@@ -676,6 +678,18 @@ int ovc_sample_actions(const float *scores, int ld, int n_actions, int64_t n_row
 int ovc_accumulate_returns(const int32_t *sparse, const int32_t *shaped, float factor, int64_t n_envs, int64_t *ret_sparse,
                            float *ret_mixed, void *stream) {
     return ovc::accumulate_returns_impl(sparse, shaped, factor, n_envs, (long long *)ret_sparse, ret_mixed, (cudaStream_t)stream);
+}
+
+int ovc_policy_tail(const void *x, int64_t n_rows, int k0, float in_slope, const void *w_first, const float *b_first,
+                    const void *w_hidden, const float *b_hidden, int n_hidden, const void *w_heads, const float *b_heads,
+                    float slope, int n_actions, uint64_t seed, uint64_t *counter, int32_t *actions, float *values, float *scores,
+                    void *stream) {
+    ovc::PolicyTailArgs a;
+    a.x = (const __nv_bfloat16 *)x, a.w_first = (const __nv_bfloat16 *)w_first, a.b_first = b_first;
+    a.w_hidden = (const __nv_bfloat16 *)w_hidden, a.b_hidden = b_hidden, a.w_heads = (const __nv_bfloat16 *)w_heads, a.b_heads = b_heads;
+    a.n_rows = n_rows, a.n_hidden = n_hidden, a.n_actions = n_actions, a.in_slope = in_slope, a.slope = slope, a.seed = seed;
+    a.counter = (unsigned long long *)counter, a.actions = actions, a.values = values, a.scores = scores;
+    return ovc::policy_tail_impl(a, k0, (cudaStream_t)stream);
 }
 
 int ovc_featurize(const void *layouts, int n_layouts, const void *lut, const int32_t *state,

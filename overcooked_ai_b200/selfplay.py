@@ -23,6 +23,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _native
+
 
 class RllibShapedCNN(nn.Module):
     def __init__(self, width, height, in_planes=26, num_filters=25, hidden=64, num_hidden_layers=3, num_actions=6):
@@ -108,6 +110,26 @@ class DenseGridPolicy(nn.Module):
         lin = self.conv_as_linear[0]
         return lin.weight.detach().t().contiguous().to(torch.bfloat16), lin.bias.detach().float().contiguous()
 
+    def tail_tables(self):
+        """The dense tail in the form ``ovc_policy_tail`` (K8) takes: (w_first bf16 [64, k0], b_first f32 [64], w_hidden bf16
+        [n_hidden, 64, 64], b_hidden f32 [n_hidden, 64], w_heads bf16 [8, 64], b_heads f32 [8]).  Its input is the LAST
+        convolution's pre-activation (``trunk``)."""
+        d = list(self.dense)
+        assert all(l.out_features == 64 for l in d) and d[0].in_features % 32 == 0 and d[0].in_features <= 256 and self.n_actions <= 7
+        bf = lambda t: t.detach().to(torch.bfloat16).contiguous()
+        f32 = lambda t: t.detach().float().contiguous()
+        return (bf(d[0].weight), f32(d[0].bias), bf(torch.stack([l.weight for l in d[1:]])), f32(torch.stack([l.bias for l in d[1:]])),
+                bf(self.heads.weight[:8]), f32(self.heads.bias[:8]))
+
+    def trunk(self, x, first, out=None):
+        """The wide layers from index ``first`` on, up to the last convolution's PRE-activation ``[rows, k0]`` (its leaky ReLU
+        is applied by K8 on load)."""
+        convs = list(self.conv_as_linear)
+        for lin in convs[first:-1]:
+            x = F.leaky_relu(lin(x), 0.2, inplace=True)
+        last = convs[-1]
+        return torch.addmm(last.bias, x, last.weight.t(), out=out)
+
     def forward_from(self, x, first):
         """The layers from index ``first`` on (0: the whole network from the observation; 1: from the first layer's
         activations, e.g. K7's output)."""
@@ -132,7 +154,7 @@ class SelfPlayRollout(object):
     """Policy-in-the-loop rollout: both agents of every environment act from the same network."""
 
     def __init__(self, env, model=None, autocast_dtype=torch.bfloat16, use_graph=True, reward_shaping_factor=1.0,
-                 obs_dtype=None, dense=True, sub_batches=1, fused_first_layer=None, native_glue=True, seed=0):
+                 obs_dtype=None, dense=True, sub_batches=1, fused_first_layer=None, native_glue=True, seed=0, fused_tail=None):
         """obs_dtype: element type K2 writes (default: bfloat16 when the policy runs in bf16 — the plane values are exact
         in bf16 and the conversion pass disappears — else float32).
         dense: evaluate the network through ``DenseGridPolicy`` (one library GEMM per layer, widths padded to 16-byte rows,
@@ -145,7 +167,10 @@ class SelfPlayRollout(object):
         GEMMs start at the second layer.
         native_glue: the joint action is drawn by ``ovc_sample_actions`` (Gumbel-max on Philox draws keyed by ``seed``,
         one kernel) and the rewards are folded into the returns by ``ovc_accumulate_returns`` (one kernel) instead of five
-        and four tensor-library kernels."""
+        and four tensor-library kernels.
+        fused_tail (default: with native_glue on the dense bf16 policy): the dense layers of 64, the heads and the draw run as
+        ONE kernel (``ovc_policy_tail``, K8) on the last convolution's pre-activation; the library GEMMs are then only the
+        two wide layers."""
         assert len({(l.width, l.height) for l in env.layouts}) == 1, "one grid shape per rollout (group envs by layout)"
         self.env = env
         l = env.layouts[0]
@@ -177,8 +202,16 @@ class SelfPlayRollout(object):
         self.ret_mixed = torch.zeros(N, dtype=torch.float32, device=dev)    # sparse + factor * shaped (rllib.py:328-329)
         self.values = torch.zeros((N, 2), dtype=torch.float32, device=dev)
         self.native_glue = bool(native_glue)
+        if fused_tail is None:
+            fused_tail = self.native_glue and dense and autocast_dtype == torch.bfloat16
+        assert not fused_tail or (self.native_glue and dense and autocast_dtype == torch.bfloat16), "K8 ends the dense bf16 policy"
+        self.fused_tail = bool(fused_tail)
+        if self.fused_tail:
+            self._tail = self.dense_model.tail_tables()
+            self._z = torch.empty((2 * N, self._tail[0].shape[1]), dtype=torch.bfloat16, device=dev)  # last convolution, pre-activation
         self.seed = int(seed)
         self._draw_counter = torch.zeros(2, dtype=torch.int64, device=dev)  # [step, scratch] of ovc_sample_actions
+        self._scores8 = None  # set to a float32 [2N, 8] tensor to make K8 also write the heads (tests)
         self._noise = torch.empty((2 * N, 6), dtype=torch.float32, device=dev)
         self._scores = torch.empty((2 * N, 6), dtype=torch.float32, device=dev)
         self.sub_batches = int(sub_batches)
@@ -198,6 +231,16 @@ class SelfPlayRollout(object):
                     flat, first = self.obs.view(rows, self.W * self.H * 26), 0
                 vals = self.values.view(rows)
                 step = rows // self.sub_batches
+                if self.fused_tail:  # K8 draws the actions itself: nothing to return
+                    for b in range(0, rows, step):
+                        self.dense_model.trunk(flat[b:b + step], first, out=self._z[b:b + step])
+                    w1, b1, wh, bh, wo, bo = self._tail
+                    _native.check(_native.lib().ovc_policy_tail(
+                        self._z.data_ptr(), rows, self._z.shape[1], 0.2, w1.data_ptr(), b1.data_ptr(), wh.data_ptr(), bh.data_ptr(),
+                        wh.shape[0], wo.data_ptr(), bo.data_ptr(), 0.3, self.dense_model.n_actions, self.seed & (2**64 - 1),
+                        self._draw_counter.data_ptr(), self.actions.data_ptr(), vals.data_ptr(),
+                        self._scores8.data_ptr() if self._scores8 is not None else 0, env._stream()))
+                    return None
                 for b in range(0, rows, step):
                     logits, value = self.dense_model.forward_from(flat[b:b + step], first)
                     self._scores[b:b + step].copy_(logits)
@@ -216,7 +259,8 @@ class SelfPlayRollout(object):
             env.lossless_state_encoding(out=self.obs)  # K2
         scores = self._policy()
         if self.native_glue:
-            env.sample_actions(scores, self._draw_counter, seed=self.seed, out=self.actions)
+            if not self.fused_tail:
+                env.sample_actions(scores, self._draw_counter, seed=self.seed, out=self.actions)
             env.step(self.actions)  # K1 (auto-reset inside)
             env.accumulate_returns(self.ret_sparse, self.ret_mixed, self.factor)
             return

@@ -407,12 +407,22 @@ def test_selfplay_fused_first_layer_equals_unfused_policy():
     env = BatchedOvercookedEnv("cramped_room", n, horizon=30, auto_reset=True)
     rng = np.random.RandomState(9)
     env.rollout(torch.from_numpy(_random_actions(rng, 17, n, 0.5)).cuda())
-    fused = SelfPlayRollout(env, use_graph=False)
+    fused = SelfPlayRollout(env, use_graph=False, fused_tail=False)
     assert fused.fused_first_layer and fused.obs is None
-    plain = SelfPlayRollout(env, model=fused.model, use_graph=False, fused_first_layer=False)
+    plain = SelfPlayRollout(env, model=fused.model, use_graph=False, fused_first_layer=False, fused_tail=False)
     env.lossless_state_encoding(out=plain.obs)
     a, b = _np(fused._policy().clone()), _np(plain._policy().clone())
     assert np.abs(a - b).max() < 0.02 and np.abs(a).max() > 0.01, np.abs(a - b).max()
+    # K8 behind K7: the heads it computes are the unfused policy's logits / values; its actions are the draw on them
+    tail = SelfPlayRollout(env, model=fused.model, use_graph=False, seed=11)
+    assert tail.fused_tail and tail.fused_first_layer
+    tail._scores8 = torch.zeros((2 * n, 8), dtype=torch.float32, device="cuda")
+    before = _np(env.state).copy()
+    assert tail._policy() is None and np.array_equal(_np(env.state), before)
+    s8 = _np(tail._scores8)
+    assert np.abs(s8[:, :6] - b).max() < 0.02 and np.abs(s8[:, 6] - _np(plain.values).reshape(-1)).max() < 0.02
+    assert np.array_equal(s8[:, 6], _np(tail.values).reshape(-1)) and _np(tail._draw_counter).tolist() == [1, 0]
+    _check_draw(_np(tail.actions).reshape(-1), s8, 11, 0)
     ref_state = _np(env.state).copy()
     for t in range(20):
         fused.run(1)
@@ -465,6 +475,62 @@ def test_sample_actions_kernel_matches_its_definition_and_softmax():
     p /= p.sum()
     f = np.bincount(a, minlength=6) / a.size
     assert np.abs(f - p).max() < 4 * np.sqrt(0.25 / a.size), (f, p)
+
+
+def _check_draw(actions, scores, seed, step, n_actions=6):
+    """actions == the ovc_sample_actions definition applied to ``scores`` (numpy restatement; near-ties exempt)."""
+    rows = np.arange(len(scores), dtype=np.uint64)
+    ctr = np.stack([rows & np.uint64(0xFFFFFFFF), rows >> np.uint64(32), np.full_like(rows, step), np.zeros_like(rows)], 1).astype(np.uint32)
+    d = np.concatenate([_philox4x32_10(seed, ctr), _philox4x32_10(seed, ctr | np.array([0, 0, 0, 1], np.uint32))], 1)[:, :n_actions]
+    u = ((d >> np.uint32(9)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -23)
+    v = scores[:, :n_actions] - np.log(-np.log(u))
+    top2 = np.sort(v, 1)[:, -2:]
+    clear = top2[:, 1] - top2[:, 0] > 1e-4  # libm and the device logf differ in the last bits: near-ties may flip
+    assert clear.mean() > 0.995 and np.array_equal(actions[clear], v.argmax(1)[clear])
+    assert actions.min() >= 0 and actions.max() < n_actions
+
+
+def _bf16(x):
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(torch.bfloat16).float().numpy()
+
+
+@pytest.mark.parametrize("k0,n_hidden,n_rows", [(160, 2, 4099), (64, 0, 16), (256, 3, 1000), (96, 1, 1)])
+def test_k8_policy_tail_vs_float_reference(k0, n_hidden, n_rows):
+    """K8 (dense tail + heads + draw in one kernel) against a float32 restatement with bf16 rounding between layers; the
+    actions are the documented draw on the heads the kernel itself reports; ragged row counts; the step advances."""
+    lib = _native.lib()
+    rng = np.random.RandomState(k0 + n_hidden)
+    x = _bf16(rng.normal(size=(n_rows, k0)))
+    w1, b1 = _bf16(rng.normal(size=(64, k0)) / np.sqrt(k0)), rng.normal(size=64).astype(np.float32) * 0.1
+    wh, bh = _bf16(rng.normal(size=(max(n_hidden, 1), 64, 64)) / 8), rng.normal(size=(max(n_hidden, 1), 64)).astype(np.float32) * 0.1
+    wo, bo = _bf16(rng.normal(size=(8, 64)) / 4), rng.normal(size=8).astype(np.float32) * 0.1
+    lrelu = lambda z, s: np.where(z > 0, z, z * np.float32(s)).astype(np.float32)
+    a = _bf16(lrelu(x, 0.2))
+    a = _bf16(lrelu(a @ w1.T + b1, 0.3))
+    for l in range(n_hidden):
+        a = _bf16(lrelu(a @ wh[l].T + bh[l], 0.3))
+    want = a @ wo.T + bo
+    dev = lambda v, dt: torch.from_numpy(np.ascontiguousarray(v)).cuda().to(dt)
+    tx, tw1, twh, two = dev(x, torch.bfloat16), dev(w1, torch.bfloat16), dev(wh, torch.bfloat16), dev(wo, torch.bfloat16)
+    tb1, tbh, tbo = dev(b1, torch.float32), dev(bh, torch.float32), dev(bo, torch.float32)
+    counter = torch.zeros(2, dtype=torch.int64, device="cuda")
+    actions = torch.full((n_rows,), -1, dtype=torch.int32, device="cuda")
+    values = torch.zeros(n_rows, dtype=torch.float32, device="cuda")
+    scores = torch.zeros((n_rows, 8), dtype=torch.float32, device="cuda")
+    for step in range(2):
+        _native.check(lib.ovc_policy_tail(tx.data_ptr(), n_rows, k0, 0.2, tw1.data_ptr(), tb1.data_ptr(), twh.data_ptr(), tbh.data_ptr(), n_hidden,
+                                          two.data_ptr(), tbo.data_ptr(), 0.3, 6, 99, counter.data_ptr(), actions.data_ptr(), values.data_ptr(),
+                                          scores.data_ptr(), 0))
+        got = _np(scores)
+        assert np.abs(got - want).max() < 0.03 * max(1.0, np.abs(want).max()), np.abs(got - want).max()
+        assert np.array_equal(_np(values), got[:, 6]) and _np(counter).tolist() == [step + 1, 0]
+        if n_rows >= 1000:
+            _check_draw(_np(actions), got, 99, step)
+        else:
+            assert _np(actions).min() >= 0 and _np(actions).max() <= 5
+    rc = lib.ovc_policy_tail(tx.data_ptr(), n_rows, 100, 0.2, tw1.data_ptr(), tb1.data_ptr(), twh.data_ptr(), tbh.data_ptr(), n_hidden,
+                             two.data_ptr(), tbo.data_ptr(), 0.3, 6, 99, counter.data_ptr(), actions.data_ptr(), 0, 0, 0)
+    assert rc == -1 and b"multiple of 32" in lib.ovc_last_error()
 
 
 def test_accumulate_returns_kernel():

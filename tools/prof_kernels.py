@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 from overcooked_ai_b200.batched import BatchedOvercookedEnv  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--which", default="k5", choices=["k1", "k5", "k2", "k2u8", "k3", "k6"])
+ap.add_argument("--which", default="k5", choices=["k1", "k5", "k2", "k2u8", "k3", "k6", "k7", "k8"])
 ap.add_argument("--n", type=int, default=65536)
 ap.add_argument("--layouts", default="cramped_room")
 ap.add_argument("--reps", type=int, default=4)
@@ -27,6 +27,12 @@ if args.which == "k5":
 elif args.which == "k1":
     for t in range(40):
         env.step(acts[t])
+elif args.which in ("k7", "k8"):  # the config-5 policy kernels: a few eager self-play transitions (ncu: -k regex:encode_linear|policy_tail)
+    from overcooked_ai_b200.selfplay import SelfPlayRollout
+    env.rollout(acts[:150])
+    sp = SelfPlayRollout(env, use_graph=False)
+    for _ in range(args.reps):
+        sp._transition()
 else:
     env.rollout(acts[:150])
     if args.which == "k6":

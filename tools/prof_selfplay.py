@@ -20,11 +20,12 @@ ap.add_argument("--eager", type=int, default=3, help="eager transitions (what nc
 ap.add_argument("--stages", action="store_true", help="time the stages with CUDA events")
 ap.add_argument("--dense", type=int, default=1)
 ap.add_argument("--sub-batches", type=int, default=1)
+ap.add_argument("--tail", type=int, default=1, help="K8 (dense tail + heads + draw in one kernel)")
 ap.add_argument("--glue", type=int, default=1, help="ovc_sample_actions / ovc_accumulate_returns instead of tensor-library ops")
 ap.add_argument("--fused", type=int, default=1, help="K7 (encoding + first layer from the record) instead of K2 + first GEMM")
 args = ap.parse_args()
 env = BatchedOvercookedEnv(["cramped_room"], args.n, horizon=400, auto_reset=True)
-sp = SelfPlayRollout(env, use_graph=False, dense=bool(args.dense), sub_batches=args.sub_batches, fused_first_layer=bool(args.fused and args.dense), native_glue=bool(args.glue))
+sp = SelfPlayRollout(env, use_graph=False, dense=bool(args.dense), sub_batches=args.sub_batches, fused_first_layer=bool(args.fused and args.dense), native_glue=bool(args.glue), fused_tail=bool(args.tail and args.glue and args.dense))
 for _ in range(args.eager):
     sp._transition()
 torch.cuda.synchronize()
@@ -53,7 +54,16 @@ if args.stages:
         wt0, b0 = sp.dense_model.first_layer_table()
         act0 = torch.empty((2 * N, wt0.shape[1]), dtype=torch.bfloat16, device=env.device)
         out["k7_encode_linear_us"] = timed(lambda: env.encoded_linear(wt0, b0, out=act0, neg_slope=0.2))
+    out["fused_tail"] = sp.fused_tail
     out["policy_us"] = timed(sp._policy)
+    if sp.dense_model is not None:
+        from overcooked_ai_b200 import _native
+        w1, b1, wh, bh, wo, bo = sp.dense_model.tail_tables()
+        z = torch.randn((2 * N, w1.shape[1]), device=env.device).to(torch.bfloat16)
+        vals = torch.empty(2 * N, dtype=torch.float32, device=env.device)
+        out["k8_policy_tail_us"] = timed(lambda: _native.check(_native.lib().ovc_policy_tail(
+            z.data_ptr(), 2 * N, z.shape[1], 0.2, w1.data_ptr(), b1.data_ptr(), wh.data_ptr(), bh.data_ptr(), wh.shape[0], wo.data_ptr(),
+            bo.data_ptr(), 0.3, 6, 1, sp._draw_counter.data_ptr(), sp.actions.data_ptr(), vals.data_ptr(), 0, env._stream())))
     if sp.dense_model is not None:
         x = obs.view(2 * N, W * H * 26)
         with torch.no_grad():
@@ -78,7 +88,7 @@ if args.stages:
     out["accumulate_native_us"] = timed(lambda: env.accumulate_returns(sp.ret_sparse, sp.ret_mixed, sp.factor))
     out["transition_eager_us"] = timed(sp._transition)
     for sb in sorted({1, 2, args.sub_batches}):
-        spg = SelfPlayRollout(env, use_graph=True, dense=bool(args.dense), sub_batches=sb, fused_first_layer=sp.fused_first_layer, native_glue=sp.native_glue)
+        spg = SelfPlayRollout(env, use_graph=True, dense=bool(args.dense), sub_batches=sb, fused_first_layer=sp.fused_first_layer, native_glue=sp.native_glue, fused_tail=sp.fused_tail)
         spg.run(4)
         out["transition_graph_sub%d_us" % sb] = timed(lambda: spg.run(1))
     print(json.dumps(out))

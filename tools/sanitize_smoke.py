@@ -105,4 +105,26 @@ assert phi.shape == (n,)
 env.reset(torch.from_numpy((rng.rand(n) < 0.5).astype(np.int32)).cuda())
 torch.cuda.synchronize()
 print("K2 x4 dtypes, K3, K6, K4 masked reset ok", flush=True)
+# K7 (first policy layer from the record), K8 (dense tail + draw), the draw / return kernels, and the self-play transition on them
+from overcooked_ai_b200.selfplay import SelfPlayRollout  # noqa: E402
+
+env = BatchedOvercookedEnv(["cramped_room"], n, horizon=40, auto_reset=True)
+env.rollout(torch.from_numpy(acts_for(25, n)).cuda())
+wt = (torch.rand((520, 128), device="cuda") - 0.5).to(torch.bfloat16)
+bias = torch.rand(128, device="cuda") - 0.5
+obs = env.lossless_state_encoding(dtype=torch.float32).view(2 * n, 520)
+want = torch.nn.functional.leaky_relu(obs @ wt.float() + bias, 0.2)
+got = env.encoded_linear(wt, bias, neg_slope=0.2).float()
+assert (got - want).abs().max().item() < 0.02
+sp = SelfPlayRollout(env, use_graph=False, seed=3)
+assert sp.fused_first_layer and sp.fused_tail
+ref_state = env.state.cpu().numpy().copy()
+for t in range(6):
+    sp.run(1)
+    cpu.step(env._tab_host, env._starts_host, ref_state, sp.actions.cpu().numpy(), horizon=40, flags=1)
+    assert np.array_equal(env.state.cpu().numpy(), ref_state)
+sp2 = SelfPlayRollout(env, model=sp.model, use_graph=False, fused_tail=False)
+sp2.run(3)
+torch.cuda.synchronize()
+print("K7, K8, sample / accumulate kernels, self-play transitions ok", flush=True)
 print("sanitize_smoke: all ok")
