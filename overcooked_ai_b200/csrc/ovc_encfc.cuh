@@ -122,6 +122,12 @@ __global__ void __launch_bounds__(EL_THREADS, 1) encode_linear_kernel(const EncL
     const int col0 = slice * CS;
 
     // ---- prologue: the table slice and the per-layout constants ----
+    unsigned char *tplane = reinterpret_cast<unsigned char *>(srow + a.n_layouts * 128);  // [n_layouts][256] terrain plane of a cell, 0 = none
+    for (int i = threadIdx.x; i < a.n_layouts * WH; i += EL_THREADS) {  // terrain code -> plane: X 11, O 12, T 13, D 14, P 10, S 15 (:2449-2465)
+        const int l = i / WH, cell = i - l * WH, x = cell / a.H, y = cell - x * a.H;
+        tplane[l * 256 + cell] = (unsigned char)((0x000F0A0E0D0C0B00ull >> ((a.layouts[l].cell[(y << 4) | x] & 7) * 8)) & 0xFF);
+    }
+    __syncthreads();
     {
         constexpr int CH = CS * 2 / 16;  // 16-byte chunks per row
         for (int i = threadIdx.x; i < n_rows * CH; i += EL_THREADS) {
@@ -131,25 +137,24 @@ __global__ void __launch_bounds__(EL_THREADS, 1) encode_linear_kernel(const EncL
             const uint4 *src = reinterpret_cast<const uint4 *>(a.wt + (size_t)(cell * N_PLANES + plane) * a.n_out + col0) + c;
             reinterpret_cast<uint4 *>(tab)[i] = __ldg(src);
         }
+        // terrain and urgency sums: one thread per (layout, column); the cells' loads are independent (plane ids staged in
+        // shared memory first), issued four at a time, added in cell order
         for (int i = threadIdx.x; i < (a.n_layouts + 1) * CS; i += EL_THREADS) {
             const int l = i / CS, c = i - l * CS;
-            float s = 0.f;
-            if (l == a.n_layouts) {  // urgency plane: ones over the whole grid (:2446-2447)
-                for (int cell = 0; cell < WH; cell++)
-                    s += __bfloat162float(a.wt[(size_t)(cell * N_PLANES + PL_URGENCY) * a.n_out + col0 + c]);
-                urg[c] = s;
-            } else {  // terrain planes of layout l (:2449-2465)
-                const ovc_layout_t *L = a.layouts + l;
-                s = a.bias[col0 + c];
-                for (int cell = 0; cell < WH; cell++) {
-                    const int x = cell / a.H, y = cell - x * a.H;
-                    const int terr = L->cell[(y << 4) | x] & 7;
-                    const int plane = (int)((0x0F0A0E0D0C0B00ull >> (terr * 8)) & 0xFF);
-                    if (terr != OVC_T_FLOOR && terr != OVC_T_OUTSIDE)
-                        s += __bfloat162float(a.wt[(size_t)(cell * N_PLANES + plane) * a.n_out + col0 + c]);
+            const unsigned char *tp = tplane + l * 256;
+            const __nv_bfloat16 *w = a.wt + col0 + c;
+            float s = l == a.n_layouts ? 0.f : a.bias[col0 + c];
+            for (int cell = 0; cell < WH; cell += 4) {
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int pl = cell + u < WH ? (l == a.n_layouts ? (int)PL_URGENCY : (int)tp[cell + u]) : 0;
+                    v[u] = pl ? __bfloat162float(w[(size_t)((cell + u) * N_PLANES + pl) * a.n_out]) : 0.f;
                 }
-                bias_eff[i] = s;
+                s = (((s + v[0]) + v[1]) + v[2]) + v[3];
             }
+            if (l == a.n_layouts) urg[c] = s;
+            else bias_eff[i] = s;
         }
         for (int i = threadIdx.x; i < a.n_layouts * 128; i += EL_THREADS) {
             const ovc_layout_t *L = a.layouts + (i >> 7);
@@ -258,7 +263,7 @@ __global__ void __launch_bounds__(EL_THREADS, 1) encode_linear_kernel(const EncL
 
 static size_t encode_linear_smem(int cpl, int n_rows, int n_layouts) {
     const size_t CS = 32 * (size_t)cpl;
-    return (size_t)n_rows * CS * 2 + ((size_t)n_layouts + 1) * CS * 4 + (size_t)n_layouts * (16 * 4 + 2 * 4 + 128 * 2) + 16;
+    return (size_t)n_rows * CS * 2 + ((size_t)n_layouts + 1) * CS * 4 + (size_t)n_layouts * (16 * 4 + 2 * 4 + 128 * 2 + 256) + 16;
 }
 
 static int encode_linear_impl(const ovc_layout_t *layouts, int n_layouts, const int32_t *state, const int32_t *view_swap,

@@ -108,12 +108,14 @@ __global__ void __launch_bounds__(PT_THREADS, 1) policy_tail_kernel(const Policy
         const int n = i / (K0 / 8), c = i - n * (K0 / 8);
         *reinterpret_cast<uint4 *>(w1 + n * FS + 8 * c) = __ldg(reinterpret_cast<const uint4 *>(p.w_first + (size_t)n * K0) + c);
     }
-    for (int i = threadIdx.x; i < (p.n_hidden * PT_H + PT_NOUT) * PT_H; i += PT_THREADS) {
-        const int n = i >> 6, pos = i & 63;  // row over [hidden layers..., heads], position in the permuted row
-        const int s = pos >> 4, tt = (pos >> 2) & 3, e = pos & 3;
-        const int k = 16 * s + (e < 2 ? 2 * tt + e : 8 + 2 * tt + e - 2);
-        const __nv_bfloat16 v = n < p.n_hidden * PT_H ? p.w_hidden[(size_t)n * PT_H + k] : p.w_heads[(size_t)(n - p.n_hidden * PT_H) * PT_H + k];
-        wh[n * PT_HS + pos] = v;  // the heads' rows follow the hidden layers' with the same stride
+    for (int i = threadIdx.x; i < (p.n_hidden * PT_H + PT_NOUT) * (PT_H / 8); i += PT_THREADS) {
+        // 8 consecutive inputs of one row (hidden layers' rows, then the heads' with the same stride): natural k = 16 s + r,
+        // r = 8 h + 2 tt + e  ->  permuted position 16 s + 4 tt + 2 h + e: the four input pairs go to four 4-byte slots
+        const int n = i >> 3, q = i & 7, s2 = q >> 1, h = q & 1;
+        const __nv_bfloat16 *src = n < p.n_hidden * PT_H ? p.w_hidden + (size_t)n * PT_H : p.w_heads + (size_t)(n - p.n_hidden * PT_H) * PT_H;
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src) + q);
+        unsigned *dst = reinterpret_cast<unsigned *>(wh + n * PT_HS + 16 * s2 + 2 * h);
+        dst[0] = v.x, dst[2] = v.y, dst[4] = v.z, dst[6] = v.w;
     }
     for (int i = threadIdx.x; i < PT_H; i += PT_THREADS) b1[i] = p.b_first[i];
     for (int i = threadIdx.x; i < p.n_hidden * PT_H; i += PT_THREADS) bh[i] = p.b_hidden[i];
