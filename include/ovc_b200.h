@@ -452,6 +452,18 @@ int ovc_policy_tail(const void *x, int64_t n_rows, int k0, float in_slope, const
                     float *scores, void *stream);
 
 /*
+ * ovc_wide_layers (K9): the two wide layers of the rollout policy between ovc_encode_linear and ovc_policy_tail
+ * (reference model: ppo_rllib.py:54-62, the two 3x3 convolutions, each folded into one matrix) as one tcgen05 kernel:
+ *   a1 = leaky_relu(a0 . w1^T + b1, slope);   z2 = a1 . w2^T + b2
+ *   a0 bfloat16 [m][k0], w1 bfloat16 [n1][k0], w2 bfloat16 [n2][n1], biases float32, z2 bfloat16 [m][n2] (pre-activation);
+ *   built for k0 = 512, n1 = 512, n2 = 160 (OVC_E_UNSUPPORTED otherwise); operands 16-byte aligned, rows contiguous.
+ * The activation tile a1 stays on chip (TMEM -> registers -> shared memory as the second layer's A operand); float32
+ * accumulation, a1 rounded to bfloat16 as a materialised activation would be.
+ */
+int ovc_wide_layers(const void *a0, int64_t m, int k0, const void *w1, const float *b1, int n1, const void *w2, const float *b2,
+                    int n2, float slope, void *z2, void *stream);
+
+/*
  * featurize_state (:2579-2898) with the default planner parameters (NO_COUNTERS_PARAMS,
  * planners.py:27-34): out float32[n_envs][2][F],
  * F = 2*(num_pots*10+28), lut = ovc_feat_lut_entry_t[n_layouts][256][4].  view_swap as above.

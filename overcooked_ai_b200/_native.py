@@ -75,6 +75,7 @@ def lib():
     L.ovc_sample_actions.argtypes = [vp, i32, i32, i64, ctypes.c_uint64, vp, vp, vp]
     L.ovc_accumulate_returns.argtypes = [vp, vp, ctypes.c_float, i64, vp, vp, vp]
     L.ovc_policy_tail.argtypes = [vp, i64, i32, ctypes.c_float, vp, vp, vp, vp, i32, vp, vp, ctypes.c_float, i32, ctypes.c_uint64, vp, vp, vp, vp, vp]
+    L.ovc_wide_layers.argtypes = [vp, i64, i32, vp, vp, i32, vp, vp, i32, ctypes.c_float, vp, vp]
     L.ovc_featurize.argtypes = [vp, i32, vp, vp, vp, vp, i64, i32, i32, vp]
     L.ovc_potential.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, i64, i32, vp]
     L.ovc_potential_table_size.restype = ctypes.c_size_t
@@ -86,7 +87,7 @@ def lib():
     L.ovc_pipeline_join.argtypes = [vp, vp]
     L.ovc_pipeline_destroy.argtypes = [vp]
     L.ovc_pipeline_destroy.restype = None
-    for f in (L.ovc_step, L.ovc_rollout, L.ovc_reset, L.ovc_encode_lossless, L.ovc_encode_linear, L.ovc_sample_actions, L.ovc_accumulate_returns, L.ovc_policy_tail, L.ovc_featurize, L.ovc_potential,
+    for f in (L.ovc_step, L.ovc_rollout, L.ovc_reset, L.ovc_encode_lossless, L.ovc_encode_linear, L.ovc_sample_actions, L.ovc_accumulate_returns, L.ovc_policy_tail, L.ovc_wide_layers, L.ovc_featurize, L.ovc_potential,
               L.ovc_expand_codes_host, L.ovc_expand_stream_host, L.ovc_pipeline_create, L.ovc_pipeline_run, L.ovc_pipeline_wait, L.ovc_pipeline_join):
         f.restype = i32
     if L.ovc_abi_version() != ABI_VERSION:
@@ -97,7 +98,7 @@ def lib():
 
 EXPORTED_SYMBOLS = (
     "ovc_abi_version", "ovc_layout_table_size", "ovc_feat_lut_entry_size", "ovc_last_error",
-    "ovc_step", "ovc_rollout", "ovc_reset", "ovc_encode_lossless", "ovc_encode_linear", "ovc_sample_actions", "ovc_accumulate_returns", "ovc_policy_tail", "ovc_featurize", "ovc_potential",
+    "ovc_step", "ovc_rollout", "ovc_reset", "ovc_encode_lossless", "ovc_encode_linear", "ovc_sample_actions", "ovc_accumulate_returns", "ovc_policy_tail", "ovc_wide_layers", "ovc_featurize", "ovc_potential",
     "ovc_potential_table_size", "ovc_expand_codes_host", "ovc_expand_stream_host",
     "ovc_pipeline_create", "ovc_pipeline_run", "ovc_pipeline_wait", "ovc_pipeline_join", "ovc_pipeline_destroy",
 )

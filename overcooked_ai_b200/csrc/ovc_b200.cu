@@ -11,9 +11,10 @@
 // K4  reset_kernel           masked copy of the per-layout start record.
 // The observation kernels (K2 lossless encode, K3 featurize) live in ovc_obs.cuh, K7 (first policy layer on the
 // encoding, evaluated from the record) and the draw / return kernels in ovc_encfc.cuh, K8 (dense tail of the policy +
-// the draw, one kernel) in ovc_tail.cuh.
+// the draw, one kernel) in ovc_tail.cuh, K9 (the policy's two wide layers as one tcgen05 / TMEM kernel) in ovc_wide.cuh.
 //
-// The path is integer, branchy and HBM-bound (no contraction anywhere): no tensor cores.
+// The environment path is integer, branchy and HBM-bound (no contraction anywhere): no tensor cores there.  The policy-in-
+// the-loop kernels K8 / K9 (config 5) are the contractions and use them.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -603,6 +604,7 @@ static int step_impl(const void *layouts, int n_layouts, const int32_t *start_re
 #include "ovc_obs.cuh"
 #include "ovc_encfc.cuh"
 #include "ovc_tail.cuh"
+#include "ovc_wide.cuh"
 #include "ovc_potential.cuh"
 #include "ovc_host.cuh"
 
@@ -690,6 +692,11 @@ int ovc_policy_tail(const void *x, int64_t n_rows, int k0, float in_slope, const
     a.n_rows = n_rows, a.n_hidden = n_hidden, a.n_actions = n_actions, a.in_slope = in_slope, a.slope = slope, a.seed = seed;
     a.counter = (unsigned long long *)counter, a.actions = actions, a.values = values, a.scores = scores;
     return ovc::policy_tail_impl(a, k0, (cudaStream_t)stream);
+}
+
+int ovc_wide_layers(const void *a0, int64_t m, int k0, const void *w1, const float *b1, int n1, const void *w2, const float *b2, int n2,
+                    float slope, void *z2, void *stream) {
+    return ovc::wide_layers_impl(a0, m, k0, w1, b1, n1, w2, b2, n2, slope, z2, (cudaStream_t)stream);
 }
 
 int ovc_featurize(const void *layouts, int n_layouts, const void *lut, const int32_t *state,

@@ -121,6 +121,12 @@ class DenseGridPolicy(nn.Module):
         return (bf(d[0].weight), f32(d[0].bias), bf(torch.stack([l.weight for l in d[1:]])), f32(torch.stack([l.bias for l in d[1:]])),
                 bf(self.heads.weight[:8]), f32(self.heads.bias[:8]))
 
+    def wide_tables(self):
+        """The two wide layers in the form ``ovc_wide_layers`` (K9) takes: (w1 bf16 [n1, k0], b1 f32, w2 bf16 [n2, n1], b2 f32)."""
+        l1, l2 = self.conv_as_linear[1], self.conv_as_linear[2]
+        bf = lambda t: t.detach().to(torch.bfloat16).contiguous()
+        return bf(l1.weight), l1.bias.detach().float().contiguous(), bf(l2.weight), l2.bias.detach().float().contiguous()
+
     def trunk(self, x, first, out=None):
         """The wide layers from index ``first`` on, up to the last convolution's PRE-activation ``[rows, k0]`` (its leaky ReLU
         is applied by K8 on load)."""
@@ -154,7 +160,7 @@ class SelfPlayRollout(object):
     """Policy-in-the-loop rollout: both agents of every environment act from the same network."""
 
     def __init__(self, env, model=None, autocast_dtype=torch.bfloat16, use_graph=True, reward_shaping_factor=1.0,
-                 obs_dtype=None, dense=True, sub_batches=1, fused_first_layer=None, native_glue=True, seed=0, fused_tail=None):
+                 obs_dtype=None, dense=True, sub_batches=1, fused_first_layer=None, native_glue=True, seed=0, fused_tail=None, fused_wide=None):
         """obs_dtype: element type K2 writes (default: bfloat16 when the policy runs in bf16 — the plane values are exact
         in bf16 and the conversion pass disappears — else float32).
         dense: evaluate the network through ``DenseGridPolicy`` (one library GEMM per layer, widths padded to 16-byte rows,
@@ -170,7 +176,10 @@ class SelfPlayRollout(object):
         and four tensor-library kernels.
         fused_tail (default: with native_glue on the dense bf16 policy): the dense layers of 64, the heads and the draw run as
         ONE kernel (``ovc_policy_tail``, K8) on the last convolution's pre-activation; the library GEMMs are then only the
-        two wide layers."""
+        two wide layers.
+        fused_wide (default: with K7 and K8 when the wide layers are 512 -> 512 -> 160, i.e. on 5x4 grids): those two layers
+        run as ONE tcgen05 kernel (``ovc_wide_layers``, K9: the 512-wide activation stays in TMEM / shared memory) — the
+        whole policy is then K7 -> K9 -> K8, no library call."""
         assert len({(l.width, l.height) for l in env.layouts}) == 1, "one grid shape per rollout (group envs by layout)"
         self.env = env
         l = env.layouts[0]
@@ -209,6 +218,13 @@ class SelfPlayRollout(object):
         if self.fused_tail:
             self._tail = self.dense_model.tail_tables()
             self._z = torch.empty((2 * N, self._tail[0].shape[1]), dtype=torch.bfloat16, device=dev)  # last convolution, pre-activation
+        if fused_wide is None:
+            fused_wide = self.fused_tail and self.fused_first_layer and self._wide_shape() == (512, 512, 160)
+        assert not fused_wide or (self.fused_tail and self.fused_first_layer and self._wide_shape() == (512, 512, 160)), \
+            "K9 sits between K7 and K8 and is built for 512 -> 512 -> 160"
+        self.fused_wide = bool(fused_wide)
+        if self.fused_wide:
+            self._wide = self.dense_model.wide_tables()
         self.seed = int(seed)
         self._draw_counter = torch.zeros(2, dtype=torch.int64, device=dev)  # [step, scratch] of ovc_sample_actions
         self._scores8 = None  # set to a float32 [2N, 8] tensor to make K8 also write the heads (tests)
@@ -218,6 +234,12 @@ class SelfPlayRollout(object):
         assert (2 * N) % self.sub_batches == 0
         self.graph = None
         self.use_graph = use_graph
+
+    def _wide_shape(self):
+        if self.dense_model is None:
+            return None
+        l1, l2 = self.dense_model.conv_as_linear[1], self.dense_model.conv_as_linear[2]
+        return (l1.in_features, l1.out_features, l2.out_features)
 
     def _policy(self):
         """(scores float32 [2N, 6] = logits, values written to self.values) for the observations in self.obs."""
@@ -232,8 +254,13 @@ class SelfPlayRollout(object):
                 vals = self.values.view(rows)
                 step = rows // self.sub_batches
                 if self.fused_tail:  # K8 draws the actions itself: nothing to return
-                    for b in range(0, rows, step):
-                        self.dense_model.trunk(flat[b:b + step], first, out=self._z[b:b + step])
+                    if self.fused_wide:
+                        w1, b1, w2, b2 = self._wide
+                        _native.check(_native.lib().ovc_wide_layers(flat.data_ptr(), rows, flat.shape[1], w1.data_ptr(), b1.data_ptr(), w1.shape[0],
+                                                                    w2.data_ptr(), b2.data_ptr(), w2.shape[0], 0.2, self._z.data_ptr(), env._stream()))
+                    else:
+                        for b in range(0, rows, step):
+                            self.dense_model.trunk(flat[b:b + step], first, out=self._z[b:b + step])
                     w1, b1, wh, bh, wo, bo = self._tail
                     _native.check(_native.lib().ovc_policy_tail(
                         self._z.data_ptr(), rows, self._z.shape[1], 0.2, w1.data_ptr(), b1.data_ptr(), wh.data_ptr(), bh.data_ptr(),

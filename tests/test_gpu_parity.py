@@ -415,13 +415,18 @@ def test_selfplay_fused_first_layer_equals_unfused_policy():
     assert np.abs(a - b).max() < 0.02 and np.abs(a).max() > 0.01, np.abs(a - b).max()
     # K8 behind K7: the heads it computes are the unfused policy's logits / values; its actions are the draw on them
     tail = SelfPlayRollout(env, model=fused.model, use_graph=False, seed=11)
-    assert tail.fused_tail and tail.fused_first_layer
+    assert tail.fused_tail and tail.fused_first_layer and tail.fused_wide
+    lib_trunk = SelfPlayRollout(env, model=fused.model, use_graph=False, seed=11, fused_wide=False)
+    lib_trunk._policy()
+    z_lib = _np(lib_trunk._z.float())
     tail._scores8 = torch.zeros((2 * n, 8), dtype=torch.float32, device="cuda")
     before = _np(env.state).copy()
     assert tail._policy() is None and np.array_equal(_np(env.state), before)
     s8 = _np(tail._scores8)
+    assert np.abs(_np(tail._z.float()) - z_lib).max() < 0.05 and np.abs(z_lib).max() > 0.05  # K9 == the two library GEMMs + activation
     assert np.abs(s8[:, :6] - b).max() < 0.02 and np.abs(s8[:, 6] - _np(plain.values).reshape(-1)).max() < 0.02
     assert np.array_equal(s8[:, 6], _np(tail.values).reshape(-1)) and _np(tail._draw_counter).tolist() == [1, 0]
+    assert _np(lib_trunk._draw_counter).tolist() == [1, 0]
     _check_draw(_np(tail.actions).reshape(-1), s8, 11, 0)
     ref_state = _np(env.state).copy()
     for t in range(20):
@@ -531,6 +536,33 @@ def test_k8_policy_tail_vs_float_reference(k0, n_hidden, n_rows):
     rc = lib.ovc_policy_tail(tx.data_ptr(), n_rows, 100, 0.2, tw1.data_ptr(), tb1.data_ptr(), twh.data_ptr(), tbh.data_ptr(), n_hidden,
                              two.data_ptr(), tbo.data_ptr(), 0.3, 6, 99, counter.data_ptr(), actions.data_ptr(), 0, 0, 0)
     assert rc == -1 and b"multiple of 32" in lib.ovc_last_error()
+
+
+@pytest.mark.parametrize("m", [128, 1000, 1, 4096 + 77])
+def test_k9_wide_layers_vs_float_reference(m):
+    """K9 (tcgen05: a1 = leaky_relu(a0 W1^T + b1) kept on chip, z2 = a1 W2^T + b2) against a float32 restatement with the
+    activation rounded to bf16 between the layers; partial last tiles."""
+    lib = _native.lib()
+    rng = np.random.RandomState(m)
+    a0 = _bf16(rng.normal(size=(m, 512)))
+    w1, b1 = _bf16(rng.normal(size=(512, 512)) / np.sqrt(512)), rng.normal(size=512).astype(np.float32) * 0.2
+    w2, b2 = _bf16(rng.normal(size=(160, 512)) / np.sqrt(512)), rng.normal(size=160).astype(np.float32) * 0.2
+    z1 = a0 @ w1.T + b1
+    a1 = _bf16(np.where(z1 > 0, z1, z1 * np.float32(0.2)))
+    want = a1 @ w2.T + b2
+    dev = lambda v, dt: torch.from_numpy(np.ascontiguousarray(v)).cuda().to(dt)
+    ta0, tw1, tw2 = dev(a0, torch.bfloat16), dev(w1, torch.bfloat16), dev(w2, torch.bfloat16)
+    tb1, tb2 = dev(b1, torch.float32), dev(b2, torch.float32)
+    z2 = torch.full((m, 160), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _native.check(lib.ovc_wide_layers(ta0.data_ptr(), m, 512, tw1.data_ptr(), tb1.data_ptr(), 512, tw2.data_ptr(), tb2.data_ptr(), 160, 0.2,
+                                      z2.data_ptr(), 0))
+    torch.cuda.synchronize()
+    got = _np(z2.float())
+    assert np.isfinite(got).all()
+    err = np.abs(got - want)
+    assert (err <= np.abs(want) * 2.0 ** -7 + 0.02).all(), (err.max(), np.abs(want).max())
+    rc = lib.ovc_wide_layers(ta0.data_ptr(), m, 256, tw1.data_ptr(), tb1.data_ptr(), 512, tw2.data_ptr(), tb2.data_ptr(), 160, 0.2, z2.data_ptr(), 0)
+    assert rc == -3 and b"512 -> 512 -> 160" in lib.ovc_last_error()
 
 
 def test_accumulate_returns_kernel():

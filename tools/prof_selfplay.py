@@ -20,12 +20,14 @@ ap.add_argument("--eager", type=int, default=3, help="eager transitions (what nc
 ap.add_argument("--stages", action="store_true", help="time the stages with CUDA events")
 ap.add_argument("--dense", type=int, default=1)
 ap.add_argument("--sub-batches", type=int, default=1)
+ap.add_argument("--wide", type=int, default=1, help="K9 (the two wide layers as one tcgen05 kernel)")
 ap.add_argument("--tail", type=int, default=1, help="K8 (dense tail + heads + draw in one kernel)")
 ap.add_argument("--glue", type=int, default=1, help="ovc_sample_actions / ovc_accumulate_returns instead of tensor-library ops")
 ap.add_argument("--fused", type=int, default=1, help="K7 (encoding + first layer from the record) instead of K2 + first GEMM")
 args = ap.parse_args()
 env = BatchedOvercookedEnv(["cramped_room"], args.n, horizon=400, auto_reset=True)
-sp = SelfPlayRollout(env, use_graph=False, dense=bool(args.dense), sub_batches=args.sub_batches, fused_first_layer=bool(args.fused and args.dense), native_glue=bool(args.glue), fused_tail=bool(args.tail and args.glue and args.dense))
+sp = SelfPlayRollout(env, use_graph=False, dense=bool(args.dense), sub_batches=args.sub_batches, fused_first_layer=bool(args.fused and args.dense), native_glue=bool(args.glue), fused_tail=bool(args.tail and args.glue and args.dense),
+                     fused_wide=bool(args.wide and args.tail and args.glue and args.dense and args.fused))
 for _ in range(args.eager):
     sp._transition()
 torch.cuda.synchronize()
@@ -55,6 +57,14 @@ if args.stages:
         act0 = torch.empty((2 * N, wt0.shape[1]), dtype=torch.bfloat16, device=env.device)
         out["k7_encode_linear_us"] = timed(lambda: env.encoded_linear(wt0, b0, out=act0, neg_slope=0.2))
     out["fused_tail"] = sp.fused_tail
+    out["fused_wide"] = sp.fused_wide
+    if sp.fused_wide:
+        from overcooked_ai_b200 import _native as _nv
+        w1_, b1_, w2_, b2_ = sp._wide
+        a0_ = torch.randn((2 * N, 512), device=env.device).to(torch.bfloat16)
+        z_ = torch.empty((2 * N, 160), dtype=torch.bfloat16, device=env.device)
+        out["k9_wide_layers_us"] = timed(lambda: _nv.check(_nv.lib().ovc_wide_layers(a0_.data_ptr(), 2 * N, 512, w1_.data_ptr(), b1_.data_ptr(), 512,
+                                                                                       w2_.data_ptr(), b2_.data_ptr(), 160, 0.2, z_.data_ptr(), env._stream())))
     out["policy_us"] = timed(sp._policy)
     if sp.dense_model is not None:
         from overcooked_ai_b200 import _native
@@ -88,7 +98,7 @@ if args.stages:
     out["accumulate_native_us"] = timed(lambda: env.accumulate_returns(sp.ret_sparse, sp.ret_mixed, sp.factor))
     out["transition_eager_us"] = timed(sp._transition)
     for sb in sorted({1, 2, args.sub_batches}):
-        spg = SelfPlayRollout(env, use_graph=True, dense=bool(args.dense), sub_batches=sb, fused_first_layer=sp.fused_first_layer, native_glue=sp.native_glue, fused_tail=sp.fused_tail)
+        spg = SelfPlayRollout(env, use_graph=True, dense=bool(args.dense), sub_batches=sb, fused_first_layer=sp.fused_first_layer, native_glue=sp.native_glue, fused_tail=sp.fused_tail, fused_wide=sp.fused_wide)
         spg.run(4)
         out["transition_graph_sub%d_us" % sb] = timed(lambda: spg.run(1))
     print(json.dumps(out))
