@@ -11,11 +11,14 @@
 // layer 2, whose accumulator re-uses TMEM columns 0..159.  As library calls the same work is two GEMMs and an activation
 // pass with a1 written once and read twice (3 x 67 MB per 65 536 rows).
 //
-// One CTA = one 128-row tile; 6 warps: warp 0 = TMA producer (one lane), warp 1 = TMEM allocation + MMA issue (one lane),
-// warps 2-5 = epilogue (TMEM lane quadrant = warp & 3).  Operand tiles arrive by TMA (cp.async.bulk.tensor.2d, 128-byte
-// swizzle) through mbarrier rings: layer 1 streams 8 k-chunks of {a0 128 x 64, W1 512 x 64} = 80 KB through two stages;
-// the a1 tile (8 chunks of 128 x 64, 128 KB) then overlays those stages and W2's chunks (160 x 64, 20 KB) stream through
-// a two-slot ring behind it.  Every mbarrier wait is bounded (a protocol error traps instead of hanging the GPU).
+// One CTA = one 128-row tile; 10 warps: warp 0 = TMA producer (one lane), warp 1 = TMEM allocation + MMA issue (one lane),
+// warps 2-9 = epilogue (TMEM lane quadrant = warp & 3, two warps per quadrant share the columns).  Operand tiles arrive by
+// TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) through mbarrier rings.  Layer 1 is computed one N-half at a time
+// (columns 0-255, then 256-511: 8 k-chunks of {a0 128 x 64, W1 256 x 64} = 48 KB each through three stages), so that the
+// epilogue of the first half — TMEM -> registers -> the first four k-chunks of the a1 tile — runs UNDER the second half's
+// MMAs; layer 2's first four k-steps then run under the second half's epilogue.  Shared memory: a1 chunks 0-3 (64 KB) own
+// their space, the three stages (144 KB) follow; once layer 1 is done a1 chunks 4-7 and W2's two-slot ring (160 x 64,
+// 20 KB per chunk) overlay the stages.  Every mbarrier wait is bounded (a protocol error traps instead of hanging the GPU).
 #pragma once
 #include <cuda_bf16.h>
 
@@ -24,14 +27,17 @@ namespace ovc {
 constexpr int WL_BM = 128, WL_BK = 64, WL_K0 = 512, WL_N1 = 512, WL_N2 = 160;
 constexpr int WL_KC = WL_K0 / WL_BK;        // k-chunks of layer 1
 constexpr int WL_KC2 = WL_N1 / WL_BK;       // k-chunks of layer 2
-constexpr int WL_THREADS = 192;
+constexpr int WL_THREADS = 320;
+constexpr int WL_STAGES = 3;
 constexpr uint32_t WL_A_BYTES = WL_BM * WL_BK * 2;            // 16 KB
-constexpr uint32_t WL_B1_BYTES = WL_N1 * WL_BK * 2;           // 64 KB (two TMA boxes of 256 rows)
-constexpr uint32_t WL_STAGE = WL_A_BYTES + WL_B1_BYTES;       // 80 KB
+constexpr uint32_t WL_B1_BYTES = 256 * WL_BK * 2;             // 32 KB: one N-half of a W1 k-chunk
+constexpr uint32_t WL_STAGE = WL_A_BYTES + WL_B1_BYTES;       // 48 KB
 constexpr uint32_t WL_A1_BYTES = WL_KC2 * WL_A_BYTES;         // 128 KB: the activation tile as layer 2's A operand
 constexpr uint32_t WL_B2_BYTES = WL_N2 * WL_BK * 2;           // 20 KB
-constexpr uint32_t WL_TILE_BYTES = WL_A1_BYTES + 2 * WL_B2_BYTES;  // 168 KB >= 2 stages (160 KB)
-constexpr uint32_t WL_SMEM = 1024 + WL_TILE_BYTES + (WL_N1 + WL_N2) * 4 + 128;
+constexpr uint32_t WL_STAGE0 = WL_A1_BYTES / 2;               // stages start behind a1 chunks 0-3
+constexpr uint32_t WL_TILE_BYTES = WL_STAGE0 + WL_STAGES * WL_STAGE;  // 208 KB >= a1 tile + W2 ring (168 KB)
+static_assert(WL_TILE_BYTES >= WL_A1_BYTES + 2 * WL_B2_BYTES, "a1 chunks 4-7 and the W2 ring overlay the stages");
+constexpr uint32_t WL_SMEM = 1024 + WL_TILE_BYTES + (WL_N1 + WL_N2) * 4 + 192;
 
 struct WideArgs {
     const float *b1, *b2;
@@ -115,16 +121,17 @@ wide_layers_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_cons
     float *bias1 = reinterpret_cast<float *>(tile + WL_TILE_BYTES);
     float *bias2 = bias1 + WL_N1;
     uint64_t *bars = reinterpret_cast<uint64_t *>(bias2 + WL_N2);
-    uint64_t *full = bars, *empty = bars + 2, *w2_full = bars + 4, *w2_empty = bars + 6;
-    uint64_t *d1_full = bars + 8, *a1_ready = bars + 9, *d2_full = bars + 10;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 11);
+    uint64_t *full = bars, *empty = bars + 3, *w2_full = bars + 6, *w2_empty = bars + 8;
+    uint64_t *d1_full = bars + 10 /* [2]: per N-half */, *a1_ready = bars + 12 /* [2] */, *d2_full = bars + 14;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 15);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * WL_BM;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; i++) mbar_init(full + i, 1), mbar_init(empty + i, 1), mbar_init(w2_full + i, 1), mbar_init(w2_empty + i, 1);
-        mbar_init(d1_full, 1), mbar_init(a1_ready, 128), mbar_init(d2_full, 1);
+        for (int i = 0; i < WL_STAGES; i++) mbar_init(full + i, 1), mbar_init(empty + i, 1);
+        for (int i = 0; i < 2; i++) mbar_init(w2_full + i, 1), mbar_init(w2_empty + i, 1), mbar_init(d1_full + i, 1), mbar_init(a1_ready + i, 256);
+        mbar_init(d2_full, 1);
         prefetch_tmap(&map_a0), prefetch_tmap(&map_w1), prefetch_tmap(&map_w2);
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -138,16 +145,15 @@ wide_layers_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_cons
     if (warp == 0) {
         if (lane == 0) {
             // ---- TMA producer ----
-            for (int c = 0; c < WL_KC; c++) {
-                const int s = c & 1, u = c >> 1;
+            for (int it = 0; it < 2 * WL_KC; it++) {  // N-half h = it / 8, k-chunk c = it % 8
+                const int h = it / WL_KC, c = it % WL_KC, s = it % WL_STAGES, u = it / WL_STAGES;
                 mbar_wait_bounded(empty + s, (u & 1) ^ 1);
-                char *st = tile + s * WL_STAGE;
+                char *st = tile + WL_STAGE0 + s * WL_STAGE;
                 mbar_expect_tx(full + s, WL_STAGE);
                 tma_load_2d(st, &map_a0, c * WL_BK, m0, full + s);
-                tma_load_2d(st + WL_A_BYTES, &map_w1, c * WL_BK, 0, full + s);
-                tma_load_2d(st + WL_A_BYTES + WL_B1_BYTES / 2, &map_w1, c * WL_BK, 256, full + s);
+                tma_load_2d(st + WL_A_BYTES, &map_w1, c * WL_BK, 256 * h, full + s);
             }
-            mbar_wait_bounded(d1_full, 0);  // layer 1 has finished reading the stages: W2's ring may overlay them
+            mbar_wait_bounded(d1_full + 1, 0);  // layer 1 has finished reading the stages: W2's ring may overlay them
             for (int c = 0; c < WL_KC2; c++) {
                 const int s = c & 1, u = c >> 1;
                 mbar_wait_bounded(w2_empty + s, (u & 1) ^ 1);
@@ -159,23 +165,22 @@ wide_layers_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_cons
         if (lane == 0) {
             // ---- MMA issue ----
             constexpr uint32_t ID1 = umma_idesc_bf16(WL_BM, 256), ID2 = umma_idesc_bf16(WL_BM, WL_N2);
-            for (int c = 0; c < WL_KC; c++) {
-                const int s = c & 1, u = c >> 1;
+            for (int it = 0; it < 2 * WL_KC; it++) {
+                const int h = it / WL_KC, c = it % WL_KC, s = it % WL_STAGES, u = it / WL_STAGES;
                 mbar_wait_bounded(full + s, u & 1);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(tile + s * WL_STAGE), b_addr = a_addr + WL_A_BYTES;
-                const uint64_t da = umma_desc_sw128(a_addr), db0 = umma_desc_sw128(b_addr), db1 = umma_desc_sw128(b_addr + WL_B1_BYTES / 2);
+                const uint32_t a_addr = smem_u32(tile + WL_STAGE0 + s * WL_STAGE);
+                const uint64_t da = umma_desc_sw128(a_addr), db = umma_desc_sw128(a_addr + WL_A_BYTES);
 #pragma unroll
-                for (int k = 0; k < WL_BK / 16; k++) {
-                    umma_bf16(tmem, da + 2 * k, db0 + 2 * k, ID1, (c | k) != 0);
-                    umma_bf16(tmem + 256, da + 2 * k, db1 + 2 * k, ID1, (c | k) != 0);
-                }
+                for (int k = 0; k < WL_BK / 16; k++) umma_bf16(tmem + 256 * h, da + 2 * k, db + 2 * k, ID1, (c | k) != 0);
                 umma_commit(empty + s);
+                if (c == WL_KC - 1) umma_commit(d1_full + h);  // this half of the accumulator is complete
             }
-            umma_commit(d1_full);
-            mbar_wait_bounded(a1_ready, 0);
-            tc_fence_after();
             for (int c = 0; c < WL_KC2; c++) {
+                if (c == 0 || c == WL_KC2 / 2) {  // a1 chunks 0-3 come from the first half's epilogue, 4-7 from the second's
+                    mbar_wait_bounded(a1_ready + (c ? 1 : 0), 0);
+                    tc_fence_after();
+                }
                 const int s = c & 1, u = c >> 1;
                 mbar_wait_bounded(w2_full + s, u & 1);
                 tc_fence_after();
@@ -188,35 +193,38 @@ wide_layers_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_cons
             umma_commit(d2_full);
         }
     } else {
-        // ---- epilogue warps: TMEM lane quadrant q, this thread's row r of the tile ----
-        const int q = warp & 3, r = q * 32 + lane;
+        // ---- epilogue warps: TMEM lane quadrant q, this thread's row r of the tile; the two warps of a quadrant split the columns ----
+        const int q = warp & 3, g = (warp - 2) >> 2, r = q * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-        mbar_wait_bounded(d1_full, 0);
-        tc_fence_after();
-        for (int j = 0; j < WL_N1 / 32; j++) {  // 32 columns at a time: bias, leaky ReLU, bf16, 64 bytes into the swizzled a1 tile
-            uint32_t v[32];
-            tmem_ld32(lane_addr + 32 * j, v);
-            uint32_t w[16];
+        for (int h = 0; h < 2; h++) {
+            mbar_wait_bounded(d1_full + h, 0);
+            tc_fence_after();
+            for (int jj = 0; jj < 4; jj++) {  // 32 columns at a time: bias, leaky ReLU, bf16, 64 bytes into the swizzled a1 tile
+                const int j = 8 * h + 4 * g + jj;
+                uint32_t v[32];
+                tmem_ld32(lane_addr + 32 * j, v);
+                uint32_t w[16];
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const float x0 = __uint_as_float(v[2 * i]) + bias1[32 * j + 2 * i], x1 = __uint_as_float(v[2 * i + 1]) + bias1[32 * j + 2 * i + 1];
-                const __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(x0, x0 * p.slope), fmaxf(x1, x1 * p.slope));
-                w[i] = *reinterpret_cast<const uint32_t *>(&h);
-            }
-            char *rowp = tile + (j >> 1) * WL_A_BYTES + r * 128;
+                for (int i = 0; i < 16; i++) {
+                    const float x0 = __uint_as_float(v[2 * i]) + bias1[32 * j + 2 * i], x1 = __uint_as_float(v[2 * i + 1]) + bias1[32 * j + 2 * i + 1];
+                    const __nv_bfloat162 hh = __floats2bfloat162_rn(fmaxf(x0, x0 * p.slope), fmaxf(x1, x1 * p.slope));
+                    w[i] = *reinterpret_cast<const uint32_t *>(&hh);
+                }
+                char *rowp = tile + (j >> 1) * WL_A_BYTES + r * 128;
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int unit = ((j & 1) * 4 + i) ^ (r & 7);  // 128-byte swizzle: 16-byte unit index XOR (row mod 8)
-                *reinterpret_cast<uint4 *>(rowp + unit * 16) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+                for (int i = 0; i < 4; i++) {
+                    const int unit = ((j & 1) * 4 + i) ^ (r & 7);  // 128-byte swizzle: 16-byte unit index XOR (row mod 8)
+                    *reinterpret_cast<uint4 *>(rowp + unit * 16) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+                }
             }
+            tc_fence_before();
+            fence_async_smem();  // generic-proxy stores above -> visible to the tensor core's (async proxy) reads
+            mbar_arrive(a1_ready + h);
         }
-        tc_fence_before();
-        fence_async_smem();  // generic-proxy stores above -> visible to the tensor core's (async proxy) reads
-        mbar_arrive(a1_ready);
         mbar_wait_bounded(d2_full, 0);
         tc_fence_after();
         const long long row = (long long)m0 + r;
-        for (int j = 0; j < WL_N2 / 32; j++) {
+        for (int j = g ? 3 : 0; j < (g ? WL_N2 / 32 : 3); j++) {
             uint32_t v[32];
             tmem_ld32(lane_addr + 32 * j, v);
             if (row < p.m) {
@@ -227,9 +235,9 @@ wide_layers_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_cons
 #pragma unroll
                     for (int e = 0; e < 4; e++) {
                         const int c0 = 8 * i + 2 * e;
-                        const __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[c0]) + bias2[32 * j + c0],
-                                                                       __uint_as_float(v[c0 + 1]) + bias2[32 * j + c0 + 1]);
-                        w[e] = *reinterpret_cast<const uint32_t *>(&h);
+                        const __nv_bfloat162 hh = __floats2bfloat162_rn(__uint_as_float(v[c0]) + bias2[32 * j + c0],
+                                                                        __uint_as_float(v[c0 + 1]) + bias2[32 * j + c0 + 1]);
+                        w[e] = *reinterpret_cast<const uint32_t *>(&hh);
                     }
                     dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
                 }
@@ -264,7 +272,7 @@ static int wide_layers_impl(const void *a0, long long m, int k0, const void *w1,
     if (m == 0) return OVC_OK;
     CUtensorMap ma, mw1, mw2;
     int rc = make_tmap_bf16(&ma, a0, m, WL_K0, WL_BM);
-    if (!rc) rc = make_tmap_bf16(&mw1, w1, WL_N1, WL_K0, 256);
+    if (!rc) rc = make_tmap_bf16(&mw1, w1, WL_N1, WL_K0, 256);  // one N-half of a k-chunk per box
     if (!rc) rc = make_tmap_bf16(&mw2, w2, WL_N2, WL_N1, WL_N2);
     if (rc) return rc;
     cudaError_t e = cudaFuncSetAttribute(wide_layers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WL_SMEM);
