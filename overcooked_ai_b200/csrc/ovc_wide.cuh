@@ -11,7 +11,7 @@
 // layer 2, whose accumulator re-uses TMEM columns 0..159.  As library calls the same work is two GEMMs and an activation
 // pass with a1 written once and read twice (3 x 67 MB per 65 536 rows).
 //
-// One CTA = one 128-row tile; 10 warps: warp 0 = TMA producer (one lane), warp 1 = TMEM allocation + MMA issue (one lane),
+// Persistent: one CTA per SM walks 128-row tiles; 10 warps: warp 0 = TMA producer (one lane), warp 1 = TMEM allocation + MMA issue (one lane),
 // warps 2-9 = epilogue (TMEM lane quadrant = warp & 3, two warps per quadrant share the columns).  Operand tiles arrive by
 // TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) through mbarrier rings.  Layer 1 is computed one N-half at a time
 // (columns 0-255, then 256-511: 8 k-chunks of {a0 128 x 64, W1 256 x 64} = 48 KB each through three stages), so that the
@@ -37,13 +37,14 @@ constexpr uint32_t WL_B2_BYTES = WL_N2 * WL_BK * 2;           // 20 KB
 constexpr uint32_t WL_STAGE0 = WL_A1_BYTES / 2;               // stages start behind a1 chunks 0-3
 constexpr uint32_t WL_TILE_BYTES = WL_STAGE0 + WL_STAGES * WL_STAGE;  // 208 KB >= a1 tile + W2 ring (168 KB)
 static_assert(WL_TILE_BYTES >= WL_A1_BYTES + 2 * WL_B2_BYTES, "a1 chunks 4-7 and the W2 ring overlay the stages");
-constexpr uint32_t WL_SMEM = 1024 + WL_TILE_BYTES + (WL_N1 + WL_N2) * 4 + 192;
+constexpr uint32_t WL_SMEM = 1024 + WL_TILE_BYTES + (WL_N1 + WL_N2) * 4 + 192;  // tile + biases + 17 mbarriers / the TMEM slot
 
 struct WideArgs {
     const float *b1, *b2;
     __nv_bfloat16 *z2;
     long long m;
     float slope;
+    int n_tiles;
 };
 
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
@@ -122,16 +123,15 @@ wide_layers_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_cons
     float *bias2 = bias1 + WL_N1;
     uint64_t *bars = reinterpret_cast<uint64_t *>(bias2 + WL_N2);
     uint64_t *full = bars, *empty = bars + 3, *w2_full = bars + 6, *w2_empty = bars + 8;
-    uint64_t *d1_full = bars + 10 /* [2]: per N-half */, *a1_ready = bars + 12 /* [2] */, *d2_full = bars + 14;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 15);
+    uint64_t *d1_full = bars + 10 /* [2]: per N-half */, *a1_ready = bars + 12 /* [2] */, *d2_full = bars + 14, *d2_drained = bars + 15;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * WL_BM;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < WL_STAGES; i++) mbar_init(full + i, 1), mbar_init(empty + i, 1);
         for (int i = 0; i < 2; i++) mbar_init(w2_full + i, 1), mbar_init(w2_empty + i, 1), mbar_init(d1_full + i, 1), mbar_init(a1_ready + i, 256);
-        mbar_init(d2_full, 1);
+        mbar_init(d2_full, 1), mbar_init(d2_drained, 256);
         prefetch_tmap(&map_a0), prefetch_tmap(&map_w1), prefetch_tmap(&map_w2);
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -144,60 +144,74 @@ wide_layers_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_cons
 
     if (warp == 0) {
         if (lane == 0) {
-            // ---- TMA producer ----
-            for (int it = 0; it < 2 * WL_KC; it++) {  // N-half h = it / 8, k-chunk c = it % 8
-                const int h = it / WL_KC, c = it % WL_KC, s = it % WL_STAGES, u = it / WL_STAGES;
-                mbar_wait_bounded(empty + s, (u & 1) ^ 1);
-                char *st = tile + WL_STAGE0 + s * WL_STAGE;
-                mbar_expect_tx(full + s, WL_STAGE);
-                tma_load_2d(st, &map_a0, c * WL_BK, m0, full + s);
-                tma_load_2d(st + WL_A_BYTES, &map_w1, c * WL_BK, 256 * h, full + s);
-            }
-            mbar_wait_bounded(d1_full + 1, 0);  // layer 1 has finished reading the stages: W2's ring may overlay them
-            for (int c = 0; c < WL_KC2; c++) {
-                const int s = c & 1, u = c >> 1;
-                mbar_wait_bounded(w2_empty + s, (u & 1) ^ 1);
-                mbar_expect_tx(w2_full + s, WL_B2_BYTES);
-                tma_load_2d(tile + WL_A1_BYTES + s * WL_B2_BYTES, &map_w2, c * WL_BK, 0, w2_full + s);
+            // ---- TMA producer: tiles blockIdx.x, + gridDim.x, ...; the rings' use counters run on across tiles ----
+            int it1 = 0, it2 = 0;
+            for (int tile_i = blockIdx.x, ti = 0; tile_i < p.n_tiles; tile_i += gridDim.x, ti++) {
+                const int m0 = tile_i * WL_BM;
+                if (ti) mbar_wait_bounded(d2_full, (ti - 1) & 1);  // the previous tile's layer 2 no longer reads what overlays the stages
+                for (int i = 0; i < 2 * WL_KC; i++, it1++) {  // N-half h = i / 8, k-chunk c = i % 8
+                    const int h = i / WL_KC, c = i % WL_KC, s = it1 % WL_STAGES, u = it1 / WL_STAGES;
+                    mbar_wait_bounded(empty + s, (u & 1) ^ 1);
+                    char *st = tile + WL_STAGE0 + s * WL_STAGE;
+                    mbar_expect_tx(full + s, WL_STAGE);
+                    tma_load_2d(st, &map_a0, c * WL_BK, m0, full + s);
+                    tma_load_2d(st + WL_A_BYTES, &map_w1, c * WL_BK, 256 * h, full + s);
+                }
+                mbar_wait_bounded(d1_full + 1, ti & 1);  // layer 1 has finished reading the stages: W2's ring may overlay them
+                for (int c = 0; c < WL_KC2; c++, it2++) {
+                    const int s = it2 & 1, u = it2 >> 1;
+                    mbar_wait_bounded(w2_empty + s, (u & 1) ^ 1);
+                    mbar_expect_tx(w2_full + s, WL_B2_BYTES);
+                    tma_load_2d(tile + WL_A1_BYTES + s * WL_B2_BYTES, &map_w2, c * WL_BK, 0, w2_full + s);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ---- MMA issue ----
             constexpr uint32_t ID1 = umma_idesc_bf16(WL_BM, 256), ID2 = umma_idesc_bf16(WL_BM, WL_N2);
-            for (int it = 0; it < 2 * WL_KC; it++) {
-                const int h = it / WL_KC, c = it % WL_KC, s = it % WL_STAGES, u = it / WL_STAGES;
-                mbar_wait_bounded(full + s, u & 1);
-                tc_fence_after();
-                const uint32_t a_addr = smem_u32(tile + WL_STAGE0 + s * WL_STAGE);
-                const uint64_t da = umma_desc_sw128(a_addr), db = umma_desc_sw128(a_addr + WL_A_BYTES);
-#pragma unroll
-                for (int k = 0; k < WL_BK / 16; k++) umma_bf16(tmem + 256 * h, da + 2 * k, db + 2 * k, ID1, (c | k) != 0);
-                umma_commit(empty + s);
-                if (c == WL_KC - 1) umma_commit(d1_full + h);  // this half of the accumulator is complete
-            }
-            for (int c = 0; c < WL_KC2; c++) {
-                if (c == 0 || c == WL_KC2 / 2) {  // a1 chunks 0-3 come from the first half's epilogue, 4-7 from the second's
-                    mbar_wait_bounded(a1_ready + (c ? 1 : 0), 0);
+            int it1 = 0, it2 = 0;
+            for (int tile_i = blockIdx.x, ti = 0; tile_i < p.n_tiles; tile_i += gridDim.x, ti++) {
+                if (ti) {  // the previous tile's second epilogue has read its accumulator out of TMEM columns 0..159
+                    mbar_wait_bounded(d2_drained, (ti - 1) & 1);
                     tc_fence_after();
                 }
-                const int s = c & 1, u = c >> 1;
-                mbar_wait_bounded(w2_full + s, u & 1);
-                tc_fence_after();
-                const uint64_t da = umma_desc_sw128(smem_u32(tile + c * WL_A_BYTES));
-                const uint64_t db = umma_desc_sw128(smem_u32(tile + WL_A1_BYTES + s * WL_B2_BYTES));
+                for (int i = 0; i < 2 * WL_KC; i++, it1++) {
+                    const int h = i / WL_KC, c = i % WL_KC, s = it1 % WL_STAGES, u = it1 / WL_STAGES;
+                    mbar_wait_bounded(full + s, u & 1);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(tile + WL_STAGE0 + s * WL_STAGE);
+                    const uint64_t da = umma_desc_sw128(a_addr), db = umma_desc_sw128(a_addr + WL_A_BYTES);
 #pragma unroll
-                for (int k = 0; k < WL_BK / 16; k++) umma_bf16(tmem, da + 2 * k, db + 2 * k, ID2, (c | k) != 0);
-                umma_commit(w2_empty + s);
+                    for (int k = 0; k < WL_BK / 16; k++) umma_bf16(tmem + 256 * h, da + 2 * k, db + 2 * k, ID1, (c | k) != 0);
+                    umma_commit(empty + s);
+                    if (c == WL_KC - 1) umma_commit(d1_full + h);  // this half of the accumulator is complete
+                }
+                for (int c = 0; c < WL_KC2; c++, it2++) {
+                    if (c == 0 || c == WL_KC2 / 2) {  // a1 chunks 0-3 come from the first half's epilogue, 4-7 from the second's
+                        mbar_wait_bounded(a1_ready + (c ? 1 : 0), ti & 1);
+                        tc_fence_after();
+                    }
+                    const int s = it2 & 1, u = it2 >> 1;
+                    mbar_wait_bounded(w2_full + s, u & 1);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_sw128(smem_u32(tile + c * WL_A_BYTES));
+                    const uint64_t db = umma_desc_sw128(smem_u32(tile + WL_A1_BYTES + s * WL_B2_BYTES));
+#pragma unroll
+                    for (int k = 0; k < WL_BK / 16; k++) umma_bf16(tmem, da + 2 * k, db + 2 * k, ID2, (c | k) != 0);
+                    umma_commit(w2_empty + s);
+                }
+                umma_commit(d2_full);
             }
-            umma_commit(d2_full);
         }
     } else {
         // ---- epilogue warps: TMEM lane quadrant q, this thread's row r of the tile; the two warps of a quadrant split the columns ----
         const int q = warp & 3, g = (warp - 2) >> 2, r = q * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+        for (int tile_i = blockIdx.x, ti = 0; tile_i < p.n_tiles; tile_i += gridDim.x, ti++) {
+        const int m0 = tile_i * WL_BM;
         for (int h = 0; h < 2; h++) {
-            mbar_wait_bounded(d1_full + h, 0);
+            mbar_wait_bounded(d1_full + h, ti & 1);
             tc_fence_after();
             for (int jj = 0; jj < 4; jj++) {  // 32 columns at a time: bias, leaky ReLU, bf16, 64 bytes into the swizzled a1 tile
                 const int j = 8 * h + 4 * g + jj;
@@ -221,7 +235,7 @@ wide_layers_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_cons
             fence_async_smem();  // generic-proxy stores above -> visible to the tensor core's (async proxy) reads
             mbar_arrive(a1_ready + h);
         }
-        mbar_wait_bounded(d2_full, 0);
+        mbar_wait_bounded(d2_full, ti & 1);
         tc_fence_after();
         const long long row = (long long)m0 + r;
         for (int j = g ? 3 : 0; j < (g ? WL_N2 / 32 : 3); j++) {
@@ -242,6 +256,9 @@ wide_layers_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_cons
                     dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
+        }
+        tc_fence_before();
+        mbar_arrive(d2_drained);  // TMEM columns 0..159 may be overwritten by the next tile's first layer
         }
     }
     tc_fence_before();
@@ -278,8 +295,13 @@ static int wide_layers_impl(const void *a0, long long m, int k0, const void *w1,
     cudaError_t e = cudaFuncSetAttribute(wide_layers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WL_SMEM);
     if (e != cudaSuccess) return cuda_fail(e, "wide_layers kernel attribute");
     WideArgs p;
+    int dev = 0, n_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     p.b1 = b1, p.b2 = b2, p.z2 = (__nv_bfloat16 *)z2, p.m = m, p.slope = slope;
-    wide_layers_kernel<<<(unsigned)((m + WL_BM - 1) / WL_BM), WL_THREADS, WL_SMEM, st>>>(ma, mw1, mw2, p);
+    p.n_tiles = (int)((m + WL_BM - 1) / WL_BM);
+    // persistent: one CTA per SM walks tiles blockIdx.x, + gridDim.x, ... (barriers, TMEM and biases are set up once)
+    wide_layers_kernel<<<(unsigned)(p.n_tiles < n_sm ? p.n_tiles : n_sm), WL_THREADS, WL_SMEM, st>>>(ma, mw1, mw2, p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "wide_layers kernel launch");
     return OVC_OK;

@@ -538,10 +538,11 @@ def test_k8_policy_tail_vs_float_reference(k0, n_hidden, n_rows):
     assert rc == -1 and b"multiple of 32" in lib.ovc_last_error()
 
 
-@pytest.mark.parametrize("m", [128, 1000, 1, 4096 + 77])
+@pytest.mark.parametrize("m", [128, 1000, 1, 4096 + 77, 128 * 449 + 5])
 def test_k9_wide_layers_vs_float_reference(m):
     """K9 (tcgen05: a1 = leaky_relu(a0 W1^T + b1) kept on chip, z2 = a1 W2^T + b2) against a float32 restatement with the
-    activation rounded to bf16 between the layers; partial last tiles."""
+    activation rounded to bf16 between the layers; partial last tiles; the largest case gives every persistent CTA three or
+    four tiles (barrier phases, TMEM and shared-memory re-use across tiles)."""
     lib = _native.lib()
     rng = np.random.RandomState(m)
     a0 = _bf16(rng.normal(size=(m, 512)))
