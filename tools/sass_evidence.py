@@ -9,7 +9,7 @@ import subprocess
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 SO = os.path.join(ROOT, "overcooked_ai_b200", "csrc", "libovc_b200.so")
 sass = subprocess.run(["cuobjdump", "-sass", SO], capture_output=True, text=True).stdout
-pats = ["UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "ACQBULK", "VOTE", "POPC", "LDS", "STS", "LDG", "STG", "HMMA", "UTC"]
+pats = ["UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "ACQBULK", "VOTE", "POPC", "LDS", "STS", "LDG", "STG", "HMMA", "UTCHMMA", "UTCBAR", "LDTM", "UTCATOMSWS"]
 rows = []
 for f in re.split(r"\n\s*Function : ", sass)[1:]:
     name = f.split("\n", 1)[0].strip()
@@ -22,11 +22,14 @@ print("Counts of the mnemonics that prove the Blackwell data-movement path, per 
       "`cp.async.bulk.tensor` (2-D tensor-map TMA load / store of the record tile, hardware swizzle), `UBLKCP` = `cp.async.bulk` (1-D bulk\n"
       "copies: layout tables in, observation tiles out), `SYNCS` = mbarrier operations, `ACQBULK` = bulk-async acquire, `VOTE` + `POPC` = warp\n"
       "votes / ranks (`__ballot_sync`: the live-lane mask of every rollout kernel, and the sparse event stream of the `..., 2>` = FMT_STREAM\n"
-      "instantiations).  No `HMMA` / `UTC*MMA`: there is no contraction on this path, tensor cores are not used (DESIGN.md section 4).\n"
+      "instantiations).  The environment kernels have no `HMMA` / `UTC*MMA`: there is no contraction on that path (DESIGN.md section 4).\n"
+      "The policy-in-the-loop kernels are the contractions: `wide_layers_kernel` (K9) = `UTCHMMA` (`tcgen05.mma`, accumulators in TMEM),\n"
+      "`UTCBAR` (`tcgen05.commit` onto an mbarrier), `LDTM` (`tcgen05.ld`), `UTCATOMSWS` (TMEM allocation), `UTMALDG` (TMA operand tiles);\n"
+      "`policy_tail_kernel` (K8) = `HMMA` (`mma.sync.m16n8k16` bf16, register-resident layer chain).\n"
       "Template arguments: `step_kernel<S, IO, RS, WIDE>`, `rollout_kernel<S, TILE, RS, FMT>`.\n")
-print("| kernel | SASS instr | UTMALDG | UTMASTG | UBLKCP | SYNCS | ACQBULK | VOTE | POPC | LDS | STS | LDG | STG | HMMA/UTC*MMA |")
-print("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
+print("| kernel | SASS instr | UTMALDG | UTMASTG | UBLKCP | SYNCS | ACQBULK | VOTE | POPC | LDS | STS | LDG | STG | HMMA | UTCHMMA | UTCBAR | LDTM | UTCATOMSWS |")
+print("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
 for short, n, c in sorted(rows):
-    print("| `%s` | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d |" % (
+    print("| `%s` | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d |" % (
         short, n, c["UTMALDG"], c["UTMASTG"], c["UBLKCP"], c["SYNCS"], c["ACQBULK"], c["VOTE"], c["POPC"], c["LDS"], c["STS"], c["LDG"], c["STG"],
-        c["HMMA"] + c["UTC"]))
+        c["HMMA"], c["UTCHMMA"], c["UTCBAR"], c["LDTM"], c["UTCATOMSWS"]))
