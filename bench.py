@@ -513,15 +513,16 @@ def policy_leg(dev, rank, world, seed, steps, warmup, envs=0):
     l = env.layouts[0]
     return {
         "workload": "config5: %s, %d envs/GPU, self-play: %s -> policy (RllibPPOModel-shaped CNN, random init, shared; "
-                    "every convolution folded into one matrix, selfplay.DenseGridPolicy; the two wide layers are library GEMMs) -> %s -> K1 step "
+                    "every convolution folded into one matrix, selfplay.DenseGridPolicy; the two wide layers: %s) -> %s -> K1 step "
                     "-> returns (ovc_accumulate_returns), whole transition in one CUDA graph" % ("+".join(layouts), n_envs,
                     "K7 (lossless encoding + first layer + leaky ReLU from the packed records, observation never materialised)"
                     if sp.fused_first_layer else "K2 lossless encode bf16",
+                    "K9, one tcgen05 / TMEM kernel" if sp.fused_wide else "library GEMMs",
                     "K8 (the dense layers of 64, the heads and the Gumbel-max action draw in one kernel)" if sp.fused_tail else "Gumbel-max sampling"),
         "what": what, "value": tot_steps / (max_ms * 1e-3), "unit": "env-steps/s", "steps": steps, "ms_per_step": max_ms / steps,
         "dtype": "int32 env / bf16 activations / bf16 policy",
-        # kernels of this library per transition: K7 (or K2), K8 (or the draw kernel), K1, the return kernel
-        "gpu_launches": (1 + int(sp.native_glue) + 1 + int(sp.native_glue)) * T * steps,
+        # kernels of this library per transition: K7 (or K2), K9, K8 (or the draw kernel), K1, the return kernel
+        "gpu_launches": (1 + int(sp.fused_wide) + int(sp.native_glue) + 1 + int(sp.native_glue)) * T * steps,
         "env_only": {"kernels": "K7 (encoding + first policy layer) + K1" if sp.fused_first_layer else "K2 + K1", "ms_per_400_transitions": max_ms_env, "env_steps_per_s_per_gpu": n_envs * T / (max_ms_env * 1e-3),
                      "share_of_pipeline_time": max_ms_env / (max_ms / steps),
                      "algorithmic_bytes_per_env_step": 2 * 4 * S + 32 + 4 * S + (2 * sp._act0.shape[1] * 2 if sp.fused_first_layer else

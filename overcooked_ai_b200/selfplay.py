@@ -16,8 +16,10 @@ channels-last memory format.
 
 The policy is shaped like the reference's ``RllibPPOModel`` defaults (ppo_rllib.py:43-79 with
 ppo_rllib_client.py:85-88: conv 5x5x25 'same', conv 3x3x25 'same', conv 3x3x25 'valid', 3 dense layers
-of 64, leaky ReLU, heads 6 + 1), random init, shared by both agents.  It is a CONSUMER of the hot
-path (library kernels: cuDNN / cuBLAS through torch), not part of it.
+of 64, leaky ReLU, heads 6 + 1), random init, shared by both agents.  ``RllibShapedCNN`` is that model in torch
+(the consumer a user brings: cuDNN / cuBLAS); ``DenseGridPolicy`` is the same function as one matrix per layer, and
+on a 5x4 grid ``SelfPlayRollout`` evaluates it entirely with this library's kernels: K7 (encoding + first layer from
+the packed records), K9 (the two wide layers, tcgen05 / TMEM), K8 (dense tail + heads + action draw).
 """
 import torch
 import torch.nn as nn
@@ -61,9 +63,9 @@ class DenseGridPolicy(nn.Module):
     ``pad_to``: every layer's width is rounded up to a multiple of it with zero weights and zero biases (leaky ReLU of 0
     is 0, the next layer's extra input columns are zero too: the function is unchanged).  Widths of 500 / 150 bf16
     elements give rows that are not 16-byte multiples, which sends the library to its Ampere-era ``align2`` mma.sync
-    kernels (measured: 160 us for the first layer at 65 536 rows, profiles/r2_selfplay.md); 512 / 160 reach the sm_100
-    kernels.  The two heads are one matrix (6 logits + 1 value, padded to 8).  The policy stays a CONSUMER of the hot path
-    (library GEMMs), not part of it."""
+    kernels (measured: 160 us for the first layer at 65 536 rows, profiles/r2_selfplay_stages_before.json); 512 / 160 reach the sm_100
+    kernels.  The two heads are one matrix (6 logits + 1 value, padded to 8).  ``forward`` / ``forward_from`` / ``trunk`` run
+    it as library GEMMs; ``first_layer_table`` / ``wide_tables`` / ``tail_tables`` hand the same weights to K7 / K9 / K8."""
 
     def __init__(self, cnn, width, height, pad_to=1):
         super().__init__()
@@ -150,7 +152,7 @@ class DenseGridPolicy(nn.Module):
 def sample_categorical(logits, noise):
     """One draw per row from softmax(logits) by the Gumbel-max rule: argmax_i (logit_i - log E_i) with E_i ~ Exp(1) picks i
     with probability softmax(logits)_i — four small kernels where softmax + ``torch.multinomial`` launch about twenty
-    (profiles/r2_selfplay.md).  ``logits`` (float32) is overwritten with the perturbed scores, ``noise`` is scratch of
+    (profiles/r2_selfplay_stages_before.json).  ``logits`` (float32) is overwritten with the perturbed scores, ``noise`` is scratch of
     the same shape."""
     logits.sub_(noise.exponential_().log_())
     return torch.argmax(logits, dim=-1)
