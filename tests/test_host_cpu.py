@@ -537,3 +537,32 @@ def test_dense_grid_policy_padding_keeps_the_function():
     with torch.no_grad():
         (l1, v1), (l2, v2) = plain(obs), padded(obs)
     assert l2.shape == (11, 6) and torch.allclose(l1, l2, atol=1e-6) and torch.allclose(v1, v2, atol=1e-6)
+
+
+def test_dense_grid_policy_kernel_tables_are_the_policy():
+    """first_layer_table / wide_tables / tail_tables (what K7 / K9 / K8 are given) evaluated with plain float matmuls equal
+    DenseGridPolicy.forward: the three kernels together are the whole network, nothing is left to a library call."""
+    import torch
+    import torch.nn.functional as F
+
+    from overcooked_ai_b200.selfplay import DenseGridPolicy, RllibShapedCNN
+
+    torch.manual_seed(4)
+    cnn = RllibShapedCNN(5, 4).eval()
+    d = DenseGridPolicy(cnn, 5, 4, pad_to=16).eval()
+    wt0, b0 = d.first_layer_table()
+    w1, b1, w2, b2 = d.wide_tables()
+    wf, bf, wh, bh, wo, bo = d.tail_tables()
+    assert wt0.shape == (520, 512) and w1.shape == (512, 512) and w2.shape == (160, 512) and wf.shape == (64, 160)
+    assert wh.shape == (2, 64, 64) and wo.shape == (8, 64) and all(t.dtype == torch.bfloat16 for t in (wt0, w1, w2, wf, wh, wo))
+    obs = (torch.rand(9, 520) < 0.1).float()
+    with torch.no_grad():
+        want_logits, want_value = d(obs)
+        a = F.leaky_relu(obs @ wt0.float() + b0, 0.2)                                   # K7
+        z = F.leaky_relu(a @ w1.float().t() + b1, 0.2) @ w2.float().t() + b2               # K9 (pre-activation out)
+        a = F.leaky_relu(F.leaky_relu(z, 0.2) @ wf.float().t() + bf, 0.3)                  # K8: activation on load, first dense layer
+        for l in range(wh.shape[0]):
+            a = F.leaky_relu(a @ wh[l].float().t() + bh[l], 0.3)
+        heads = a @ wo.float().t() + bo
+    # the tables hold the weights rounded to bf16: agreement to bf16 accuracy of the weights
+    assert torch.allclose(heads[:, :6], want_logits, atol=3e-3) and torch.allclose(heads[:, 6], want_value, atol=3e-3)
