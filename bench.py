@@ -70,6 +70,17 @@ def workload_string(name, n_envs=None):
         name, "+".join(layouts), n_envs or n, horizon)
 
 
+def load_tensor_peak():
+    """(dense bf16 TFLOP/s, source): the driver-measured burst figure (a kernel timed alone), else the profiling recipe's fallback."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        if "bf16_tflops" in d:
+            return float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
+    return 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)"
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -511,6 +522,40 @@ def policy_leg(dev, rank, world, seed, steps, warmup, envs=0):
     ok_all, _, _ = D.reduce_counters(0.0 if bad else 1.0, 0, 0, device=dev)
     S = env.state_words
     l = env.layouts[0]
+    # ---- the policy-side kernels on their own (CUDA events, on the states / activations the run left behind) ----
+    kernels = {}
+    if sp.fused_first_layer and sp.fused_wide and sp.fused_tail:
+        from overcooked_ai_b200 import _native as NV
+
+        def kernel_us(fn, reps=20):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            return e0.elapsed_time(e1) / reps * 1e3
+
+        rows = 2 * n_envs
+        w1, b1, w2, b2 = sp._wide
+        t1, c1, th, ch, to, co = sp._tail
+        k7 = kernel_us(lambda: env.encoded_linear(sp._wt0, sp._b0, out=sp._act0, neg_slope=0.2))
+        k9 = kernel_us(lambda: NV.check(NV.lib().ovc_wide_layers(sp._act0.data_ptr(), rows, 512, w1.data_ptr(), b1.data_ptr(), 512, w2.data_ptr(),
+                                                                 b2.data_ptr(), 160, 0.2, sp._z.data_ptr(), env._stream())))
+        k8 = kernel_us(lambda: NV.check(NV.lib().ovc_policy_tail(sp._z.data_ptr(), rows, 160, 0.2, t1.data_ptr(), c1.data_ptr(), th.data_ptr(), ch.data_ptr(),
+                                                                 th.shape[0], to.data_ptr(), co.data_ptr(), 0.3, 6, 1, sp._draw_counter.data_ptr(),
+                                                                 sp.actions.data_ptr(), sp.values.data_ptr(), 0, env._stream())))
+        flops = rows * 2.0 * (512 * 512 + 512 * 160)
+        peak_tf, peak_src = load_tensor_peak()
+        kernels = {"k7_encode_linear_us": k7, "k9_wide_layers_us": k9, "k8_policy_tail_us": k8,
+                   "roofline_k9": {"bound": "tensor", "kernel": "ovc::wide_layers_kernel (tcgen05.mma, accumulators in TMEM): 512 -> 512 -> 160 for %d rows" % rows,
+                                   "achieved": flops / (k9 * 1e-6) / 1e12, "peak": peak_tf, "unit": "TFLOP/s", "frac": flops / (k9 * 1e-6) / 1e12 / peak_tf,
+                                   "peak_source": peak_src, "flops_per_launch": flops, "avg_launch_us": k9,
+                                   "traffic": (load_ncu_summary().get("config5_k9") or {}).get("dram_bytes_per_launch"),
+                                   "note": "timed alone, back to back (burst peak); achieved = 2 * rows * (512*512 + 512*160) / duration"}}
     return {
         "workload": "config5: %s, %d envs/GPU, self-play: %s -> policy (RllibPPOModel-shaped CNN, random init, shared; "
                     "every convolution folded into one matrix, selfplay.DenseGridPolicy; the two wide layers: %s) -> %s -> K1 step "
@@ -528,7 +573,7 @@ def policy_leg(dev, rank, world, seed, steps, warmup, envs=0):
                      "algorithmic_bytes_per_env_step": 2 * 4 * S + 32 + 4 * S + (2 * sp._act0.shape[1] * 2 if sp.fused_first_layer else
                                                                                   2 * l.width * l.height * 26 * sp.obs.element_size())},
         "spot_check": ("ok" if not bad else "MISMATCH in " + ",".join(bad)) if ok_all == world else "MISMATCH on some rank",
-        "spot_check_envs_per_rank": len(ids), "sparse_reward_sum": tot_reward,
+        "spot_check_envs_per_rank": len(ids), "sparse_reward_sum": tot_reward, "policy_kernels": kernels,
     }
 
 
