@@ -40,6 +40,29 @@ class RllibShapedCNN(nn.Module):
         self.logits = nn.Linear(hidden, num_actions)
         self.value = nn.Linear(hidden, 1)
 
+    def load_keras_weights(self, conv, dense, logits, value):
+        """Weights of the reference's ``RllibPPOModel`` (ppo_rllib.py:43-79, a Keras model) into this module: ``conv`` =
+        [(kernel, bias)] of conv_initial, conv_0, conv_1 with Keras kernels ``(kh, kw, in, out)`` over an observation of shape
+        ``(W, H, 26)``; ``dense`` = [(kernel, bias)] of the hidden layers with Keras kernels ``(in, out)``, the first one over
+        Keras' flatten order ``(x, y, channel)``; ``logits`` / ``value`` = (kernel, bias) of the two heads.  Arrays or
+        tensors.  The function computed is the Keras model's (tests/test_host_cpu.py restates it in numpy)."""
+        t = lambda a: torch.as_tensor(a, dtype=torch.float32)
+        with torch.no_grad():
+            for mod, (k, b) in zip((self.conv_initial, self.conv_0, self.conv_1), conv):
+                mod.weight.copy_(t(k).permute(3, 2, 0, 1))  # (kh, kw, in, out) -> (out, in, kh, kw): the grid's x is the kernel's first axis in both
+                mod.bias.copy_(t(b))
+            co = self.conv_1.out_channels
+            k0, b0 = dense[0]
+            k0 = t(k0)  # rows in (x, y, c) order; torch flattens (c, x, y)
+            wo_ho = k0.shape[0] // co
+            self.dense[0].weight.copy_(k0.view(wo_ho, co, -1).permute(2, 1, 0).reshape(k0.shape[1], -1))
+            self.dense[0].bias.copy_(t(b0))
+            for mod, (k, b) in zip(list(self.dense)[1:], dense[1:]):
+                mod.weight.copy_(t(k).t()), mod.bias.copy_(t(b))
+            self.logits.weight.copy_(t(logits[0]).t()), self.logits.bias.copy_(t(logits[1]))
+            self.value.weight.copy_(t(value[0]).t()), self.value.bias.copy_(t(value[1]))
+        return self
+
     def forward(self, obs_nchw):
         x = F.leaky_relu(self.conv_initial(obs_nchw), 0.2)
         x = F.leaky_relu(self.conv_0(x), 0.2)

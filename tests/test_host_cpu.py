@@ -566,3 +566,49 @@ def test_dense_grid_policy_kernel_tables_are_the_policy():
         heads = a @ wo.float().t() + bo
     # the tables hold the weights rounded to bf16: agreement to bf16 accuracy of the weights
     assert torch.allclose(heads[:, :6], want_logits, atol=3e-3) and torch.allclose(heads[:, 6], want_value, atol=3e-3)
+
+
+def test_policy_loads_the_reference_keras_model_weights():
+    """RllibShapedCNN.load_keras_weights: weights in the reference PPO model's own (Keras) layouts give the Keras model's
+    function — restated here in numpy from ppo_rllib.py:43-79 (Conv2D 5x5 'same', 3x3 'same', 3x3 'valid' with
+    tf.nn.leaky_relu = 0.2, Flatten over (x, y, channel), Dense + LeakyReLU() = 0.3, two linear heads) — and so does the
+    dense-matrix form the kernels consume."""
+    import torch
+
+    from overcooked_ai_b200.selfplay import DenseGridPolicy, RllibShapedCNN
+
+    rng = np.random.RandomState(11)
+    W, H, C, NF, HID = 5, 4, 26, 25, 64
+    conv = [(rng.normal(size=(5, 5, C, NF)) * 0.1, rng.normal(size=NF) * 0.1), (rng.normal(size=(3, 3, NF, NF)) * 0.1, rng.normal(size=NF) * 0.1),
+            (rng.normal(size=(3, 3, NF, NF)) * 0.1, rng.normal(size=NF) * 0.1)]
+    flat = (W - 2) * (H - 2) * NF
+    dense = [(rng.normal(size=(flat, HID)) * 0.1, rng.normal(size=HID) * 0.1)] + [(rng.normal(size=(HID, HID)) * 0.1, rng.normal(size=HID) * 0.1) for _ in range(2)]
+    logits, value = (rng.normal(size=(HID, 6)) * 0.1, rng.normal(size=6) * 0.1), (rng.normal(size=(HID, 1)) * 0.1, rng.normal(size=1) * 0.1)
+
+    def conv2d(x, k, b, same):  # x (n, W, H, cin) channels last, k (kh, kw, cin, cout): Keras Conv2D, stride 1
+        kh, kw = k.shape[:2]
+        if same:
+            x = np.pad(x, ((0, 0), (kh // 2, kh // 2), (kw // 2, kw // 2), (0, 0)))
+        wo, ho = x.shape[1] - kh + 1, x.shape[2] - kw + 1
+        out = np.zeros((x.shape[0], wo, ho, k.shape[3]))
+        for i in range(kh):
+            for j in range(kw):
+                out += x[:, i:i + wo, j:j + ho, :] @ k[i, j]
+        return out + b
+
+    lrelu = lambda z, a: np.where(z > 0, z, a * z)
+    obs = (rng.rand(7, W, H, C) < 0.1).astype(np.float64) * rng.randint(1, 4, size=(7, W, H, C))
+    x = lrelu(conv2d(obs, *conv[0], True), 0.2)
+    x = lrelu(conv2d(x, *conv[1], True), 0.2)
+    x = lrelu(conv2d(x, *conv[2], False), 0.2).reshape(7, -1)
+    for k, b in dense:
+        x = lrelu(x @ k + b, 0.3)
+    want_logits, want_value = x @ logits[0] + logits[1], (x @ value[0] + value[1])[:, 0]
+
+    cnn = RllibShapedCNN(W, H).eval().load_keras_weights(conv, dense, logits, value)
+    t_obs = torch.from_numpy(obs).float()
+    with torch.no_grad():
+        l1, v1 = cnn(t_obs.permute(0, 3, 1, 2))
+        l2, v2 = DenseGridPolicy(cnn, W, H, pad_to=16).eval()(t_obs.reshape(7, -1))
+    for l, v in ((l1, v1), (l2, v2)):
+        assert np.allclose(l.numpy(), want_logits, atol=2e-4) and np.allclose(v.numpy(), want_value, atol=2e-4)
