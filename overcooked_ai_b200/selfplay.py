@@ -172,6 +172,19 @@ class DenseGridPolicy(nn.Module):
         return hv[:, :self.n_actions], hv[:, self.n_actions]
 
 
+def fused_kernel_support(dense_model, width, height):
+    """(K7, K9, K8) usable for this network on this grid: K7 needs the first layer's width to be a multiple of 64 and its
+    narrowest column slice (64 columns of the 19 dynamic planes) to fit shared memory; K9 is built for 512 -> 512 -> 160 (5x4
+    grids); K8 for a tail of 64-wide layers behind an input of a multiple of 32 (<= 256) and at most 7 actions.  Whatever is
+    not supported runs as library GEMMs / the separate draw kernel."""
+    l0, l1, l2 = dense_model.conv_as_linear
+    d = list(dense_model.dense)
+    k7 = l0.out_features % 64 == 0 and width * height * 19 * 64 * 2 + 4096 <= 227 * 1024
+    k9 = (l1.in_features, l1.out_features, l2.out_features) == (512, 512, 160)
+    k8 = all(l.out_features == 64 for l in d) and d[0].in_features % 32 == 0 and d[0].in_features <= 256 and dense_model.n_actions <= 7
+    return k7, k9, k8
+
+
 def sample_categorical(logits, noise):
     """One draw per row from softmax(logits) by the Gumbel-max rule: argmax_i (logit_i - log E_i) with E_i ~ Exp(1) picks i
     with probability softmax(logits)_i — four small kernels where softmax + ``torch.multinomial`` launch about twenty
@@ -217,9 +230,11 @@ class SelfPlayRollout(object):
             self.dense_model = DenseGridPolicy(self.model, self.W, self.H, pad_to=16).to(dev).eval()
             if autocast_dtype is not None:
                 self.dense_model = self.dense_model.to(autocast_dtype)
+        k7_ok, k9_ok, k8_ok = fused_kernel_support(self.dense_model, self.W, self.H) if dense else (False, False, False)
         if fused_first_layer is None:
-            fused_first_layer = dense and autocast_dtype == torch.bfloat16
-        assert not fused_first_layer or (dense and autocast_dtype == torch.bfloat16), "K7 feeds the dense bf16 policy"
+            fused_first_layer = dense and autocast_dtype == torch.bfloat16 and k7_ok
+        assert not fused_first_layer or (dense and autocast_dtype == torch.bfloat16 and k7_ok), \
+            "K7 feeds the dense bf16 policy (first layer width a multiple of 64, table within shared memory)"
         self.fused_first_layer = bool(fused_first_layer)
         self.factor = float(reward_shaping_factor)
         N = env.n_envs
@@ -237,15 +252,16 @@ class SelfPlayRollout(object):
         self.values = torch.zeros((N, 2), dtype=torch.float32, device=dev)
         self.native_glue = bool(native_glue)
         if fused_tail is None:
-            fused_tail = self.native_glue and dense and autocast_dtype == torch.bfloat16
-        assert not fused_tail or (self.native_glue and dense and autocast_dtype == torch.bfloat16), "K8 ends the dense bf16 policy"
+            fused_tail = self.native_glue and dense and autocast_dtype == torch.bfloat16 and k8_ok
+        assert not fused_tail or (self.native_glue and dense and autocast_dtype == torch.bfloat16 and k8_ok), \
+            "K8 ends the dense bf16 policy (64-wide tail behind an input of a multiple of 32, <= 256)"
         self.fused_tail = bool(fused_tail)
         if self.fused_tail:
             self._tail = self.dense_model.tail_tables()
             self._z = torch.empty((2 * N, self._tail[0].shape[1]), dtype=torch.bfloat16, device=dev)  # last convolution, pre-activation
         if fused_wide is None:
-            fused_wide = self.fused_tail and self.fused_first_layer and self._wide_shape() == (512, 512, 160)
-        assert not fused_wide or (self.fused_tail and self.fused_first_layer and self._wide_shape() == (512, 512, 160)), \
+            fused_wide = self.fused_tail and self.fused_first_layer and k9_ok
+        assert not fused_wide or (self.fused_tail and self.fused_first_layer and k9_ok), \
             "K9 sits between K7 and K8 and is built for 512 -> 512 -> 160"
         self.fused_wide = bool(fused_wide)
         if self.fused_wide:
@@ -259,12 +275,6 @@ class SelfPlayRollout(object):
         assert (2 * N) % self.sub_batches == 0
         self.graph = None
         self.use_graph = use_graph
-
-    def _wide_shape(self):
-        if self.dense_model is None:
-            return None
-        l1, l2 = self.dense_model.conv_as_linear[1], self.dense_model.conv_as_linear[2]
-        return (l1.in_features, l1.out_features, l2.out_features)
 
     def _policy(self):
         """(scores float32 [2N, 6] = logits, values written to self.values) for the observations in self.obs."""

@@ -612,3 +612,15 @@ def test_policy_loads_the_reference_keras_model_weights():
         l2, v2 = DenseGridPolicy(cnn, W, H, pad_to=16).eval()(t_obs.reshape(7, -1))
     for l, v in ((l1, v1), (l2, v2)):
         assert np.allclose(l.numpy(), want_logits, atol=2e-4) and np.allclose(v.numpy(), want_value, atol=2e-4)
+
+
+def test_fused_kernel_support_by_grid():
+    """Which of K7 / K9 / K8 a grid's policy can use (the rest runs as library GEMMs): all three on 5x4, K7 only on 5x5
+    (tail input 240 is not a multiple of 32), none on 9x5 (first layer 1136 wide: not a multiple of 64; tail input 528)."""
+    import torch
+
+    from overcooked_ai_b200.selfplay import DenseGridPolicy, RllibShapedCNN, fused_kernel_support
+
+    for (W, H), want in (((5, 4), (True, True, True)), ((5, 5), (True, False, False)), ((9, 5), (False, False, False))):
+        d = DenseGridPolicy(RllibShapedCNN(W, H), W, H, pad_to=16)
+        assert fused_kernel_support(d, W, H) == want, (W, H, fused_kernel_support(d, W, H))
