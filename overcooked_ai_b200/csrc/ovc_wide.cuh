@@ -18,7 +18,7 @@
 // epilogue of the first half — TMEM -> registers -> the first four k-chunks of the a1 tile — runs UNDER the second half's
 // MMAs; layer 2's first four k-steps then run under the second half's epilogue.  Shared memory: a1 chunks 0-3 (64 KB) own
 // their space, the three stages (144 KB) follow; once layer 1 is done a1 chunks 4-7 and W2's two-slot ring (160 x 64,
-// 20 KB per chunk) overlay the stages.  Every mbarrier wait is bounded (a protocol error traps instead of hanging the GPU).
+// 20 KB per chunk) overlay the stages.  Every mbarrier wait is bounded (~10 s; a protocol error traps instead of hanging the GPU).
 #pragma once
 #include <cuda_bf16.h>
 
@@ -58,7 +58,7 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity
             : "=r"(ok)
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
-        if (!ok && clock64() - t0 > 4000000000ll) __trap();  // ~2 s: a protocol error must not hang the device
+        if (!ok && clock64() - t0 > 20000000000ll) __trap();  // ~10 s: a protocol error must not hang the device
     } while (!ok);
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {

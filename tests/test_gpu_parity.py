@@ -482,6 +482,27 @@ def test_sample_actions_kernel_matches_its_definition_and_softmax():
     assert np.abs(f - p).max() < 4 * np.sqrt(0.25 / a.size), (f, p)
 
 
+@pytest.mark.parametrize("layout,flags", [("coordination_ring", (True, False, False)), ("asymmetric_advantages", (False, False, False))])
+def test_selfplay_other_grids_fall_back_to_library_layers(layout, flags):
+    """Grids whose policy widths the fused kernels are not built for (5x5: K7 only; 9x5: none) run the remaining layers as
+    library GEMMs with the separate draw kernel; the environments still follow the oracle on the drawn actions."""
+    from overcooked_ai_b200.selfplay import SelfPlayRollout
+
+    n = 300
+    torch.manual_seed(1)
+    env = BatchedOvercookedEnv(layout, n, horizon=25, auto_reset=True)
+    sp = SelfPlayRollout(env, use_graph=False, seed=2)
+    assert (sp.fused_first_layer, sp.fused_wide, sp.fused_tail) == flags and sp.native_glue
+    ref_state = _np(env.state).copy()
+    for t in range(30):
+        sp.run(1)
+        a = _np(sp.actions)
+        assert a.min() >= 0 and a.max() <= 5
+        cpu.step(env._tab_host, env._starts_host, ref_state, a, horizon=25, flags=1)
+        assert np.array_equal(_np(env.state), ref_state), t
+    assert len(np.unique(_np(sp.actions))) > 3
+
+
 def _check_draw(actions, scores, seed, step, n_actions=6):
     """actions == the ovc_sample_actions definition applied to ``scores`` (numpy restatement; near-ties exempt)."""
     rows = np.arange(len(scores), dtype=np.uint64)
